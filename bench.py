@@ -1,0 +1,442 @@
+#!/usr/bin/env python
+"""bench.py -- env-steps/sec of the batched manipulation simulator (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--num-envs E] [--impl reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+One "step" = one env.step() of EVERY env of the job (E envs per GPU, weak scaling).
+Workload (BASELINE.json configs[1] scaled to the metric's 1M-env end so the state is larger than
+L2): experiments/config_default.json -- dense reward, max_episode_steps 200,
+CurriculumScheduler(easy -> hard, threshold 0.3, window 15, min episodes 20, 5 steps) fed from
+the device counters, random policy actions U(-1,1) resident in HBM, auto-reset (respawn).
+
+Printed JSON (one line, rank 0):
+  value      whole-job env-steps/s, inputs resident in HBM (API mode: dexsim_step per step)
+  e2e        same metric through env.step_host(): pinned HOST actions in, obs/reward/flags out,
+             H2D + D2H copies inside the timed region
+  roofline   step kernel: algorithmic 410 B/env-step / CUDA-event kernel time
+  cpu_baseline   the reference's own Python loop on this box's host cores (bounded sample)
+  fused_rollout, sweep   extra measurements (in-kernel policy; other env counts)
+`--impl reference` times the UNMODIFIED reference (byte-compiled in oracle/_ref) with one
+process per host core; it never touches CUDA.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+ALGO_BYTES_PER_ENV_STEP = 410          # SURVEY.md 8d / BASELINE.md section 4 (API mode)
+METRIC = "env_steps_per_sec"
+UNIT = "env-steps/s"
+# experiments/config_default.json:16-23 and :3-12
+SCHED = dict(success_rate_threshold=0.3, window_size=15, min_episodes_before_progression=20, progression_steps=5)
+MAX_EPISODE_STEPS = 200
+SEED = 42
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=1000)
+    ap.add_argument("--warmup", type=int, default=100)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--num-envs", type=int, default=1 << 20, help="envs per GPU")
+    ap.add_argument("--poll-every", type=int, default=100, help="curriculum driver poll period (steps)")
+    ap.add_argument("--e2e-steps", type=int, default=30)
+    ap.add_argument("--no-sweep", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-seconds", type=float, default=12.0, help="target CPU time of the cpu_baseline sample")
+    ap.add_argument("--ref-steps-per-proc", type=int, default=2000, help="reference arm: env-steps per process per bench step")
+    ap.add_argument("--ref-procs", type=int, default=0, help="reference arm: processes (0 = all host cores)")
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------------------------ reference arm
+def _ref_worker(conn, steps_per_call, seed):
+    """One process = one reference env driven exactly like config 2 on the CPU: dense reward,
+    RandomPolicy, CurriculumScheduler(easy -> hard) updated per episode, fresh spawn per episode."""
+    try:
+        from oracle import ref_harness
+        R = ref_harness.load()
+        import numpy as np
+        np.random.seed(seed)
+        sched = R.CurriculumScheduler(R.CurriculumConfig.easy(), R.CurriculumConfig.hard(), **SCHED)
+        env = R.DexterousManipulationEnv(curriculum_config=sched.get_current_config(), reward_type="dense",
+                                         max_episode_steps=MAX_EPISODE_STEPS)
+        policy = R.policies.RandomPolicy(env.action_space)
+        obs, _ = env.reset(seed=seed)
+        ep_steps = 0
+        conn.send(("ready", ref_harness.kind()))
+        while True:
+            msg = conn.recv()
+            if msg == "stop":
+                break
+            t0 = time.perf_counter()
+            for _ in range(steps_per_call):
+                obs, r, term, trunc, info = env.step(policy.select_action(obs))
+                ep_steps += 1
+                if term or trunc or ep_steps >= MAX_EPISODE_STEPS:
+                    if sched.update(bool(term), ep_steps):
+                        env.curriculum_config = sched.get_current_config()
+                    env.object_position = None          # fresh-env semantics: respawn the object
+                    obs, _ = env.reset()
+                    ep_steps = 0
+            conn.send(("done", time.perf_counter() - t0))
+    except Exception as exc:       # pragma: no cover - reported to the parent
+        conn.send(("error", repr(exc)))
+
+
+def _oracle_port_worker(conn, steps_per_call, seed):
+    """Fallback when the byte-compiled reference is absent: the C restatement (oracle port)."""
+    try:
+        import numpy as np
+        from oracle import oracle
+        n = 256
+        ob = oracle.OracleBatch(n, dense=True, max_episode_steps=MAX_EPISODE_STEPS)
+        grp = oracle.make_group(object_size=0.03, object_mass=0.2, friction_coefficient=0.3)
+        rng = np.random.default_rng(seed)
+        ob.reset_predrawn(rng.uniform(-0.1, 0.1, (n, 15)).astype(np.float32), 0.03, 0.2, 0.3,
+                          np.stack([rng.uniform(-0.1, 0.1, n), rng.uniform(-0.1, 0.1, n), rng.uniform(0.05, 0.2, n)], 1).astype(np.float32))
+        conn.send(("ready", "port"))
+        while True:
+            msg = conn.recv()
+            if msg == "stop":
+                break
+            t0 = time.perf_counter()
+            ob.rollout(grp, max(steps_per_call // n, 1), seed, policy_kind=1, respawn=True, loop_max_steps=MAX_EPISODE_STEPS)
+            conn.send(("done", time.perf_counter() - t0))
+    except Exception as exc:       # pragma: no cover
+        conn.send(("error", repr(exc)))
+
+
+def run_reference(args, n_gpus):
+    """--impl reference: all host cores, each bench step = every process advances its env by
+    `ref_steps_per_proc` env-steps.  Never imports torch.cuda."""
+    import multiprocessing as mp
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    from oracle import ref_harness
+    kind = "reference" if ref_harness.available() else "port"
+    ctx = mp.get_context("fork")
+    procs = args.ref_procs or (os.cpu_count() or 1)
+    spc = args.ref_steps_per_proc
+    target = _ref_worker if kind == "reference" else _oracle_port_worker
+    workers = []
+    for k in range(procs):
+        a, b = ctx.Pipe()
+        p = ctx.Process(target=target, args=(b, spc, SEED + k), daemon=True)
+        p.start()
+        workers.append((p, a))
+    form = None
+    for _, c in workers:
+        tag, val = c.recv()
+        if tag != "ready":
+            print(json.dumps({"impl": "reference", "unavailable": f"worker failed: {val}"}))
+            return 0
+        form = val
+
+    def one_step():
+        for _, c in workers:
+            c.send("go")
+        for _, c in workers:
+            tag, val = c.recv()
+            if tag != "done":
+                raise RuntimeError(val)
+
+    for _ in range(args.warmup):
+        one_step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        one_step()
+    dt = time.perf_counter() - t0
+    for p, c in workers:
+        c.send("stop")
+    for p, _ in workers:
+        p.join(timeout=5)
+    steps_per_bench_step = procs * (spc if kind == "reference" else max(spc // 256, 1) * 256)
+    value = steps_per_bench_step * args.steps / dt
+    sample = (f"{procs} processes x 1 env x {spc} env-steps per bench step, {args.steps} steps; config_default dense + "
+              f"CurriculumScheduler + RandomPolicy; reference form: {form}")
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "impl": "reference", "n_gpus": n_gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * dt / max(args.steps, 1), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32+f64", "data": "synthetic",
+        "config": {"workload": "config_default.json dense + curriculum_scheduler, random_policy; reference Python loop, "
+                               "one env per host process", "envs": procs},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": procs, "kind": kind, "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+    return 0
+
+
+# ------------------------------------------------------------------------------------ clocks
+class ClockSampler:
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.rows = []
+        self.proc = None
+        self.thread = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            self.proc = None
+            return
+        self.thread = threading.Thread(target=self._read, daemon=True)
+        self.thread.start()
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+        for r in self.rows:
+            parts = [x.strip() for x in r.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                sm.append(float(parts[0])); mx = float(parts[1])
+            except ValueError:
+                continue
+            for name, flag in zip(names, parts[3:7]):
+                if flag.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------------------------ b200 arm
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+    import dexterous_rl_manipulation_b200 as dx
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    n_gpus = max(args.gpus, world)
+
+    cpu_base = None
+    if rank == 0 and n_gpus == 1 and not args.no_cpu_baseline:
+        cpu_base = measure_cpu_baseline(args)      # before CUDA is initialised (workers fork)
+
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    E = args.num_envs
+    CC = dx.CurriculumConfig
+
+    def make_env(n, seed=SEED, gid0=0):
+        env = dx.BatchedManipulationEnv(n, dev, max_episode_steps=MAX_EPISODE_STEPS, reward_type="dense",
+                                        curriculum_config=CC.easy(), auto_reset=True, respawn=True,
+                                        loop_max_steps=MAX_EPISODE_STEPS, track_episodes=True, seed=seed, env_gid0=gid0)
+        sched = dx.CurriculumScheduler(CC.easy(), CC.hard(), **SCHED)
+        drv = dx.BatchedCurriculumDriver(env, sched)
+        env.reset(seed=seed)
+        return env, sched, drv
+
+    def action_pool(n, k=4):
+        g = torch.Generator(device=dev).manual_seed(SEED + rank)
+        return [torch.rand(n, 15, device=dev, generator=g) * 2 - 1 for _ in range(k)]
+
+    def timed_api(env, drv, pool, steps, warmup, poll_every):
+        for t in range(warmup):
+            env.step(pool[t % len(pool)])
+            if poll_every and (t + 1) % poll_every == 0:
+                drv.poll()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for t in range(steps):
+            env.step(pool[t % len(pool)])
+            if poll_every and (t + 1) % poll_every == 0:
+                drv.poll()
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            tms = torch.tensor([ms], device=dev, dtype=torch.float64)
+            dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+            ms = float(tms.item())
+        return ms
+
+    # ---- main timed region: API mode, device-resident actions -------------------------------------
+    env, sched, drv = make_env(E, gid0=rank * E)
+    pool = action_pool(E)
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    ms = timed_api(env, drv, pool, args.steps, args.warmup, args.poll_every)
+    clocks = sampler.stop() if sampler else None
+    dx.distributed.allreduce_counters(env.counters, env.ret_sums)
+    value = E * n_gpus * args.steps / (ms * 1e-3)
+    launches = args.steps
+
+    # ---- kernel-only roofline: the step kernel alone, CUDA events on its stream --------------------
+    for t in range(5):
+        env.step(pool[t % 4])
+    torch.cuda.synchronize(dev)
+    reps = 40
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for t in range(reps):
+        env.step(pool[t % 4])
+    e1.record()
+    torch.cuda.synchronize(dev)
+    k_ms = e0.elapsed_time(e1) / reps
+    peaks = {}
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
+            peaks = json.load(fh)
+    except OSError:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    achieved = ALGO_BYTES_PER_ENV_STEP * E / (k_ms * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "kernel": "dexsim::step_kernel<dense, AoS action, extras>", "achieved": achieved,
+                "peak": peak, "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s",
+                "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                "algorithmic_bytes_per_env_step": ALGO_BYTES_PER_ENV_STEP, "envs_per_launch": E,
+                "kernel_ms": k_ms}
+
+    # ---- end to end: pinned host actions in, obs / reward / flags out ------------------------------
+    h_pool = [torch.rand(E, 15).mul_(2).sub_(1).pin_memory() for _ in range(2)]
+    for t in range(3):
+        env.step_host(h_pool[t % 2])
+    barrier()
+    t0 = time.perf_counter()
+    for t in range(args.e2e_steps):
+        env.step_host(h_pool[t % 2])
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    if world > 1:
+        tt = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        e2e_s = float(tt.item())
+    e2e = {"value": E * n_gpus * args.e2e_steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": E * 15 * 4,
+           "d2h_bytes_per_step": env.ld * 45 * 4 + E * (4 + 3), "steps": args.e2e_steps,
+           "api": "BatchedManipulationEnv.step_host -> dexsim_step_host"}
+    launches += args.e2e_steps
+
+    # ---- fused rollout (policy in-kernel, K steps per launch) ---------------------------------------
+    fused = None
+    if rank == 0 or world > 1:
+        env2 = dx.BatchedManipulationEnv(E, dev, max_episode_steps=MAX_EPISODE_STEPS, reward_type="dense",
+                                         curriculum_config=CC.hard(), track_episodes=True, seed=SEED, env_gid0=rank * E)
+        env2.reset(seed=SEED)
+        chunk = 50
+        env2.rollout(chunk, policy="random")
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        nl = 4
+        for _ in range(nl):
+            env2.rollout(chunk, policy="random")
+        e1.record()
+        barrier()
+        f_ms = e0.elapsed_time(e1)
+        fused = {"value": E * n_gpus * chunk * nl / (f_ms * 1e-3), "unit": UNIT, "steps_per_launch": chunk,
+                 "launches": nl, "policy": "random (Philox, in-kernel)", "note": "state in registers across the launch"}
+        del env2
+
+    # ---- sweep over env counts (API mode, no curriculum polling) -------------------------------------
+    sweep = []
+    if not args.no_sweep and world == 1:
+        for n in (4096, 65536, 131072):
+            if n == E:
+                continue
+            env_s, _, drv_s = make_env(n)
+            pool_s = action_pool(n)
+            s_ms = timed_api(env_s, drv_s, pool_s, 300, 30, 0)
+            v = n * 300 / (s_ms * 1e-3)
+            sweep.append({"envs": n, "value": v, "ms_per_step": s_ms / 300,
+                          "roofline_frac": v * ALGO_BYTES_PER_ENV_STEP / 1e9 / peak,
+                          "note": "state is L2-resident at this size; launch/latency-bound"})
+            del env_s, pool_s
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": n_gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32+f64", "data": "synthetic",
+            "config": {
+                "workload": f"config_default.json dense + curriculum_scheduler(easy->hard), random_policy actions resident in HBM, "
+                            f"{E} envs per GPU, auto-reset respawn, max_episode_steps 200",
+                "envs_per_gpu": E, "envs_total": E * n_gpus, "l2": "state + actions per step exceed the 126 MB L2 (no flush needed)"
+                if E * ALGO_BYTES_PER_ENV_STEP > 130e6 else "state fits in L2 at this size",
+                "curriculum": {"difficulty": sched.current_difficulty_level, "progressions": drv.progressions,
+                               "poll_every": args.poll_every},
+                "parallelism": f"env-sharded dp{n_gpus}, no data-path collective",
+            },
+            "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu_base,
+            "fused_rollout": fused, "sweep": sweep, "clocks": clocks,
+            "episodes": int(env.counters[:, 0].sum().item()),
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+def measure_cpu_baseline(args):
+    """cpu_baseline leg: the reference arm on a bounded sample, in a subprocess (never shares the
+    CUDA context).  Sized from a 1-step probe to take about --cpu-seconds."""
+    cmd = [sys.executable, os.path.abspath(__file__), "--impl", "reference", "--ref-steps-per-proc", "500"]
+    try:
+        probe = subprocess.run(cmd + ["--steps", "1", "--warmup", "1"], capture_output=True, text=True, timeout=180)
+        line = json.loads(probe.stdout.strip().splitlines()[-1])
+        if "unavailable" in line:
+            return {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "reference", "sample": line["unavailable"]}
+        per_step = line["ms_per_step"] * 1e-3
+        steps = max(2, min(200, int(args.cpu_seconds / max(per_step, 1e-3))))
+        full = subprocess.run(cmd + ["--steps", str(steps), "--warmup", "1"], capture_output=True, text=True, timeout=600)
+        line = json.loads(full.stdout.strip().splitlines()[-1])
+        return line["cpu_baseline"]
+    except Exception as exc:       # report, never fake a number
+        return {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "reference", "sample": f"failed: {exc!r}"}
+
+
+def main():
+    args = parse_args()
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        return run_reference(args, max(args.gpus, world))
+    return run_b200(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -1,0 +1,354 @@
+// dexsim_core.cuh -- per-env arithmetic of the batched manipulation simulator (sm_100a).
+//
+// One env's state lives in registers (EnvRegs); the kernels in dexsim_kernels.cu move it
+// between HBM and registers.  Everything here mirrors, operation for operation and rounding
+// for rounding, what the reference computes under numpy 2.3.5 (NEP 50):
+//   envs/manipulation_env.py:124-182 (reset), :184-252 (step), :285-310 (contacts),
+//   rewards/reward_shaping.py:50-187 (dense), :205-242 (sparse),
+//   evaluation/metrics.py:39-96 and evaluation/failure_taxonomy.py:156-239 (failure labels).
+// Joints and velocities are float32; the object position, the fingertip distances and the
+// contact test are float64 because the reference's are.  Every product
+// and sum the reference rounds separately is written with __f*_rn / __d*_rn intrinsics, which
+// nvcc never contracts into FMA (the file is also compiled with -fmad=false).
+#pragma once
+
+#include <cstdint>
+#include <cuda_runtime.h>
+
+#include "../../include/dexsim.h"
+
+namespace dexsim {
+
+constexpr int NJ = DEXSIM_NJ;
+constexpr int NF = DEXSIM_NF;
+constexpr int NOBS = DEXSIM_OBS;
+
+#if defined(__CUDACC__)
+#define DEXSIM_HD __host__ __device__ __forceinline__
+#define DEXSIM_D __device__ __forceinline__
+#else
+#define DEXSIM_HD inline
+#define DEXSIM_D inline
+#endif
+
+struct EnvRegs {
+    float    jp[NJ];
+    float    jv[NJ];
+    double   op[3];
+    float    ov[3];
+    double   thr;     // object_size * 1.5
+    float    damp;    // float32(1.0 - friction * 0.1 * 0.01)
+    int      sc;      // step_count; sc == 0 <=> object_position is still the float32 array of reset()
+    unsigned cmask;   // bit f: finger f in contact after the last contact update
+};
+
+struct StepResult {
+    double total, distance, contact, closure, stability;
+    int    n_c;
+    bool   terminated, truncated;
+};
+
+// np.clip == minimum(maximum(x, lo), hi): NaN propagates (fminf/fmaxf would swallow it)
+DEXSIM_D float clip_f32(float x, float lo, float hi) {
+    const float y = (x < lo) ? lo : x;
+    return (y > hi) ? hi : y;
+}
+DEXSIM_D double clip_f64(double x, double lo, double hi) {
+    const double y = (x < lo) ? lo : x;
+    return (y > hi) ? hi : y;
+}
+
+// envs/manipulation_env.py:285-310.  Returns the contact mask, count and min distance.
+DEXSIM_D unsigned update_contacts(const EnvRegs& e, int& n_c, double& dmin) {
+    unsigned mask = 0u;
+    n_c = 0;
+    dmin = 0.0;
+#pragma unroll
+    for (int f = 0; f < NF; ++f) {
+        // :301-302 float32 sequential sum of 3 joints, "* 0.1" stays float32, then widened (:300)
+        const float s = __fadd_rn(__fadd_rn(e.jp[3 * f], e.jp[3 * f + 1]), e.jp[3 * f + 2]);
+        const double tip = (double)__fmul_rn(s, 0.1f);
+        // :309 np.linalg.norm(axis=1) in float64, left to right
+        const double dx = __dsub_rn(tip, e.op[0]);
+        const double dy = __dsub_rn(tip, e.op[1]);
+        const double dz = __dsub_rn(tip, e.op[2]);
+        const double sq = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
+        const double d = __dsqrt_rn(sq);
+        const bool c = d < e.thr;                                  // :310
+        mask |= (c ? 1u : 0u) << f;
+        n_c += c ? 1 : 0;
+        dmin = (f == 0) ? d : ((d < dmin) ? d : dmin);             // np.min, reward_shaping.py:112
+    }
+    return mask;
+}
+
+// envs/manipulation_env.py:124-182 with the draws supplied (reference order: joints, size,
+// mass, friction, x, y, z).  keep_pos: reused env object, position re-cast to float32 (:160-161).
+DEXSIM_D void env_reset(EnvRegs& e, const float* jp0, double size, double friction,
+                        const float* pos, bool keep_pos) {
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) { e.jp[j] = jp0[j]; e.jv[j] = 0.0f; }
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        e.op[i] = keep_pos ? (double)(float)e.op[i] : (double)pos[i];
+        e.ov[i] = 0.0f;
+    }
+    e.thr = __dmul_rn(size, 1.5);                                            // :293
+    e.damp = (float)__dsub_rn(1.0, __dmul_rn(__dmul_rn(friction, 0.1), 0.01)); // :215
+    e.sc = 0;
+    int n_c; double dmin;
+    e.cmask = update_contacts(e, n_c, dmin);                                 // :176
+}
+
+// envs/manipulation_env.py:184-252 + rewards/reward_shaping.py (compute)
+template <bool DENSE>
+DEXSIM_D void env_step(EnvRegs& e, const float* a, const DexsimParams& p, StepResult& r) {
+    // :199-207
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) {
+        const float aj = clip_f32(a[j], -1.0f, 1.0f);
+        e.jv[j] = __fadd_rn(__fmul_rn(0.9f, e.jv[j]), __fmul_rn(0.1f, aj));
+        e.jp[j] = clip_f32(__fadd_rn(e.jp[j], __fmul_rn(e.jv[j], 0.01f)), -1.0f, 1.0f);
+    }
+    // :211-219  (gravity is a float64 array: the += happens in float64, rounded back to float32)
+    constexpr double kGravZ = -9.81 * 0.01;
+    e.ov[0] = (float)__dadd_rn((double)__fmul_rn(e.ov[0], e.damp), 0.0);
+    e.ov[1] = (float)__dadd_rn((double)__fmul_rn(e.ov[1], e.damp), 0.0);
+    e.ov[2] = (float)__dadd_rn((double)__fmul_rn(e.ov[2], e.damp), kGravZ);
+    // :222  float32 in-place add on the first step after reset, float64 afterwards
+    const bool first = (e.sc == 0);
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        const float dq = __fmul_rn(e.ov[i], 0.01f);
+        const double p32 = (double)__fadd_rn((float)e.op[i], dq);
+        const double p64 = __dadd_rn(e.op[i], (double)dq);
+        e.op[i] = first ? p32 : p64;
+    }
+    // :225-235
+    const double lo[3] = {-0.2, -0.2, 0.0};
+    const double hi[3] = {0.2, 0.2, 0.3};
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        e.op[i] = clip_f64(e.op[i], lo[i], hi[i]);
+        if ((e.op[i] <= lo[i] && e.ov[i] < 0.0f) || (e.op[i] >= hi[i] && e.ov[i] > 0.0f)) e.ov[i] = 0.0f;
+    }
+    // :238
+    double dmin;
+    const unsigned prev = e.cmask;
+    e.cmask = update_contacts(e, r.n_c, dmin);
+    // :241
+    if (DENSE) {
+        r.distance = exp(__dmul_rn(-5.0, dmin));                              // reward_shaping.py:116
+        r.contact = __ddiv_rn((double)r.n_c, 5.0);                            // :134
+        float msum = -0.0f;                                                   // :149-162
+#pragma unroll
+        for (int f = 0; f < NF; ++f) {
+            float s = -0.0f;
+#pragma unroll
+            for (int j = 0; j < 3; ++j) {
+                const float v = e.jp[3 * f + j];
+                s = (v < 0.0f) ? __fadd_rn(s, v) : s;
+            }
+            msum = __fadd_rn(msum, -s);
+        }
+        const float avg = __fdiv_rn(msum, 5.0f);
+        r.closure = (double)clip_f32(__fdiv_rn(avg, 5.0f), 0.0f, 1.0f);
+        if (first) {                                                          // :172-175
+            r.stability = 0.0;
+        } else {                                                              // :178-183
+            const float changes = (float)__popc(prev ^ e.cmask);
+            r.stability = (double)clip_f32(__fsub_rn(1.0f, __fdiv_rn(changes, 5.0f)), 0.0f, 1.0f);
+        }
+        r.total = __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(p.w_distance, r.distance),
+                                                __dmul_rn(p.w_contact, r.contact)),
+                                      __dmul_rn(p.w_closure, r.closure)),
+                            __dmul_rn(p.w_stability, r.stability));           // :86-91
+    } else {
+        r.total = (r.n_c >= 3) ? 1.0 : -0.01;                                 // :231-234
+        r.distance = r.contact = r.closure = r.stability = 0.0;
+    }
+    r.terminated = r.n_c >= p.success_threshold;                              // :244
+    r.truncated = e.sc >= p.max_episode_steps;                                // :245
+    e.sc += 1;                                                                // :247
+}
+
+// ---- counter-based RNG: Philox4x32-10 (Salmon et al. SC'11), DESIGN.md "RNG" -----------------
+struct U4 { uint32_t x, y, z, w; };
+
+DEXSIM_D U4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1) {
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+        const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+        const uint32_t n0 = hi1 ^ c1 ^ k0, n2 = hi0 ^ c3 ^ k1;
+        c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    return U4{c0, c1, c2, c3};
+}
+
+enum : uint32_t { STREAM_RESET = 0, STREAM_POLICY = 1, STREAM_DYN = 2, STREAM_OBS = 3, STREAM_LEARNER = 4 };
+
+DEXSIM_D U4 rng_block(uint64_t seed, uint32_t gid, uint32_t episode, uint32_t step, uint32_t stream,
+                      uint32_t block) {
+    return philox4x32_10(gid, episode, step, stream | (block << 8), (uint32_t)seed, (uint32_t)(seed >> 32));
+}
+
+DEXSIM_D float u24(uint32_t x) { return (float)(x >> 8) * 5.9604644775390625e-08f; }
+DEXSIM_D double u53(uint32_t a, uint32_t b) {
+    return __ddiv_rn(__dadd_rn(__dmul_rn((double)(a >> 5), 67108864.0), (double)(b >> 6)), 9007199254740992.0);
+}
+DEXSIM_D double lerp_rn(double lo, double hi, double u) {   // low + (high - low) * u, as Generator.uniform
+    return __dadd_rn(lo, __dmul_rn(__dsub_rn(hi, lo), u));
+}
+
+// Philox stand-in for the PCG64 draws of envs/manipulation_env.py:143-161 + experiments/config.py:44-113
+DEXSIM_D void reset_draws(uint64_t seed, uint32_t gid, uint32_t episode, const DexsimGroup& g, float* jp0,
+                          double& size, double& mass, double& friction, float* pos) {
+    uint32_t w[28];
+#pragma unroll
+    for (uint32_t b = 0; b < 7; ++b) {
+        const U4 o = rng_block(seed, gid, episode, 0u, STREAM_RESET, b);
+        w[4 * b] = o.x; w[4 * b + 1] = o.y; w[4 * b + 2] = o.z; w[4 * b + 3] = o.w;
+    }
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) jp0[j] = (float)__dadd_rn(-0.1, __dmul_rn(0.2, (double)u24(w[j])));
+    const double d0 = u53(w[16], w[17]), d1 = u53(w[18], w[19]), d2 = u53(w[20], w[21]);
+    size = g.size_ranged ? lerp_rn(g.size_lo, g.size_hi, d0) : g.size;
+    mass = g.mass_ranged ? lerp_rn(g.mass_lo, g.mass_hi, d1) : g.mass;
+    friction = g.fric_ranged ? lerp_rn(g.fric_lo, g.fric_hi, d2) : g.friction;
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+        pos[i] = (float)lerp_rn(g.spawn_lo[i], g.spawn_hi[i], u53(w[22 + 2 * i], w[23 + 2 * i]));
+}
+
+// policies/random_policy.py:40 and policies/heuristic_policy.py:55-62 on Philox bits
+DEXSIM_D void policy_action(uint64_t seed, uint32_t gid, uint32_t episode, uint32_t step, int kind, float* a) {
+    uint32_t w[16];
+#pragma unroll
+    for (uint32_t b = 0; b < 4; ++b) {
+        const U4 o = rng_block(seed, gid, episode, step, STREAM_POLICY, b);
+        w[4 * b] = o.x; w[4 * b + 1] = o.y; w[4 * b + 2] = o.z; w[4 * b + 3] = o.w;
+    }
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) {
+        const float u = __fsub_rn(__fmul_rn(2.0f, u24(w[j])), 1.0f);
+        a[j] = (kind == DEXSIM_POLICY_HEURISTIC)
+                   ? clip_f32(__fadd_rn(-0.5f, __fmul_rn(u, 0.1f)), -1.0f, 1.0f) : u;
+    }
+}
+
+// float32 N(0,1) pairs by Box-Muller on Philox words (device-only; parity runs pre-draw noise
+// with dexsim_fill_normal and hand the same tensors to the oracle).
+DEXSIM_D void normal_pair(uint32_t wa, uint32_t wb, float& z0, float& z1) {
+    const float u1 = (float)((wa >> 8) + 1u) * 5.9604644775390625e-08f;   // (0, 1]
+    const float u2 = u24(wb);
+    const float rad = sqrtf(-2.0f * __logf(u1));
+    float s, c;
+    sincospif(2.0f * u2, &s, &c);
+    z0 = rad * c; z1 = rad * s;
+}
+template <int ROWS>
+DEXSIM_D void normal_rows(uint64_t seed, uint32_t gid, uint32_t episode, uint32_t step, uint32_t stream,
+                          float sigma, float* out) {
+    constexpr int NBLK = (ROWS + 3) / 4;
+#pragma unroll
+    for (int b = 0; b < NBLK; ++b) {
+        const U4 o = rng_block(seed, gid, episode, step, stream, (uint32_t)b);
+        float z[4];
+        normal_pair(o.x, o.y, z[0], z[1]);
+        normal_pair(o.z, o.w, z[2], z[3]);
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+            if (4 * b + k < ROWS) out[4 * b + k] = sigma * z[k];
+    }
+}
+
+// ---- episode history summary + failure labels --------------------------------------------------
+// Packed per-env summary of the per-step contact COUNTS an Evaluator would have collected
+// (evaluation/evaluator.py:148-150): enough to run both classifiers without the history.
+//   w0: [15:0] sum of counts   [20:16] sum of the first five   [23:21] max count
+//   w1: [16:0] sum of squares  [31:17] last five counts, 3 bits each (newest in the low bits)
+struct EpStats { uint32_t w0, w1; };
+
+DEXSIM_HD void epstats_push(EpStats& s, int hist_len_before, int n_c) {
+    uint32_t sum = s.w0 & 0xFFFFu, first5 = (s.w0 >> 16) & 0x1Fu, mx = (s.w0 >> 21) & 0x7u;
+    uint32_t sq = s.w1 & 0x1FFFFu, ring = s.w1 >> 17;
+    sum += (uint32_t)n_c; sq += (uint32_t)(n_c * n_c);
+    if (hist_len_before < 5) first5 += (uint32_t)n_c;
+    mx = ((uint32_t)n_c > mx) ? (uint32_t)n_c : mx;
+    ring = ((ring << 3) | (uint32_t)n_c) & 0x7FFFu;
+    s.w0 = (sum & 0xFFFFu) | (first5 << 16) | (mx << 21);
+    s.w1 = (sq & 0x1FFFFu) | (ring << 17);
+}
+
+DEXSIM_HD void epstats_unpack(const EpStats& s, int& sum, int& sq, int& first5, int& last5, int& mx) {
+    sum = (int)(s.w0 & 0xFFFFu); first5 = (int)((s.w0 >> 16) & 0x1Fu); mx = (int)((s.w0 >> 21) & 0x7u);
+    sq = (int)(s.w1 & 0x1FFFFu);
+    const uint32_t ring = s.w1 >> 17;
+    last5 = (int)((ring & 7u) + ((ring >> 3) & 7u) + ((ring >> 6) & 7u) + ((ring >> 9) & 7u) + ((ring >> 12) & 7u));
+}
+
+// Both classifiers from the summary.  var = (n*Q - S^2)/n^2 is compared as integers; an exact
+// tie with a threshold (where numpy's float64 pairwise sum may land on either side) sets
+// var_tie and is resolved as in exact arithmetic.  The slippage trend reproduces
+// np.mean(last5) - np.mean(first5) with two IEEE divisions and one subtraction.
+DEXSIM_HD void classify_summary(const DexsimEpisodeSummary& e, int max_steps, int thr,
+                                int& label_a, int& label_b, int& var_tie) {
+    var_tie = 0;
+    label_a = label_b = DEXSIM_LABEL_NONE;
+    if (e.success) return;                                        // metrics.py:53-55, failure_taxonomy.py:171-173
+    const long long n = e.hist_len;
+    const long long vnum = n * (long long)e.sum_sq_counts - (long long)e.sum_counts * e.sum_counts;  // var * n^2
+    const bool var_gt2 = vnum > 2 * n * n, var_lt1 = vnum < n * n;
+    const bool tie2 = (n > 5) && (vnum == 2 * n * n), tie1 = (n > 1) && (vnum == n * n);
+#if defined(__CUDA_ARCH__)
+    const double trend = __dsub_rn(__ddiv_rn((double)e.last5_sum, 5.0), __ddiv_rn((double)e.first5_sum, 5.0));
+#else
+    const double trend = (double)e.last5_sum / 5.0 - (double)e.first5_sum / 5.0;
+#endif
+    // EvaluationMetrics.classify_failure, evaluation/metrics.py:63-96
+    {
+        int lab;
+        if (e.episode_steps >= max_steps) lab = DEXSIM_LABEL_TIMEOUT;
+        else if (e.final_contacts == 0) lab = DEXSIM_LABEL_DROPPED;
+        else {
+            lab = -1;
+            if (n > 5) {
+                if (var_gt2) lab = DEXSIM_LABEL_UNSTABLE;
+                else {
+                    if (tie2) var_tie = 1;
+                    if (n > 10 && trend < -1.0) lab = DEXSIM_LABEL_SLIPPAGE;
+                }
+            }
+            if (lab < 0) lab = (e.num_contacts > 0 && e.num_contacts < thr) ? DEXSIM_LABEL_MISALIGNED
+                                                                            : DEXSIM_LABEL_INSUFFICIENT;
+        }
+        label_a = lab;
+    }
+    // FailureClassifier.classify, evaluation/failure_taxonomy.py:183-239
+    {
+        const int max_c = (n > 0) ? e.max_count : e.num_contacts;
+        const bool has_var = n > 1;                                // :187 (variance is 0.0 otherwise)
+        int lab;
+        if (e.episode_steps >= max_steps) lab = DEXSIM_LABEL_TIMEOUT;
+        else if (e.final_contacts == 0 && max_c > 0) lab = DEXSIM_LABEL_DROPPED;
+        else {
+            lab = -1;
+            if (n > 5) {
+                if (n > 10 && trend < -1.0 && max_c >= 1) lab = DEXSIM_LABEL_SLIPPAGE;
+                else if (var_gt2) lab = DEXSIM_LABEL_UNSTABLE;
+                else if (tie2) var_tie = 1;
+            }
+            if (lab < 0 && e.num_contacts >= 1 && e.num_contacts <= 2) {
+                const bool lt1 = has_var ? var_lt1 : true;
+                if (has_var && tie1) var_tie = 1;
+                if (lt1) lab = DEXSIM_LABEL_MISALIGNED;
+            }
+            if (lab < 0) lab = DEXSIM_LABEL_INSUFFICIENT;
+        }
+        label_b = lab;
+    }
+}
+
+}  // namespace dexsim

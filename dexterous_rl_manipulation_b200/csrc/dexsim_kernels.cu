@@ -1,0 +1,709 @@
+// dexsim_kernels.cu -- sm_100a kernels + C ABI (include/dexsim.h) of the batched simulator.
+//
+// Kernels
+//   step_kernel      one env-step for every env: SoA state in HBM -> registers -> HBM.  Streaming,
+//                    HBM-bound (DESIGN.md "Roofline"): every field is read and written at most once,
+//                    coalesced 128-byte rows per warp, unchanged fields are not written back.
+//   rollout_kernel   k env-steps per env in one launch with the policy drawn in-kernel (Philox),
+//                    state in registers for the whole launch, episodes auto-reset, per-group
+//                    counters aggregated in shared memory and flushed with one atomic per counter.
+//   reset_*_kernel   episode (re)initialisation from pre-drawn or Philox draws.
+// No CPU fallback exists: every entry point launches CUDA work or returns an error code.
+#include <cstdio>
+#include <cstring>
+
+#include "dexsim_core.cuh"
+
+namespace dexsim {
+
+constexpr int STEP_THREADS = 256;
+constexpr int SMEM_GROUPS_MAX = 64;     // group table + block counters are staged in smem up to this many groups
+
+// ---- state <-> registers -----------------------------------------------------------------------
+struct Hot {            // what a step needs beyond EnvRegs to decide which rows changed
+    double op_old[3];
+    float  ov_old[3];
+    unsigned cmask_old;
+};
+
+__device__ __forceinline__ void load_env(const DexsimState& st, int64_t i, EnvRegs& e) {
+    const int64_t ld = st.ld;
+    const float* __restrict__ obs = st.obs;
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) e.jp[j] = obs[(DEXSIM_ROW_JP + j) * ld + i];
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) e.jv[j] = obs[(DEXSIM_ROW_JV + j) * ld + i];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) e.ov[k] = obs[(DEXSIM_ROW_OV + k) * ld + i];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) e.op[k] = st.op64[k * ld + i];
+    e.thr = st.thr[i];
+    e.damp = st.damp[i];
+    e.sc = st.step_count[i];
+    e.cmask = st.cmask[i];
+}
+
+// Full write-back (reset paths): every row including the constant quaternion.
+__device__ __forceinline__ void store_env_full(const DexsimState& st, int64_t i, const EnvRegs& e) {
+    const int64_t ld = st.ld;
+    float* __restrict__ obs = st.obs;
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) obs[(DEXSIM_ROW_JP + j) * ld + i] = e.jp[j];
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) obs[(DEXSIM_ROW_JV + j) * ld + i] = e.jv[j];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        obs[(DEXSIM_ROW_OP + k) * ld + i] = (float)e.op[k];
+        obs[(DEXSIM_ROW_OV + k) * ld + i] = e.ov[k];
+        st.op64[k * ld + i] = e.op[k];
+    }
+    obs[(DEXSIM_ROW_QUAT + 0) * ld + i] = 1.0f;          // envs/manipulation_env.py:164
+    obs[(DEXSIM_ROW_QUAT + 1) * ld + i] = 0.0f;
+    obs[(DEXSIM_ROW_QUAT + 2) * ld + i] = 0.0f;
+    obs[(DEXSIM_ROW_QUAT + 3) * ld + i] = 0.0f;
+#pragma unroll
+    for (int f = 0; f < NF; ++f) obs[(DEXSIM_ROW_CONTACT + f) * ld + i] = ((e.cmask >> f) & 1u) ? 1.0f : 0.0f;
+    st.thr[i] = e.thr;
+    st.damp[i] = e.damp;
+    st.step_count[i] = e.sc;
+    st.cmask[i] = (uint8_t)e.cmask;
+}
+
+// Step write-back: joints always; object rows, contact rows and the mask only when they changed
+// (x, y never move after the first step; z rests at 0 for most of a long episode; contact flags
+// flip rarely).  The sector was read by this thread just before, so partial writes merge in L2.
+__device__ __forceinline__ void store_env_step(const DexsimState& st, int64_t i, const EnvRegs& e, const Hot& h) {
+    const int64_t ld = st.ld;
+    float* __restrict__ obs = st.obs;
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) obs[(DEXSIM_ROW_JP + j) * ld + i] = e.jp[j];
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) obs[(DEXSIM_ROW_JV + j) * ld + i] = e.jv[j];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        if (__double_as_longlong(e.op[k]) != __double_as_longlong(h.op_old[k])) {
+            st.op64[k * ld + i] = e.op[k];
+            obs[(DEXSIM_ROW_OP + k) * ld + i] = (float)e.op[k];
+        }
+        if (__float_as_uint(e.ov[k]) != __float_as_uint(h.ov_old[k])) obs[(DEXSIM_ROW_OV + k) * ld + i] = e.ov[k];
+    }
+    const unsigned flip = e.cmask ^ h.cmask_old;
+    if (flip) {
+#pragma unroll
+        for (int f = 0; f < NF; ++f)
+            if ((flip >> f) & 1u) obs[(DEXSIM_ROW_CONTACT + f) * ld + i] = ((e.cmask >> f) & 1u) ? 1.0f : 0.0f;
+        st.cmask[i] = (uint8_t)e.cmask;
+    }
+    st.step_count[i] = e.sc;
+}
+
+__device__ __forceinline__ int group_index(const uint16_t* group_of_env, int64_t i, int64_t gid, int num_groups) {
+    return group_of_env ? (int)group_of_env[i] : (int)((uint32_t)gid % (uint32_t)num_groups);
+}
+
+// One finished episode -> per-group counters (rows of DEXSIM_NCOUNTERS int64) + return sums.
+__device__ __forceinline__ void record_episode(unsigned long long* cnt, double* rs, int success, int steps,
+                                               int final_c, int la, int lb, int tie, double ret) {
+    atomicAdd(&cnt[DEXSIM_CNT_EPISODES], 1ull);
+    if (success) atomicAdd(&cnt[DEXSIM_CNT_SUCCESSES], 1ull);
+    atomicAdd(&cnt[DEXSIM_CNT_SUM_STEPS], (unsigned long long)steps);
+    atomicAdd(&cnt[DEXSIM_CNT_SUM_STEPS_SQ], (unsigned long long)steps * (unsigned long long)steps);
+    if (final_c) atomicAdd(&cnt[DEXSIM_CNT_SUM_FINAL_CONTACTS], (unsigned long long)final_c);
+    if (la != DEXSIM_LABEL_NONE) atomicAdd(&cnt[DEXSIM_CNT_LABEL_METRICS + la], 1ull);
+    if (lb != DEXSIM_LABEL_NONE) atomicAdd(&cnt[DEXSIM_CNT_LABEL_TAXONOMY + lb], 1ull);
+    if (tie) atomicAdd(&cnt[DEXSIM_CNT_VAR_TIES], 1ull);
+    if (rs) { atomicAdd(&rs[0], ret); atomicAdd(&rs[1], __dmul_rn(ret, ret)); }
+}
+
+// Episode end shared by the step kernel's auto-reset and the rollout kernel
+// (loop shape of evaluation/evaluator.py:135-173 / training/episode_utils.py:42-55).
+__device__ __forceinline__ void finish_and_reset(EnvRegs& e, const DexsimParams& p, const DexsimGroup& grp,
+                                                 uint32_t gid, uint32_t& episode, double& ep_return, EpStats& es,
+                                                 bool terminated, int n_c, unsigned long long* cnt, double* rs,
+                                                 double& size, double& mass, double& friction) {
+    if (cnt) {
+        DexsimEpisodeSummary s;
+        s.success = p.success_is_terminated ? (terminated ? 1 : 0) : 0;
+        s.episode_steps = e.sc; s.num_contacts = n_c; s.final_contacts = n_c; s.hist_len = e.sc;
+        int sum, sq, f5, l5, mx;
+        epstats_unpack(es, sum, sq, f5, l5, mx);
+        s.max_count = mx; s.sum_counts = sum; s.sum_sq_counts = sq; s.first5_sum = f5; s.last5_sum = l5;
+        int la, lb, tie;
+        classify_summary(s, p.loop_max_steps > 0 ? p.loop_max_steps : p.max_episode_steps, p.success_threshold,
+                         la, lb, tie);
+        record_episode(cnt, rs, s.success, e.sc, n_c, la, lb, tie, ep_return);
+    }
+    episode += 1u;
+    float jp0[NJ], pos[3];
+    reset_draws(p.seed, gid, episode, grp, jp0, size, mass, friction, pos);
+    env_reset(e, jp0, size, friction, pos, /*keep_pos=*/!p.respawn);
+    ep_return = 0.0;
+    es.w0 = 0u; es.w1 = 0u;
+}
+
+// ---- step kernel -----------------------------------------------------------------------------------
+// DENSE: reward type.  AOS: action is [n, 15] (reference layout) and is transposed through shared
+// memory with coalesced float4 reads (15 is odd, so the per-thread reads are bank-conflict free).
+// EXTRAS: noise, reward components, episode tracking, auto-reset -- the plain path carries none
+// of their registers or branches.
+template <bool DENSE, bool AOS, bool EXTRAS>
+__global__ void __launch_bounds__(STEP_THREADS, 2)
+step_kernel(const DexsimState st, const DexsimParams p, const DexsimGroup* __restrict__ groups,
+            const uint16_t* __restrict__ group_of_env, const DexsimStepIO io) {
+    __shared__ __align__(16) float sh_act[AOS ? STEP_THREADS * NJ : 4];
+    const int64_t n = st.n, ld = st.ld;
+    for (int64_t base = (int64_t)blockIdx.x * STEP_THREADS; base < n; base += (int64_t)gridDim.x * STEP_THREADS) {
+        const int64_t i = base + threadIdx.x;
+        const bool active = i < n;
+        float a[NJ];
+        if (AOS) {
+            // tile = envs [base, base + 256) -> 3840 contiguous floats starting 16-byte aligned
+            const int64_t tile_floats = (((n - base) < STEP_THREADS) ? (n - base) : STEP_THREADS) * NJ;
+            const float* __restrict__ src = io.action + base * NJ;
+            __syncthreads();                         // previous tile fully consumed
+            const int64_t nvec = tile_floats >> 2;
+            for (int64_t v = threadIdx.x; v < nvec; v += STEP_THREADS)
+                reinterpret_cast<float4*>(sh_act)[v] = __ldg(reinterpret_cast<const float4*>(src) + v);
+            for (int64_t r = (nvec << 2) + threadIdx.x; r < tile_floats; r += STEP_THREADS) sh_act[r] = __ldg(src + r);
+            __syncthreads();
+            if (active) {
+#pragma unroll
+                for (int j = 0; j < NJ; ++j) a[j] = sh_act[threadIdx.x * NJ + j];
+            }
+        } else if (active) {
+#pragma unroll
+            for (int j = 0; j < NJ; ++j) a[j] = __ldg(io.action + j * ld + i);
+        }
+        if (!active) continue;
+
+        EnvRegs e;
+        load_env(st, i, e);
+        Hot h;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) { h.op_old[k] = e.op[k]; h.ov_old[k] = e.ov[k]; }
+        h.cmask_old = e.cmask;
+
+        if (EXTRAS && io.dyn_noise) {                // evaluation/robustness_tests.py:180-187
+#pragma unroll
+            for (int j = 0; j < NJ; ++j)
+                a[j] = clip_f32(__fadd_rn(a[j], __ldg(io.dyn_noise + j * ld + i)), -1.0f, 1.0f);
+        }
+
+        StepResult r;
+        env_step<DENSE>(e, a, p, r);
+
+        io.reward[i] = (float)r.total;
+        io.terminated[i] = r.terminated ? 1 : 0;
+        io.truncated[i] = r.truncated ? 1 : 0;
+        io.num_contacts[i] = (uint8_t)r.n_c;
+
+        if (!EXTRAS) {
+            store_env_step(st, i, e, h);
+            continue;
+        }
+
+        if (io.reward_comps) {
+            io.reward_comps[0 * ld + i] = (float)r.distance;
+            io.reward_comps[1 * ld + i] = (float)r.contact;
+            io.reward_comps[2 * ld + i] = (float)r.closure;
+            io.reward_comps[3 * ld + i] = (float)r.stability;
+        }
+        const bool tracking = st.ep_return != nullptr && st.ep_stats != nullptr;
+        double ep_return = 0.0;
+        EpStats es{0u, 0u};
+        if (tracking) {
+            ep_return = __dadd_rn(st.ep_return[i], r.total);           // evaluator.py:144
+            es.w0 = st.ep_stats[i]; es.w1 = st.ep_stats[ld + i];
+            epstats_push(es, e.sc - 1, r.n_c);                         // evaluator.py:148-150
+        }
+        const bool done = r.terminated || r.truncated || (p.loop_max_steps > 0 && e.sc >= p.loop_max_steps);
+        bool finished = false;
+        if (p.auto_reset && done) {
+            finished = true;
+            const int64_t gid = p.env_gid0 + i;
+            const int g = group_index(group_of_env, i, gid, p.num_groups);
+            uint32_t episode = st.episode[i];
+            double size, mass, friction;
+            unsigned long long* cnt = (io.counters && tracking)
+                ? reinterpret_cast<unsigned long long*>(io.counters) + (int64_t)g * DEXSIM_NCOUNTERS : nullptr;
+            double* rs = io.ret_sums ? io.ret_sums + 2 * g : nullptr;
+            finish_and_reset(e, p, groups[g], (uint32_t)gid, episode, ep_return, es, r.terminated, r.n_c,
+                             cnt, rs, size, mass, friction);
+            st.episode[i] = episode;
+            st.size[i] = size; st.mass[i] = mass; st.friction[i] = friction;
+            store_env_full(st, i, e);
+        } else {
+            store_env_step(st, i, e, h);
+        }
+        if (tracking) {
+            st.ep_return[i] = ep_return;
+            st.ep_stats[i] = es.w0; st.ep_stats[ld + i] = es.w1;
+        }
+        if (io.finished) io.finished[i] = finished ? 1 : 0;
+        if (io.noisy_obs && io.obs_noise) {          // evaluation/robustness_tests.py:204-205, all 45 entries
+            const float* __restrict__ nz = io.obs_noise;
+            float* __restrict__ out = io.noisy_obs;
+#pragma unroll
+            for (int j = 0; j < NJ; ++j) {
+                out[(DEXSIM_ROW_JP + j) * ld + i] = __fadd_rn(e.jp[j], __ldg(nz + (DEXSIM_ROW_JP + j) * ld + i));
+                out[(DEXSIM_ROW_JV + j) * ld + i] = __fadd_rn(e.jv[j], __ldg(nz + (DEXSIM_ROW_JV + j) * ld + i));
+            }
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                out[(DEXSIM_ROW_OP + k) * ld + i] = __fadd_rn((float)e.op[k], __ldg(nz + (DEXSIM_ROW_OP + k) * ld + i));
+                out[(DEXSIM_ROW_OV + k) * ld + i] = __fadd_rn(e.ov[k], __ldg(nz + (DEXSIM_ROW_OV + k) * ld + i));
+            }
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+                out[(DEXSIM_ROW_QUAT + k) * ld + i] = __fadd_rn(k == 0 ? 1.0f : 0.0f, __ldg(nz + (DEXSIM_ROW_QUAT + k) * ld + i));
+#pragma unroll
+            for (int f = 0; f < NF; ++f)
+                out[(DEXSIM_ROW_CONTACT + f) * ld + i] =
+                    __fadd_rn(((e.cmask >> f) & 1u) ? 1.0f : 0.0f, __ldg(nz + (DEXSIM_ROW_CONTACT + f) * ld + i));
+        }
+    }
+}
+
+// ---- reset kernels --------------------------------------------------------------------------------
+__global__ void __launch_bounds__(STEP_THREADS)
+reset_predrawn_kernel(const DexsimState st, const uint8_t* __restrict__ mask, const float* __restrict__ jp0,
+                      const double* __restrict__ size, const double* __restrict__ mass,
+                      const double* __restrict__ friction, const float* __restrict__ pos) {
+    const int64_t n = st.n, ld = st.ld;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        if (mask && !mask[i]) continue;
+        EnvRegs e;
+        float j0[NJ], ps[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+        for (int j = 0; j < NJ; ++j) j0[j] = jp0[j * ld + i];
+        if (pos) {
+#pragma unroll
+            for (int k = 0; k < 3; ++k) ps[k] = pos[k * ld + i];
+        } else {
+#pragma unroll
+            for (int k = 0; k < 3; ++k) e.op[k] = st.op64[k * ld + i];
+        }
+        env_reset(e, j0, size[i], friction[i], ps, pos == nullptr);
+        store_env_full(st, i, e);
+        st.size[i] = size[i]; st.mass[i] = mass[i]; st.friction[i] = friction[i];
+        if (st.ep_return) st.ep_return[i] = 0.0;
+        if (st.ep_stats) { st.ep_stats[i] = 0u; st.ep_stats[ld + i] = 0u; }
+    }
+}
+
+__global__ void __launch_bounds__(STEP_THREADS)
+reset_philox_kernel(const DexsimState st, const DexsimParams p, const DexsimGroup* __restrict__ groups,
+                    const uint16_t* __restrict__ group_of_env, const uint8_t* __restrict__ mask, int respawn) {
+    const int64_t n = st.n, ld = st.ld;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        if (mask && !mask[i]) continue;
+        const int64_t gid = p.env_gid0 + i;
+        const int g = group_index(group_of_env, i, gid, p.num_groups);
+        EnvRegs e;
+        if (!respawn) {
+#pragma unroll
+            for (int k = 0; k < 3; ++k) e.op[k] = st.op64[k * ld + i];
+        }
+        float j0[NJ], ps[3];
+        double size, mass, friction;
+        reset_draws(p.seed, (uint32_t)gid, st.episode[i], groups[g], j0, size, mass, friction, ps);
+        env_reset(e, j0, size, friction, ps, !respawn);
+        store_env_full(st, i, e);
+        st.size[i] = size; st.mass[i] = mass; st.friction[i] = friction;
+        if (st.ep_return) st.ep_return[i] = 0.0;
+        if (st.ep_stats) { st.ep_stats[i] = 0u; st.ep_stats[ld + i] = 0u; }
+    }
+}
+
+// ---- fused rollout ------------------------------------------------------------------------------------
+template <bool DENSE>
+__global__ void __launch_bounds__(STEP_THREADS, 2)
+rollout_kernel(const DexsimState st, const DexsimParams p, const DexsimGroup* __restrict__ groups,
+               const uint16_t* __restrict__ group_of_env, const int k_steps, const int policy_kind,
+               const float* __restrict__ actions, const float* __restrict__ dyn_noise,
+               int64_t* __restrict__ counters, double* __restrict__ ret_sums) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int G = p.num_groups;
+    const bool staged = G <= SMEM_GROUPS_MAX;
+    DexsimGroup* sh_groups = reinterpret_cast<DexsimGroup*>(smem_raw);
+    unsigned long long* sh_cnt = reinterpret_cast<unsigned long long*>(sh_groups + (staged ? G : 0));
+    double* sh_rs = reinterpret_cast<double*>(sh_cnt + (staged ? G * DEXSIM_NCOUNTERS : 0));
+    if (staged) {
+        // per-env object / curriculum parameters are read from shared memory at every reset
+        const int words = G * (int)(sizeof(DexsimGroup) / 4);
+        for (int w = threadIdx.x; w < words; w += blockDim.x)
+            reinterpret_cast<uint32_t*>(sh_groups)[w] = reinterpret_cast<const uint32_t*>(groups)[w];
+        for (int w = threadIdx.x; w < G * DEXSIM_NCOUNTERS; w += blockDim.x) sh_cnt[w] = 0ull;
+        for (int w = threadIdx.x; w < G * 2; w += blockDim.x) sh_rs[w] = 0.0;
+        __syncthreads();
+    }
+    const DexsimGroup* gtab = staged ? sh_groups : groups;
+    unsigned long long* cnt_base = staged ? sh_cnt : reinterpret_cast<unsigned long long*>(counters);
+    double* rs_base = staged ? sh_rs : ret_sums;
+
+    const int64_t n = st.n, ld = st.ld;
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) {
+        const int64_t gid64 = p.env_gid0 + i;
+        const uint32_t gid = (uint32_t)gid64;
+        const int g = group_index(group_of_env, i, gid64, G);
+        const DexsimGroup& grp = gtab[g];
+        unsigned long long* cnt = counters ? cnt_base + (int64_t)g * DEXSIM_NCOUNTERS : nullptr;
+        double* rs = (ret_sums && counters) ? rs_base + 2 * g : nullptr;
+        const float sigma_dyn = grp.sigma_dyn;
+
+        EnvRegs e;
+        load_env(st, i, e);
+        uint32_t episode = st.episode[i];
+        const bool tracking = st.ep_return != nullptr && st.ep_stats != nullptr;
+        double ep_return = tracking ? st.ep_return[i] : 0.0;
+        EpStats es{0u, 0u};
+        if (tracking) { es.w0 = st.ep_stats[i]; es.w1 = st.ep_stats[ld + i]; }
+        double size = st.size[i], mass = st.mass[i], friction = st.friction[i];
+        bool params_dirty = false;
+
+        for (int t = 0; t < k_steps; ++t) {
+            float a[NJ];
+            if (policy_kind == DEXSIM_POLICY_EXTERNAL) {
+#pragma unroll
+                for (int j = 0; j < NJ; ++j) a[j] = __ldg(actions + ((int64_t)t * NJ + j) * ld + i);
+            } else {
+                policy_action(p.seed, gid, episode, (uint32_t)e.sc, policy_kind, a);
+            }
+            if (dyn_noise) {                               // pre-drawn, already scaled by sigma
+#pragma unroll
+                for (int j = 0; j < NJ; ++j)
+                    a[j] = clip_f32(__fadd_rn(a[j], __ldg(dyn_noise + ((int64_t)t * NJ + j) * ld + i)), -1.0f, 1.0f);
+            } else if (sigma_dyn > 0.0f) {                 // evaluation/robustness_tests.py:180-187
+                float nz[NJ];
+                normal_rows<NJ>(p.seed, gid, episode, (uint32_t)e.sc, STREAM_DYN, sigma_dyn, nz);
+#pragma unroll
+                for (int j = 0; j < NJ; ++j) a[j] = clip_f32(__fadd_rn(a[j], nz[j]), -1.0f, 1.0f);
+            }
+            StepResult r;
+            env_step<DENSE>(e, a, p, r);
+            ep_return = __dadd_rn(ep_return, r.total);
+            epstats_push(es, e.sc - 1, r.n_c);
+            const bool done = r.terminated || r.truncated || (p.loop_max_steps > 0 && e.sc >= p.loop_max_steps);
+            if (done) {
+                finish_and_reset(e, p, grp, gid, episode, ep_return, es, r.terminated, r.n_c, cnt, rs,
+                                 size, mass, friction);
+                params_dirty = true;
+            }
+        }
+        store_env_full(st, i, e);
+        st.episode[i] = episode;
+        if (tracking) {
+            st.ep_return[i] = ep_return;
+            st.ep_stats[i] = es.w0; st.ep_stats[ld + i] = es.w1;
+        }
+        if (params_dirty) { st.size[i] = size; st.mass[i] = mass; st.friction[i] = friction; }
+    }
+    if (staged && counters) {
+        __syncthreads();
+        unsigned long long* gc = reinterpret_cast<unsigned long long*>(counters);
+        for (int w = threadIdx.x; w < G * DEXSIM_NCOUNTERS; w += blockDim.x)
+            if (sh_cnt[w]) atomicAdd(&gc[w], sh_cnt[w]);
+        if (ret_sums)
+            for (int w = threadIdx.x; w < G * 2; w += blockDim.x)
+                if (sh_rs[w] != 0.0) atomicAdd(&ret_sums[w], sh_rs[w]);
+    }
+}
+
+// ---- RNG exposure ------------------------------------------------------------------------------------
+__global__ void fill_policy_kernel(const DexsimState st, const DexsimParams p, int policy_kind, float* __restrict__ out) {
+    const int64_t n = st.n, ld = st.ld;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        float a[NJ];
+        policy_action(p.seed, (uint32_t)(p.env_gid0 + i), st.episode[i], (uint32_t)st.step_count[i], policy_kind, a);
+#pragma unroll
+        for (int j = 0; j < NJ; ++j) out[j * ld + i] = a[j];
+    }
+}
+
+template <int ROWS>
+__global__ void fill_normal_kernel(const DexsimState st, const DexsimParams p, uint32_t stream, float sigma,
+                                   float* __restrict__ out) {
+    const int64_t n = st.n, ld = st.ld;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        float z[ROWS];
+        normal_rows<ROWS>(p.seed, (uint32_t)(p.env_gid0 + i), st.episode[i], (uint32_t)st.step_count[i], stream, sigma, z);
+#pragma unroll
+        for (int j = 0; j < ROWS; ++j) out[j * ld + i] = z[j];
+    }
+}
+
+// ---- host side -----------------------------------------------------------------------------------------
+struct DeviceInfo { int sm_count = 0; int step_ctas = 0; int rollout_ctas = 0; bool valid = false; };
+
+static int query_device(DeviceInfo& d) {
+    int dev = 0;
+    cudaError_t err = cudaGetDevice(&dev);
+    if (err != cudaSuccess) return -(int)err;
+    err = cudaDeviceGetAttribute(&d.sm_count, cudaDevAttrMultiProcessorCount, dev);
+    if (err != cudaSuccess) return -(int)err;
+    err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&d.step_ctas, step_kernel<true, false, false>, STEP_THREADS, 0);
+    if (err != cudaSuccess) return -(int)err;
+    err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&d.rollout_ctas, rollout_kernel<true>, STEP_THREADS, 0);
+    if (err != cudaSuccess) return -(int)err;
+    d.valid = true;
+    return 0;
+}
+
+static int device_info_cached(DeviceInfo& out) {
+    static thread_local DeviceInfo cache[64];
+    int dev = 0;
+    cudaError_t err = cudaGetDevice(&dev);
+    if (err != cudaSuccess) return -(int)err;
+    if (dev < 0 || dev >= 64) { return query_device(out); }
+    if (!cache[dev].valid) {
+        const int rc = query_device(cache[dev]);
+        if (rc) return rc;
+    }
+    out = cache[dev];
+    return 0;
+}
+
+static int check_state(const DexsimState* st) {
+    if (!st) return DEXSIM_E_NULL;
+    if (st->n < 0 || st->ld < st->n || (st->ld % 32) != 0) return DEXSIM_E_SIZE;
+    if (!st->obs || !st->op64 || !st->thr || !st->damp || !st->step_count || !st->cmask || !st->size ||
+        !st->mass || !st->friction || !st->episode)
+        return DEXSIM_E_NULL;
+    if ((reinterpret_cast<uintptr_t>(st->obs) & 15u) || (reinterpret_cast<uintptr_t>(st->op64) & 15u)) return DEXSIM_E_ALIGN;
+    if ((st->ep_return == nullptr) != (st->ep_stats == nullptr)) return DEXSIM_E_NULL;
+    return 0;
+}
+
+static int check_params(const DexsimParams* p, bool need_groups, const DexsimGroup* groups) {
+    if (!p) return DEXSIM_E_NULL;
+    if (p->reward_type != 0 && p->reward_type != 1) return DEXSIM_E_PARAM;
+    if (p->max_episode_steps < 0 || p->success_threshold < 0) return DEXSIM_E_PARAM;
+    if (need_groups) {
+        if (p->num_groups < 1 || p->num_groups > DEXSIM_MAX_GROUPS) return DEXSIM_E_GROUPS;
+        if (!groups) return DEXSIM_E_NULL;
+    }
+    return 0;
+}
+
+static int grid_for(int64_t n, int threads, int ctas_per_sm, int sm_count) {
+    int64_t blocks = (n + threads - 1) / threads;
+    const int64_t cap = (int64_t)sm_count * (ctas_per_sm > 0 ? ctas_per_sm : 1);   // one full resident wave
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    return (int)blocks;
+}
+
+static inline int cuda_rc(cudaError_t e) { return e == cudaSuccess ? 0 : -(int)e; }
+
+template <bool DENSE, bool AOS>
+static void launch_step_variant(bool extras, int grid, cudaStream_t s, const DexsimState& st, const DexsimParams& p,
+                                const DexsimGroup* groups, const uint16_t* goe, const DexsimStepIO& io) {
+    if (extras) step_kernel<DENSE, AOS, true><<<grid, STEP_THREADS, 0, s>>>(st, p, groups, goe, io);
+    else        step_kernel<DENSE, AOS, false><<<grid, STEP_THREADS, 0, s>>>(st, p, groups, goe, io);
+}
+
+static int launch_step(const DexsimState* st, const DexsimParams* p, const DexsimGroup* groups,
+                       const uint16_t* goe, const DexsimStepIO* io, cudaStream_t s) {
+    int rc = check_state(st);
+    if (rc) return rc;
+    if (!io || !io->action || !io->reward || !io->terminated || !io->truncated || !io->num_contacts) return DEXSIM_E_NULL;
+    if (io->action_layout != 0 && io->action_layout != 1) return DEXSIM_E_PARAM;
+    if ((io->obs_noise != nullptr) != (io->noisy_obs != nullptr)) return DEXSIM_E_NULL;
+    const bool extras = io->dyn_noise || io->obs_noise || io->reward_comps || io->finished || p->auto_reset ||
+                        st->ep_return != nullptr;
+    rc = check_params(p, p && p->auto_reset, groups);
+    if (rc) return rc;
+    if (st->n == 0) return 0;
+    DeviceInfo di;
+    rc = device_info_cached(di);
+    if (rc) return rc;
+    const int grid = grid_for(st->n, STEP_THREADS, di.step_ctas, di.sm_count);
+    const bool dense = p->reward_type == 1, aos = io->action_layout == 1;
+    if (dense) { if (aos) launch_step_variant<true, true>(extras, grid, s, *st, *p, groups, goe, *io);
+                 else     launch_step_variant<true, false>(extras, grid, s, *st, *p, groups, goe, *io); }
+    else       { if (aos) launch_step_variant<false, true>(extras, grid, s, *st, *p, groups, goe, *io);
+                 else     launch_step_variant<false, false>(extras, grid, s, *st, *p, groups, goe, *io); }
+    return cuda_rc(cudaGetLastError());
+}
+
+}  // namespace dexsim
+
+using namespace dexsim;
+
+extern "C" {
+
+int dexsim_version(void) { return DEXSIM_ABI_VERSION; }
+
+const char* dexsim_error_string(int code) {
+    switch (code) {
+        case DEXSIM_OK: return "ok";
+        case DEXSIM_E_NULL: return "dexsim: required pointer is NULL";
+        case DEXSIM_E_SIZE: return "dexsim: bad size (need n >= 0, ld >= n, ld % 32 == 0, k_steps >= 1)";
+        case DEXSIM_E_ALIGN: return "dexsim: array base not 16-byte aligned";
+        case DEXSIM_E_PARAM: return "dexsim: bad enum or flag value";
+        case DEXSIM_E_GROUPS: return "dexsim: num_groups out of range";
+        case DEXSIM_E_GEOMETRY: return "dexsim: only num_fingers=5, joints_per_finger=3 is supported";
+        default: break;
+    }
+    if (code < 0 && code > -1000) return cudaGetErrorString((cudaError_t)(-code));
+    return "dexsim: unknown error code";
+}
+
+int dexsim_sizeof_state(void) { return (int)sizeof(DexsimState); }
+int dexsim_sizeof_params(void) { return (int)sizeof(DexsimParams); }
+int dexsim_sizeof_group(void) { return (int)sizeof(DexsimGroup); }
+int dexsim_sizeof_step_io(void) { return (int)sizeof(DexsimStepIO); }
+
+int dexsim_device_info(int* sm_count, int* step_ctas_per_sm, int* rollout_ctas_per_sm) {
+    DeviceInfo di;
+    const int rc = device_info_cached(di);
+    if (rc) return rc;
+    if (sm_count) *sm_count = di.sm_count;
+    if (step_ctas_per_sm) *step_ctas_per_sm = di.step_ctas;
+    if (rollout_ctas_per_sm) *rollout_ctas_per_sm = di.rollout_ctas;
+    return 0;
+}
+
+int dexsim_reset_predrawn(const DexsimState* st, const DexsimParams* p, const uint8_t* mask, const float* jp0,
+                          const double* size, const double* mass, const double* friction, const float* pos,
+                          void* stream) {
+    (void)p;
+    int rc = check_state(st);
+    if (rc) return rc;
+    if (!jp0 || !size || !mass || !friction) return DEXSIM_E_NULL;
+    if (st->n == 0) return 0;
+    DeviceInfo di;
+    rc = device_info_cached(di);
+    if (rc) return rc;
+    const int grid = grid_for(st->n, STEP_THREADS, 4, di.sm_count);
+    reset_predrawn_kernel<<<grid, STEP_THREADS, 0, (cudaStream_t)stream>>>(*st, mask, jp0, size, mass, friction, pos);
+    return cuda_rc(cudaGetLastError());
+}
+
+int dexsim_reset_philox(const DexsimState* st, const DexsimParams* p, const DexsimGroup* groups,
+                        const uint16_t* group_of_env, const uint8_t* mask, int32_t respawn, void* stream) {
+    int rc = check_state(st);
+    if (rc) return rc;
+    rc = check_params(p, true, groups);
+    if (rc) return rc;
+    if (st->n == 0) return 0;
+    DeviceInfo di;
+    rc = device_info_cached(di);
+    if (rc) return rc;
+    const int grid = grid_for(st->n, STEP_THREADS, 4, di.sm_count);
+    reset_philox_kernel<<<grid, STEP_THREADS, 0, (cudaStream_t)stream>>>(*st, *p, groups, group_of_env, mask, respawn ? 1 : 0);
+    return cuda_rc(cudaGetLastError());
+}
+
+int dexsim_step(const DexsimState* st, const DexsimParams* p, const DexsimGroup* groups,
+                const uint16_t* group_of_env, const DexsimStepIO* io, void* stream) {
+    if (!p) return DEXSIM_E_NULL;
+    return launch_step(st, p, groups, group_of_env, io, (cudaStream_t)stream);
+}
+
+int dexsim_rollout(const DexsimState* st, const DexsimParams* p, const DexsimGroup* groups,
+                   const uint16_t* group_of_env, int32_t k_steps, int32_t policy_kind, const float* actions,
+                   const float* dyn_noise, int64_t* counters, double* ret_sums, void* stream) {
+    int rc = check_state(st);
+    if (rc) return rc;
+    rc = check_params(p, true, groups);
+    if (rc) return rc;
+    if (k_steps < 1) return DEXSIM_E_SIZE;
+    if (policy_kind < DEXSIM_POLICY_EXTERNAL || policy_kind > DEXSIM_POLICY_HEURISTIC) return DEXSIM_E_PARAM;
+    if (policy_kind == DEXSIM_POLICY_EXTERNAL && !actions) return DEXSIM_E_NULL;
+    if (ret_sums && !counters) return DEXSIM_E_NULL;
+    if (counters && !st->ep_return) return DEXSIM_E_NULL;   // labels need the per-env history summary
+    if (st->n == 0) return 0;
+    DeviceInfo di;
+    rc = device_info_cached(di);
+    if (rc) return rc;
+    // Small batches are latency-bound: spread warps over as many SM sub-partitions as possible
+    // (4 per SM) by shrinking the CTA; large batches use full 256-thread CTAs.
+    const int64_t warps = (st->n + 31) / 32;
+    int threads = STEP_THREADS;
+    while (threads > 32 && warps * 32 / threads < (int64_t)di.sm_count * 4) threads >>= 1;
+    const int64_t blocks = (st->n + threads - 1) / threads;
+    if (blocks > 0x7FFFFFFFll) return DEXSIM_E_SIZE;
+    const int G = p->num_groups;
+    const size_t smem = G <= SMEM_GROUPS_MAX
+        ? (size_t)G * (sizeof(DexsimGroup) + DEXSIM_NCOUNTERS * sizeof(unsigned long long) + 2 * sizeof(double)) : 0;
+    cudaStream_t s = (cudaStream_t)stream;
+    if (p->reward_type == 1)
+        rollout_kernel<true><<<(int)blocks, threads, smem, s>>>(*st, *p, groups, group_of_env, k_steps, policy_kind,
+                                                                actions, dyn_noise, counters, ret_sums);
+    else
+        rollout_kernel<false><<<(int)blocks, threads, smem, s>>>(*st, *p, groups, group_of_env, k_steps, policy_kind,
+                                                                 actions, dyn_noise, counters, ret_sums);
+    return cuda_rc(cudaGetLastError());
+}
+
+int dexsim_fill_policy_actions(const DexsimState* st, const DexsimParams* p, int32_t policy_kind, float* actions,
+                               void* stream) {
+    int rc = check_state(st);
+    if (rc) return rc;
+    if (!p || !actions) return DEXSIM_E_NULL;
+    if (policy_kind != DEXSIM_POLICY_RANDOM && policy_kind != DEXSIM_POLICY_HEURISTIC) return DEXSIM_E_PARAM;
+    if (st->n == 0) return 0;
+    const int grid = (int)((st->n + 255) / 256 > 65535 ? 65535 : (st->n + 255) / 256);
+    fill_policy_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(*st, *p, policy_kind, actions);
+    return cuda_rc(cudaGetLastError());
+}
+
+int dexsim_fill_normal(const DexsimState* st, const DexsimParams* p, int32_t rng_stream, int32_t rows, float sigma,
+                       float* out, void* stream) {
+    int rc = check_state(st);
+    if (rc) return rc;
+    if (!p || !out) return DEXSIM_E_NULL;
+    if (rng_stream != (int)STREAM_DYN && rng_stream != (int)STREAM_OBS) return DEXSIM_E_PARAM;
+    if (rows != NJ && rows != NOBS) return DEXSIM_E_PARAM;
+    if (st->n == 0) return 0;
+    const int grid = (int)((st->n + 255) / 256 > 65535 ? 65535 : (st->n + 255) / 256);
+    if (rows == NJ) fill_normal_kernel<NJ><<<grid, 256, 0, (cudaStream_t)stream>>>(*st, *p, (uint32_t)rng_stream, sigma, out);
+    else fill_normal_kernel<NOBS><<<grid, 256, 0, (cudaStream_t)stream>>>(*st, *p, (uint32_t)rng_stream, sigma, out);
+    return cuda_rc(cudaGetLastError());
+}
+
+int dexsim_classify_summary(const DexsimEpisodeSummary* s, int32_t max_steps, int32_t success_threshold,
+                            int32_t* label_metrics, int32_t* label_taxonomy, int32_t* var_tie) {
+    if (!s || !label_metrics || !label_taxonomy) return DEXSIM_E_NULL;
+    int la, lb, tie;
+    classify_summary(*s, max_steps, success_threshold, la, lb, tie);
+    *label_metrics = la; *label_taxonomy = lb;
+    if (var_tie) *var_tie = tie;
+    return 0;
+}
+
+int dexsim_step_host(const DexsimState* st, const DexsimParams* p, const DexsimGroup* groups,
+                     const uint16_t* group_of_env, const DexsimStepIO* io, const float* h_action, float* h_obs,
+                     float* h_reward, uint8_t* h_terminated, uint8_t* h_truncated, uint8_t* h_num_contacts,
+                     void* stream) {
+    int rc = check_state(st);
+    if (rc) return rc;
+    if (!p || !io || !io->action || !h_action || !h_reward || !h_terminated || !h_truncated) return DEXSIM_E_NULL;
+    cudaStream_t s = (cudaStream_t)stream;
+    const int64_t n = st->n, ld = st->ld;
+    const size_t act_bytes = (io->action_layout == 1 ? (size_t)n * NJ : (size_t)ld * NJ) * sizeof(float);
+    cudaError_t err = cudaMemcpyAsync(const_cast<float*>(io->action), h_action, act_bytes, cudaMemcpyHostToDevice, s);
+    if (err != cudaSuccess) return -(int)err;
+    rc = launch_step(st, p, groups, group_of_env, io, s);
+    if (rc) return rc;
+    if (h_obs) {
+        const float* src = (io->noisy_obs && io->obs_noise) ? io->noisy_obs : st->obs;
+        err = cudaMemcpyAsync(h_obs, src, (size_t)ld * NOBS * sizeof(float), cudaMemcpyDeviceToHost, s);
+        if (err != cudaSuccess) return -(int)err;
+    }
+    err = cudaMemcpyAsync(h_reward, io->reward, (size_t)n * sizeof(float), cudaMemcpyDeviceToHost, s);
+    if (err != cudaSuccess) return -(int)err;
+    err = cudaMemcpyAsync(h_terminated, io->terminated, (size_t)n, cudaMemcpyDeviceToHost, s);
+    if (err != cudaSuccess) return -(int)err;
+    err = cudaMemcpyAsync(h_truncated, io->truncated, (size_t)n, cudaMemcpyDeviceToHost, s);
+    if (err != cudaSuccess) return -(int)err;
+    if (h_num_contacts) {
+        err = cudaMemcpyAsync(h_num_contacts, io->num_contacts, (size_t)n, cudaMemcpyDeviceToHost, s);
+        if (err != cudaSuccess) return -(int)err;
+    }
+    return cuda_rc(cudaStreamSynchronize(s));
+}
+
+}  // extern "C"

@@ -1,0 +1,625 @@
+"""BatchedManipulationEnv -- drop-in for the reference's DexterousManipulationEnv
+(envs/manipulation_env.py:14-356) that steps ``num_envs`` independent envs on one B200.
+
+Same constructor keywords, ``reset(seed=None, options=None) -> (obs, info)``,
+``step(action) -> (obs, reward, terminated, truncated, info)``, ``action_space``,
+``observation_space``, ``max_episode_steps``, mutable ``curriculum_config``, ``metadata``,
+``close()``.  With ``num_envs == 1`` it returns NumPy arrays / Python scalars / the reference's
+``info`` keys, so ``run_episode`` (training/episode_utils.py:13-55), ``Evaluator``
+(evaluation/evaluator.py:71-189), ``RobustnessTester`` (evaluation/robustness_tests.py:240-328)
+run against it unmodified.  With ``num_envs > 1`` everything is a CUDA tensor (batch first).
+
+Env state lives in torch tensors (structure-of-arrays, ``[field, ld]``); all arithmetic is in
+libdexsim_b200.so (csrc/dexsim_kernels.cu).  There is no CPU path.
+"""
+import ctypes as C
+from typing import Optional, Sequence
+
+import numpy as np
+import torch
+
+from . import _lib
+from .config import CurriculumConfig, group_table
+
+_L = _lib
+
+
+class Box:
+    """The slice of ``gymnasium.spaces.Box`` the reference's policies use
+    (policies/heuristic_policy.py:62, policies/random_policy.py:40, policies/simple_learner.py:46,69)."""
+
+    def __init__(self, low, high, shape, dtype=np.float32, seed=None):
+        self.shape = tuple(shape)
+        self.dtype = np.dtype(dtype)
+        self.low = np.full(self.shape, low, dtype=self.dtype)
+        self.high = np.full(self.shape, high, dtype=self.dtype)
+        self._rng = np.random.Generator(np.random.PCG64(np.random.SeedSequence(seed)))
+
+    def seed(self, seed=None):
+        self._rng = np.random.Generator(np.random.PCG64(np.random.SeedSequence(seed)))
+        return [seed]
+
+    def sample(self):
+        if not (np.all(np.isfinite(self.low)) and np.all(np.isfinite(self.high))):
+            return self._rng.normal(size=self.shape).astype(self.dtype)
+        return self._rng.uniform(self.low, self.high, self.shape).astype(self.dtype)
+
+    def contains(self, x):
+        x = np.asarray(x)
+        return bool(x.shape == self.shape and np.all(x >= self.low) and np.all(x <= self.high))
+
+
+def _round_up(x, m):
+    return (x + m - 1) // m * m
+
+
+def _reward_spec(reward_type, reward_shaping):
+    """(reward_type code, weights) from the reference's constructor arguments
+    (envs/manipulation_env.py:65-74; rewards/reward_shaping.py:20-25)."""
+    default = (1.0, 0.5, 0.3, 0.2)
+    if reward_shaping is None:
+        if reward_type not in ("dense", "sparse"):
+            # the reference treats anything that is not "dense" as sparse (:68-74)
+            return 0, default
+        return (1 if reward_type == "dense" else 0), default
+    names = ("distance_weight", "contact_weight", "closure_weight", "stability_weight")
+    if all(hasattr(reward_shaping, k) for k in names):
+        return 1, tuple(float(getattr(reward_shaping, k)) for k in names)
+    if type(reward_shaping).__name__ == "SparseReward":
+        return 0, default
+    raise NotImplementedError(
+        "reward_shaping objects other than RewardShaping(weights) / SparseReward cannot be fused "
+        "into the step kernel; there is no CPU path to call arbitrary Python reward code")
+
+
+class BatchedManipulationEnv:
+    metadata = {"render_modes": ["human", "rgb_array"], "render_fps": 30}   # envs/manipulation_env.py:22
+
+    def __init__(
+        self,
+        num_envs: int = 1,
+        device="cuda",
+        num_fingers: int = 5,
+        joints_per_finger: int = 3,
+        object_position=None,
+        max_episode_steps: int = 200,
+        render_mode: Optional[str] = None,
+        reward_type: str = "sparse",
+        reward_shaping=None,
+        curriculum_config=None,
+        *,
+        auto_reset: bool = False,
+        respawn: Optional[bool] = None,
+        loop_max_steps: int = 0,
+        success_is_terminated: bool = True,
+        info_success: bool = False,
+        track_episodes: Optional[bool] = None,
+        reward_components: Optional[bool] = None,
+        rng: Optional[str] = None,
+        seed: int = 0,
+        env_gid0: int = 0,
+        groups: Optional[Sequence] = None,
+        group_sigma_obs=0.0,
+        group_sigma_dyn=0.0,
+        group_of_env=None,
+        observation_noise_std: float = 0.0,
+        dynamics_noise_std: float = 0.0,
+    ):
+        if num_fingers != 5 or joints_per_finger != 3:
+            raise _lib.DexsimError(-1006, "BatchedManipulationEnv")
+        if num_envs < 1:
+            raise ValueError("num_envs must be >= 1")
+        self._lib = _lib.lib()
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise RuntimeError("BatchedManipulationEnv needs a CUDA device; there is no CPU path")
+        if self.device.index is None:
+            self.device = torch.device("cuda", torch.cuda.current_device())
+        self.num_envs = int(num_envs)
+        self.num_fingers, self.joints_per_finger, self.num_joints = 5, 3, 15
+        self.max_episode_steps = int(max_episode_steps)
+        self.render_mode = render_mode
+        self.reward_type = reward_type
+        self.reward_shaping = reward_shaping
+        self._reward_code, self._weights = _reward_spec(reward_type, reward_shaping)
+        self.auto_reset = bool(auto_reset)
+        self.respawn = respawn
+        self.loop_max_steps = int(loop_max_steps)
+        self.success_is_terminated = bool(success_is_terminated)
+        self.info_success = bool(info_success)
+        self.single = self.num_envs == 1
+        self.track_episodes = self.auto_reset if track_episodes is None else bool(track_episodes)
+        self.reward_components = self.single if reward_components is None else bool(reward_components)
+        self.rng_mode = rng or ("numpy" if self.single else "philox")
+        if self.rng_mode not in ("numpy", "philox"):
+            raise ValueError("rng must be 'numpy' or 'philox'")
+        self.seed = int(seed)
+        self.env_gid0 = int(env_gid0)
+        self.observation_noise_std = float(observation_noise_std)
+        self.dynamics_noise_std = float(dynamics_noise_std)
+
+        self.action_space = Box(-1.0, 1.0, (15,), np.float32)                 # :85-90
+        self.observation_space = Box(-np.inf, np.inf, (45,), np.float32)      # :96-106
+        self._curriculum_config = curriculum_config if curriculum_config is not None else CurriculumConfig()
+        self._group_cfgs = list(groups) if groups is not None else None
+        self._group_sigma = (group_sigma_obs, group_sigma_dyn)
+        self._groups_dirty = True
+        self._object_position_arg = None if object_position is None else np.asarray(object_position, np.float32)
+        self._spawned = False          # reference: self.object_position is None until the first reset (:156)
+        self._np_rngs = None
+
+        n, ld = self.num_envs, _round_up(self.num_envs, 32)
+        self.ld = ld
+        dev = self.device
+        z = lambda *shape, dtype: torch.zeros(*shape, dtype=dtype, device=dev)
+        self._obs = z(45, ld, dtype=torch.float32)
+        self._obs[_L.ROW_QUAT].fill_(1.0)
+        self._op64 = z(3, ld, dtype=torch.float64)
+        self._thr = z(ld, dtype=torch.float64)
+        self._damp = z(ld, dtype=torch.float32)
+        self._step_count = z(ld, dtype=torch.int32)
+        self._cmask = z(ld, dtype=torch.uint8)
+        self._size = z(ld, dtype=torch.float64)
+        self._mass = z(ld, dtype=torch.float64)
+        self._friction = z(ld, dtype=torch.float64)
+        self._episode = z(ld, dtype=torch.int32)
+        self._ep_return = z(ld, dtype=torch.float64) if self.track_episodes else None
+        self._ep_stats = z(2, ld, dtype=torch.int32) if self.track_episodes else None
+        self._reward = z(ld, dtype=torch.float32)
+        self._comps = z(4, ld, dtype=torch.float32) if self.reward_components else None
+        self._terminated = z(ld, dtype=torch.uint8)
+        self._truncated = z(ld, dtype=torch.uint8)
+        self._num_contacts = z(ld, dtype=torch.uint8)
+        self._finished = z(ld, dtype=torch.uint8) if self.auto_reset else None
+        self._action_dev = z(n, 15, dtype=torch.float32)
+        self._noisy_obs = None
+        self._obs_noise = None
+        self._dyn_noise = None
+        self._goe = None
+        if group_of_env is not None:
+            goe = torch.as_tensor(group_of_env).to(torch.int16).to(dev)
+            self._goe = torch.zeros(ld, dtype=torch.int16, device=dev)
+            self._goe[:n] = goe
+        self._groups_dev = None
+        self.counters = None
+        self.ret_sums = None
+        self._state = _lib.DexsimState()
+        self._params = _lib.DexsimParams()
+        self._io = _lib.DexsimStepIO()
+        self._refresh_structs()
+        self._sync_groups()
+        # persistent output views (batch first)
+        self._obs_view = self._obs[:, :n].t()
+        self._info = None
+        self._did_reset = False
+
+    # ------------------------------------------------------------------ plumbing
+    @staticmethod
+    def _ptr(t):
+        return None if t is None else t.data_ptr()
+
+    def _refresh_structs(self):
+        s, p, io = self._state, self._params, self._io
+        s.n, s.ld = self.num_envs, self.ld
+        s.obs, s.op64, s.thr, s.damp = self._ptr(self._obs), self._ptr(self._op64), self._ptr(self._thr), self._ptr(self._damp)
+        s.step_count, s.cmask = self._ptr(self._step_count), self._ptr(self._cmask)
+        s.size, s.mass, s.friction = self._ptr(self._size), self._ptr(self._mass), self._ptr(self._friction)
+        s.episode, s.ep_return, s.ep_stats = self._ptr(self._episode), self._ptr(self._ep_return), self._ptr(self._ep_stats)
+        p.w_distance, p.w_contact, p.w_closure, p.w_stability = self._weights
+        p.reward_type = self._reward_code
+        p.max_episode_steps = self.max_episode_steps
+        p.success_threshold = 3
+        p.auto_reset = int(self.auto_reset)
+        p.respawn = int(True if self.respawn is None else self.respawn)
+        p.success_is_terminated = int(self.success_is_terminated)
+        p.loop_max_steps = self.loop_max_steps
+        p.seed = self.seed & 0xFFFFFFFFFFFFFFFF
+        p.env_gid0 = self.env_gid0
+        io.reward, io.reward_comps = self._ptr(self._reward), self._ptr(self._comps)
+        io.terminated, io.truncated = self._ptr(self._terminated), self._ptr(self._truncated)
+        io.num_contacts, io.finished = self._ptr(self._num_contacts), self._ptr(self._finished)
+        io.counters, io.ret_sums = self._ptr(self.counters), self._ptr(self.ret_sums)
+
+    @property
+    def curriculum_config(self):
+        return self._curriculum_config
+
+    @curriculum_config.setter
+    def curriculum_config(self, cfg):
+        # callers assign this between episodes (evaluation/component_ablation.py:163-166);
+        # effective at the next reset, including in-kernel auto-resets of later launches
+        self._curriculum_config = cfg
+        if self._group_cfgs is None:
+            self._groups_dirty = True
+
+    def set_groups(self, configs, sigma_obs=0.0, sigma_dyn=0.0, group_of_env=None):
+        """Several curriculum / object / noise cells in one batch; env -> group is
+        ``group_of_env`` or ``global env id % len(configs)``."""
+        self._group_cfgs = list(configs)
+        self._group_sigma = (sigma_obs, sigma_dyn)
+        if group_of_env is not None:
+            self._goe = torch.zeros(self.ld, dtype=torch.int16, device=self.device)
+            self._goe[:self.num_envs] = torch.as_tensor(group_of_env).to(torch.int16).to(self.device)
+        self._groups_dirty = True
+
+    @property
+    def num_groups(self):
+        return len(self._group_cfgs) if self._group_cfgs is not None else 1
+
+    def _sync_groups(self):
+        if not self._groups_dirty:
+            return
+        cfgs = self._group_cfgs if self._group_cfgs is not None else [self._curriculum_config]
+        so, sd = self._group_sigma
+        if self._group_cfgs is None:
+            so, sd = self.observation_noise_std, self.dynamics_noise_std
+        table = group_table(cfgs, so, sd)
+        raw = torch.frombuffer(bytearray(bytes(table)), dtype=torch.uint8)
+        if self._groups_dev is None or self._groups_dev.numel() != raw.numel():
+            self._groups_dev = torch.empty(raw.numel(), dtype=torch.uint8, device=self.device)
+        self._groups_dev.copy_(raw, non_blocking=False)
+        G = len(cfgs)
+        if self.counters is None or self.counters.shape[0] != G:
+            self.counters = torch.zeros(G, _L.NCOUNTERS, dtype=torch.int64, device=self.device)
+            self.ret_sums = torch.zeros(G, 2, dtype=torch.float64, device=self.device)
+        self._params.num_groups = G
+        self._io.counters, self._io.ret_sums = self._ptr(self.counters), self._ptr(self.ret_sums)
+        self._groups_dirty = False
+
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    # ------------------------------------------------------------------ reset
+    def _host_rngs(self, seed):
+        n = self.num_envs
+        if self._np_rngs is None:
+            self._np_rngs = [None] * n
+        if seed is not None:
+            seeds = [int(seed) + i for i in range(n)] if np.isscalar(seed) else [int(s) for s in seed]
+            if len(seeds) != n:
+                raise ValueError("need one seed per env")
+            for i, s in enumerate(seeds):
+                self._np_rngs[i] = np.random.Generator(np.random.PCG64(np.random.SeedSequence(s)))
+        for i in range(n):
+            if self._np_rngs[i] is None:          # gymnasium seeds lazily from entropy
+                self._np_rngs[i] = np.random.Generator(np.random.PCG64(np.random.SeedSequence(None)))
+        return self._np_rngs
+
+    def _config_of_env(self, i):
+        if self._group_cfgs is None:
+            return self._curriculum_config
+        if self._goe is not None:
+            return self._group_cfgs[int(self._goe[i])]
+        return self._group_cfgs[(self.env_gid0 + i) % len(self._group_cfgs)]
+
+    def _respawn_now(self):
+        if self.respawn is not None:
+            return bool(self.respawn)
+        return not self._spawned and self._object_position_arg is None
+
+    def reset(self, seed=None, options=None):
+        """envs/manipulation_env.py:124-182.  ``options={"mask": BoolTensor[num_envs]}`` resets a subset."""
+        with torch.cuda.device(self.device):
+            self._sync_groups()
+            mask = None
+            if options and options.get("mask") is not None:
+                m = torch.as_tensor(options["mask"]).to(self.device).to(torch.uint8)
+                mask = torch.zeros(self.ld, dtype=torch.uint8, device=self.device)
+                mask[:self.num_envs] = m
+            n, ld = self.num_envs, self.ld
+            respawn = self._respawn_now()
+            if self.rng_mode == "numpy":
+                rngs = self._host_rngs(seed)
+                jp0 = np.zeros((15, ld), np.float32)
+                size = np.zeros(ld); mass = np.zeros(ld); fric = np.zeros(ld)
+                pos = np.zeros((3, ld), np.float32) if (respawn or (not self._spawned and self._object_position_arg is not None)) else None
+                mask_host = None if mask is None else mask.cpu().numpy()
+                for i in range(n):
+                    if mask_host is not None and not mask_host[i]:
+                        continue
+                    r, cfg = rngs[i], self._config_of_env(i)
+                    jp0[:, i] = r.uniform(low=-0.1, high=0.1, size=(15,)).astype(np.float32)       # :143-145
+                    size[i] = cfg.get_object_size(r); mass[i] = cfg.get_object_mass(r)            # :151-153
+                    fric[i] = cfg.get_friction_coefficient(r)
+                    if respawn:
+                        pos[:, i] = np.array(cfg.get_spawn_position(r), dtype=np.float32)         # :156-159
+                    elif pos is not None:
+                        a = self._object_position_arg
+                        pos[:, i] = a if a.ndim == 1 else a[i]                                     # :160-161
+                dev = self.device
+                t = lambda a: torch.from_numpy(a).to(dev)
+                jp0_d, size_d, mass_d, fric_d = t(jp0), t(size), t(mass), t(fric)
+                pos_d = None if pos is None else t(pos)
+                _lib.check(self._lib.dexsim_reset_predrawn(
+                    C.byref(self._state), C.byref(self._params), self._ptr(mask), self._ptr(jp0_d), self._ptr(size_d),
+                    self._ptr(mass_d), self._ptr(fric_d), self._ptr(pos_d), self._stream()), "dexsim_reset_predrawn")
+                torch.cuda.current_stream(self.device).synchronize()     # host arrays go out of scope
+            else:
+                if seed is not None:
+                    self.seed = int(seed)
+                    self._params.seed = self.seed & 0xFFFFFFFFFFFFFFFF
+                    if mask is None:
+                        self._episode.zero_()
+                elif self._did_reset:
+                    if mask is None:
+                        self._episode.add_(1)
+                    else:
+                        self._episode.add_(mask.to(torch.int32))
+                if not respawn and not self._spawned and self._object_position_arg is not None:
+                    a = torch.as_tensor(self._object_position_arg, device=self.device)
+                    self._op64[:, :n] = (a.reshape(3, 1) if a.ndim == 1 else a.t()).to(torch.float64)
+                _lib.check(self._lib.dexsim_reset_philox(
+                    C.byref(self._state), C.byref(self._params), self._ptr(self._groups_dev), self._ptr(self._goe),
+                    self._ptr(mask), int(respawn), self._stream()), "dexsim_reset_philox")
+            self._spawned = True
+            self._did_reset = True
+            obs = self._emit_obs(reset=True)
+            return obs, self._make_info(after_reset=True)
+
+    def reset_from_draws(self, jp0, size, mass, friction, pos=None, mask=None):
+        """Reset with caller-supplied draws (batch first): jp0 [n,15] float32, size/mass/friction [n]
+        float64, pos [n,3] float32 or None = keep each env's current position cast to float32
+        (envs/manipulation_env.py:160-161).  This is the parity entry: identical initial states."""
+        n, ld, dev = self.num_envs, self.ld, self.device
+        with torch.cuda.device(dev):
+            self._sync_groups()
+
+            def soa(x, rows, dtype):
+                t = torch.as_tensor(np.asarray(x), dtype=dtype).reshape(n, rows) if rows else \
+                    torch.as_tensor(np.broadcast_to(np.asarray(x, np.float64), (n,)).copy(), dtype=dtype)
+                out = torch.zeros((rows, ld) if rows else (ld,), dtype=dtype, device=dev)
+                if rows:
+                    out[:, :n] = t.t().to(dev)
+                else:
+                    out[:n] = t.to(dev)
+                return out
+
+            jp0_d = soa(jp0, 15, torch.float32)
+            size_d, mass_d, fric_d = soa(size, 0, torch.float64), soa(mass, 0, torch.float64), soa(friction, 0, torch.float64)
+            pos_d = None if pos is None else soa(pos, 3, torch.float32)
+            mask_d = None
+            if mask is not None:
+                mask_d = torch.zeros(ld, dtype=torch.uint8, device=dev)
+                mask_d[:n] = torch.as_tensor(np.asarray(mask)).to(torch.uint8).to(dev)
+            _lib.check(self._lib.dexsim_reset_predrawn(
+                C.byref(self._state), C.byref(self._params), self._ptr(mask_d), self._ptr(jp0_d), self._ptr(size_d),
+                self._ptr(mass_d), self._ptr(fric_d), self._ptr(pos_d), self._stream()), "dexsim_reset_predrawn")
+            torch.cuda.current_stream(dev).synchronize()
+            self._spawned = True
+            self._did_reset = True
+            return self._emit_obs(reset=True), self._make_info(after_reset=True)
+
+    # ------------------------------------------------------------------ step
+    def _ingest_action(self, action):
+        n = self.num_envs
+        if isinstance(action, torch.Tensor) and action.is_cuda:
+            a = action
+            if a.dtype != torch.float32:
+                a = a.to(torch.float32)
+            a = a.reshape(n, 15)
+            if not a.is_contiguous():
+                a = a.contiguous()
+            if a.data_ptr() % 16:
+                self._action_dev.copy_(a)
+                a = self._action_dev
+            return a
+        a = np.asarray(action.detach().cpu() if isinstance(action, torch.Tensor) else action)
+        if a.dtype != np.float32:
+            # the reference silently promotes float64 actions and corrupts its own dtypes
+            # (SURVEY.md 8a-1); the batched env takes float32 only
+            a = a.astype(np.float32)
+        self._action_dev.copy_(torch.from_numpy(np.ascontiguousarray(a.reshape(n, 15))), non_blocking=False)
+        return self._action_dev
+
+    def _noise_buffers(self):
+        if self._noisy_obs is None:
+            self._noisy_obs = torch.zeros(45, self.ld, dtype=torch.float32, device=self.device)
+            self._obs_noise = torch.zeros(45, self.ld, dtype=torch.float32, device=self.device)
+            self._dyn_noise = torch.zeros(15, self.ld, dtype=torch.float32, device=self.device)
+
+    def _soa(self, x, rows):
+        """[n, rows] batch-first (or [rows] for a single env) -> SoA [rows, ld] device tensor."""
+        t = torch.as_tensor(x, dtype=torch.float32, device=self.device).reshape(self.num_envs, rows)
+        out = torch.zeros(rows, self.ld, dtype=torch.float32, device=self.device)
+        out[:, :self.num_envs] = t.t()
+        return out
+
+    def step(self, action, dyn_noise=None, obs_noise=None):
+        """envs/manipulation_env.py:184-252 for every env.  ``dyn_noise`` [n,15] / ``obs_noise`` [n,45]
+        are optional PRE-DRAWN float32 noise tensors (evaluation/robustness_tests.py:177-207); without
+        them, ``dynamics_noise_std`` / ``observation_noise_std`` > 0 draw Philox normals on the device."""
+        if not self._did_reset:
+            raise RuntimeError("call reset() before step()")
+        with torch.cuda.device(self.device):
+            self._sync_groups()
+            io = self._io
+            a = self._ingest_action(action)
+            io.action, io.action_layout = a.data_ptr(), 1
+            keep = [a]
+            want_dyn = dyn_noise is not None or self.dynamics_noise_std > 0.0
+            want_obs = obs_noise is not None or self.observation_noise_std > 0.0
+            io.dyn_noise = io.obs_noise = io.noisy_obs = None
+            if want_dyn or want_obs:
+                self._noise_buffers()
+            if want_dyn:
+                if dyn_noise is not None:
+                    dn = self._soa(dyn_noise, 15)
+                else:
+                    dn = self._dyn_noise
+                    _lib.check(self._lib.dexsim_fill_normal(
+                        C.byref(self._state), C.byref(self._params), _L.RNG_STREAM_DYN, 15,
+                        C.c_float(self.dynamics_noise_std), dn.data_ptr(), self._stream()), "dexsim_fill_normal")
+                io.dyn_noise = dn.data_ptr(); keep.append(dn)
+            if obs_noise is not None:
+                on = self._soa(obs_noise, 45)
+                io.obs_noise, io.noisy_obs = on.data_ptr(), self._noisy_obs.data_ptr()
+                keep.append(on)
+            _lib.check(self._lib.dexsim_step(C.byref(self._state), C.byref(self._params), self._ptr(self._groups_dev),
+                                             self._ptr(self._goe), C.byref(io), self._stream()), "dexsim_step")
+            if want_obs and obs_noise is None:
+                # Philox observation noise is keyed by (episode, step count AFTER the step), so it is
+                # drawn once the step has run (evaluation/robustness_tests.py:204-205)
+                _lib.check(self._lib.dexsim_fill_normal(
+                    C.byref(self._state), C.byref(self._params), _L.RNG_STREAM_OBS, 45,
+                    C.c_float(self.observation_noise_std), self._obs_noise.data_ptr(), self._stream()), "dexsim_fill_normal")
+                torch.add(self._obs, self._obs_noise, out=self._noisy_obs)
+            obs = self._emit_obs(noisy=want_obs)
+            n = self.num_envs
+            if self.single:
+                vals = torch.stack([self._reward[0].to(torch.float64), self._terminated[0].to(torch.float64),
+                                    self._truncated[0].to(torch.float64)]).cpu().numpy()
+                return obs, float(vals[0]), bool(vals[1]), bool(vals[2]), self._make_info()
+            return (obs, self._reward[:n], self._terminated[:n].view(torch.bool), self._truncated[:n].view(torch.bool),
+                    self._make_info())
+
+    def _emit_obs(self, reset=False, noisy=False):
+        n = self.num_envs
+        if reset and self.observation_noise_std > 0.0:
+            # evaluation/robustness_tests.py:171-175: noise is added to the reset observation too
+            self._noise_buffers()
+            _lib.check(self._lib.dexsim_fill_normal(
+                C.byref(self._state), C.byref(self._params), _L.RNG_STREAM_OBS, 45,
+                C.c_float(self.observation_noise_std), self._obs_noise.data_ptr(), self._stream()), "dexsim_fill_normal")
+            torch.add(self._obs, self._obs_noise, out=self._noisy_obs)
+            noisy = True
+        src = self._noisy_obs if noisy else self._obs
+        if self.single:
+            return src[:, 0].cpu().numpy().copy()
+        return src[:, :n].t()
+
+    def _make_info(self, after_reset=False):
+        n = self.num_envs
+        if self.single:
+            host = torch.cat([self._op64[:, 0], self._size[:1], self._mass[:1], self._friction[:1],
+                              self._step_count[:1].to(torch.float64), self._num_contacts[:1].to(torch.float64)
+                              if not after_reset else self._cmask[:1].to(torch.float64)]).cpu().numpy()
+            nc = int(host[7]) if not after_reset else bin(int(host[7])).count("1")
+            info = {
+                "step_count": int(host[6]),
+                "object_position": host[0:3].copy(),
+                "num_contacts": nc,
+                "curriculum": {"object_size": float(host[3]), "object_mass": float(host[4]),
+                               "friction_coefficient": float(host[5])},
+            }
+            if not after_reset and self._comps is not None:
+                c = self._comps[:, 0].to(torch.float64).cpu().numpy()
+                info["reward_components"] = {"total": float(self._reward[0]), "distance": float(c[0]),
+                                             "contact": float(c[1]), "closure": float(c[2]), "stability": float(c[3])}
+            if self.info_success and not after_reset:
+                info["success"] = bool(self._terminated[0])
+            return info
+        if self._info is None:
+            self._info = {
+                "step_count": self._step_count[:n],
+                "object_position": self._op64[:, :n].t(),
+                "num_contacts": self._num_contacts[:n],
+                "curriculum": {"object_size": self._size[:n], "object_mass": self._mass[:n],
+                               "friction_coefficient": self._friction[:n]},
+            }
+            if self._comps is not None:
+                self._info["reward_components"] = {
+                    "total": self._reward[:n], "distance": self._comps[0, :n], "contact": self._comps[1, :n],
+                    "closure": self._comps[2, :n], "stability": self._comps[3, :n]}
+            if self._finished is not None:
+                self._info["finished"] = self._finished[:n].view(torch.bool)
+            if self.info_success:
+                self._info["success"] = self._terminated[:n].view(torch.bool)
+        if after_reset:
+            info = dict(self._info)
+            info["num_contacts"] = sum(((self._cmask[:n] >> f) & 1) for f in range(5)).to(torch.uint8)
+            info.pop("reward_components", None)
+            return info
+        return self._info
+
+    # ------------------------------------------------------------------ host-buffer step (end to end)
+    def step_host(self, action_host):
+        """One step with HOST buffers: ``action_host`` is a float32 [num_envs, 15] NumPy array or CPU
+        tensor (pinned memory makes the copies true DMA); returns CPU tensors
+        ``(obs [num_envs,45], reward, terminated, truncated, info)`` living in pinned buffers that
+        the next call overwrites.  One C-ABI call (dexsim_step_host): H2D copy of the actions, the
+        step kernel, D2H copies of observation / reward / flags, stream synchronize."""
+        if not self._did_reset:
+            raise RuntimeError("call reset() before step_host()")
+        n, ld = self.num_envs, self.ld
+        if getattr(self, "_h_obs", None) is None:
+            pin = lambda *shape, dtype: torch.zeros(*shape, dtype=dtype).pin_memory()
+            self._h_obs = pin(45, ld, dtype=torch.float32)
+            self._h_reward = pin(ld, dtype=torch.float32)
+            self._h_term, self._h_trunc, self._h_nc = (pin(ld, dtype=torch.uint8) for _ in range(3))
+            self._h_info = {"num_contacts": self._h_nc[:n]}
+        a = action_host if isinstance(action_host, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(action_host, np.float32))
+        if a.dtype != torch.float32 or not a.is_contiguous() or a.numel() != n * 15:
+            a = a.to(torch.float32).reshape(n, 15).contiguous()
+        with torch.cuda.device(self.device):
+            self._sync_groups()
+            io = self._io
+            io.action, io.action_layout = self._action_dev.data_ptr(), 1
+            io.dyn_noise = io.obs_noise = io.noisy_obs = None
+            _lib.check(self._lib.dexsim_step_host(
+                C.byref(self._state), C.byref(self._params), self._ptr(self._groups_dev), self._ptr(self._goe),
+                C.byref(io), a.data_ptr(), self._h_obs.data_ptr(), self._h_reward.data_ptr(), self._h_term.data_ptr(),
+                self._h_trunc.data_ptr(), self._h_nc.data_ptr(), self._stream()), "dexsim_step_host")
+        return (self._h_obs[:, :n].t(), self._h_reward[:n], self._h_term[:n].view(torch.bool),
+                self._h_trunc[:n].view(torch.bool), self._h_info)
+
+    # ------------------------------------------------------------------ fused rollout
+    def rollout(self, k_steps, policy="random", actions=None, dyn_noise=None, loop_max_steps=None,
+                success_is_terminated=None, respawn=True, zero_counters=False):
+        """k env-steps per env in ONE kernel launch with the policy generated in-kernel
+        (caller loops of training/episode_utils.py:42-53 / evaluation/evaluator.py:135-158).
+        Returns (counters [G, 18] int64, ret_sums [G, 2] float64) device tensors (accumulated)."""
+        if not self._did_reset:
+            raise RuntimeError("call reset() before rollout()")
+        if self._ep_return is None:
+            raise RuntimeError("rollout() needs track_episodes=True (per-env history summaries)")
+        kind = {"external": _L.POLICY_EXTERNAL, "random": _L.POLICY_RANDOM, "heuristic": _L.POLICY_HEURISTIC}[policy]
+        with torch.cuda.device(self.device):
+            self._sync_groups()
+            if zero_counters:
+                self.counters.zero_(); self.ret_sums.zero_()
+            p = _lib.DexsimParams.from_buffer_copy(self._params)
+            p.loop_max_steps = self.max_episode_steps if loop_max_steps is None else int(loop_max_steps)
+            p.success_is_terminated = int(self.success_is_terminated if success_is_terminated is None else success_is_terminated)
+            p.respawn = int(respawn)
+            keep = []
+            a_ptr = n_ptr = None
+            if kind == _L.POLICY_EXTERNAL:
+                a = torch.as_tensor(actions, dtype=torch.float32, device=self.device).reshape(k_steps, self.num_envs, 15)
+                buf = torch.zeros(k_steps, 15, self.ld, dtype=torch.float32, device=self.device)
+                buf[:, :, :self.num_envs] = a.permute(0, 2, 1)
+                a_ptr = buf.data_ptr(); keep.append(buf)
+            if dyn_noise is not None:
+                d = torch.as_tensor(dyn_noise, dtype=torch.float32, device=self.device).reshape(k_steps, self.num_envs, 15)
+                nbuf = torch.zeros(k_steps, 15, self.ld, dtype=torch.float32, device=self.device)
+                nbuf[:, :, :self.num_envs] = d.permute(0, 2, 1)
+                n_ptr = nbuf.data_ptr(); keep.append(nbuf)
+            _lib.check(self._lib.dexsim_rollout(
+                C.byref(self._state), C.byref(p), self._ptr(self._groups_dev), self._ptr(self._goe), int(k_steps), kind,
+                a_ptr, n_ptr, self._ptr(self.counters), self._ptr(self.ret_sums), self._stream()), "dexsim_rollout")
+            self._spawned = True
+        return self.counters, self.ret_sums
+
+    # ------------------------------------------------------------------ misc API of the reference env
+    def render(self):
+        if self.render_mode == "rgb_array":
+            return np.zeros((480, 640, 3), dtype=np.uint8)     # envs/manipulation_env.py:338-346 placeholder
+        return None
+
+    def close(self):
+        pass
+
+    @property
+    def unwrapped(self):
+        return self
+
+    def state_dict(self):
+        """All device state (checkpoint / resume is a torch.save away)."""
+        keys = ("_obs", "_op64", "_thr", "_damp", "_step_count", "_cmask", "_size", "_mass", "_friction",
+                "_episode", "_ep_return", "_ep_stats")
+        return {k: getattr(self, k).clone() for k in keys if getattr(self, k) is not None}
+
+    def load_state_dict(self, sd):
+        for k, v in sd.items():
+            getattr(self, k).copy_(v)
+        self._did_reset = True
+        self._spawned = True

@@ -1,0 +1,224 @@
+/*
+ * dexsim.h -- C ABI of the B200-native batched manipulation simulator (libdexsim_b200.so).
+ *
+ * The reference (I2S9/dexterous-rl-manipulation) has no FFI or plugin registry: the boundary
+ * its callers use is the duck-typed Gymnasium env object.  The Python class
+ * dexterous_rl_manipulation_b200.BatchedManipulationEnv mirrors that object and calls the
+ * entry points below through ctypes; INTEGRATION.md shows the binding.  Each entry point names
+ * the reference interface it replaces (file:line relative to the reference root).
+ *
+ * Conventions
+ *   - extern "C", plain pointers and sizes, no torch / C++ types.
+ *   - Every pointer in DexsimState / DexsimStepIO is a DEVICE pointer owned by the caller
+ *     (the Python side allocates them as torch tensors); the *_host entry points take HOST
+ *     pointers (pinned for full speed) and are documented as such.
+ *   - `stream` is a cudaStream_t passed as void* (0 = legacy default stream).  Calls are
+ *     asynchronous on that stream unless stated; no hidden global state, no allocation
+ *     (except dexsim_host_ctx_create) => thread-safe per (device, stream).
+ *   - Return value: 0 = ok; negative cudaError_t (-e) for CUDA failures; DEXSIM_E_* for
+ *     argument errors.  No exceptions cross the boundary.  dexsim_error_string() explains.
+ *   - Per-env arrays are structure-of-arrays with leading dimension `ld` (>= n, multiple of
+ *     32 so every row starts 128-byte aligned): field f of env i lives at base[f * ld + i].
+ *   - Only num_fingers = 5, joints_per_finger = 3 is built (the only geometry any reference
+ *     config uses: experiments/experiment_config.py:32-33); other geometries are rejected by
+ *     the Python face with DEXSIM_E_GEOMETRY semantics.
+ */
+#ifndef DEXSIM_H
+#define DEXSIM_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DEXSIM_ABI_VERSION 1
+#define DEXSIM_NJ 15      /* joints            envs/manipulation_env.py:52 */
+#define DEXSIM_NF 5       /* fingers           envs/manipulation_env.py:50 */
+#define DEXSIM_OBS 45     /* observation width envs/manipulation_env.py:96-106 */
+
+/* observation rows (envs/manipulation_env.py:254-264) */
+#define DEXSIM_ROW_JP 0
+#define DEXSIM_ROW_JV 15
+#define DEXSIM_ROW_OP 30
+#define DEXSIM_ROW_QUAT 33
+#define DEXSIM_ROW_OV 37
+#define DEXSIM_ROW_CONTACT 40
+
+/* error codes */
+#define DEXSIM_OK 0
+#define DEXSIM_E_NULL (-1001)        /* required pointer is NULL */
+#define DEXSIM_E_SIZE (-1002)        /* n < 0, ld < n, ld % 32 != 0, k_steps < 1 ... */
+#define DEXSIM_E_ALIGN (-1003)       /* a row base is not 16-byte aligned */
+#define DEXSIM_E_PARAM (-1004)       /* bad enum / flag value */
+#define DEXSIM_E_GROUPS (-1005)      /* num_groups out of range [1, DEXSIM_MAX_GROUPS] */
+#define DEXSIM_E_GEOMETRY (-1006)    /* unsupported num_fingers / joints_per_finger */
+
+#define DEXSIM_MAX_GROUPS 256
+
+/* policy kinds (policies/random_policy.py:40, policies/heuristic_policy.py:55-62) */
+#define DEXSIM_POLICY_EXTERNAL 0
+#define DEXSIM_POLICY_RANDOM 1
+#define DEXSIM_POLICY_HEURISTIC 2
+
+/* failure-label codes = enum declaration order of FailureType (evaluation/metrics.py:15-22)
+ * and FailureMode (evaluation/failure_taxonomy.py:14-26) */
+#define DEXSIM_LABEL_SLIPPAGE 0
+#define DEXSIM_LABEL_UNSTABLE 1
+#define DEXSIM_LABEL_MISALIGNED 2
+#define DEXSIM_LABEL_TIMEOUT 3
+#define DEXSIM_LABEL_DROPPED 4
+#define DEXSIM_LABEL_INSUFFICIENT 5
+#define DEXSIM_LABEL_NONE 255
+
+/* per-group int64 counters written by rollouts / auto-reset (one row per group) */
+#define DEXSIM_CNT_EPISODES 0
+#define DEXSIM_CNT_SUCCESSES 1
+#define DEXSIM_CNT_SUM_STEPS 2
+#define DEXSIM_CNT_SUM_FINAL_CONTACTS 3
+#define DEXSIM_CNT_LABEL_METRICS 4      /* +label code, 6 slots: evaluation/metrics.py:39-96 */
+#define DEXSIM_CNT_LABEL_TAXONOMY 10    /* +label code, 6 slots: evaluation/failure_taxonomy.py:156-239 */
+#define DEXSIM_CNT_VAR_TIES 16          /* episodes whose contact-count variance sat exactly on a threshold */
+#define DEXSIM_CNT_SUM_STEPS_SQ 17
+#define DEXSIM_NCOUNTERS 18
+
+/*
+ * Device-resident state of one shard of n envs.  `obs` doubles as the hot state: its rows ARE
+ * the observation (quaternion rows are written once at reset), so stepping produces the
+ * observation tensor for free.  The float64 object position and contact threshold exist
+ * because the reference's contact test is (accidentally) float64.
+ */
+typedef struct DexsimState {
+    int64_t   n;           /* envs in this shard */
+    int64_t   ld;          /* leading dimension of every per-env array */
+    float*    obs;         /* [45, ld]  hot state == observation, envs/manipulation_env.py:254-264 */
+    double*   op64;        /* [3, ld]   object_position in float64, :222-229 */
+    double*   thr;         /* [ld]      object_size * 1.5 (float64), :293 */
+    float*    damp;        /* [ld]      float32(1.0 - friction * 0.1 * dt), :215-216 */
+    int32_t*  step_count;  /* [ld]      :173,247 */
+    uint8_t*  cmask;       /* [ld]      bit f = finger f in contact after the last step (RewardShaping.prev_contacts) */
+    double*   size;        /* [ld]      info["curriculum"]["object_size"], :273 */
+    double*   mass;        /* [ld]      info["curriculum"]["object_mass"], :274 */
+    double*   friction;    /* [ld]      info["curriculum"]["friction_coefficient"], :275 */
+    uint32_t* episode;     /* [ld]      episodes finished by this env (Philox counter word) */
+    double*   ep_return;   /* [ld]      running episode return (float64 like evaluator.py:144); NULL = not tracked */
+    uint32_t* ep_stats;    /* [2, ld]   packed contact-count history summary; NULL = not tracked */
+} DexsimState;
+
+/* Scalars of one DexterousManipulationEnv construction + the batched env's own switches. */
+typedef struct DexsimParams {
+    double   w_distance, w_contact, w_closure, w_stability; /* rewards/reward_shaping.py:20-25 */
+    int32_t  reward_type;            /* 0 sparse (rewards/reward_shaping.py:190), 1 dense (:12) */
+    int32_t  max_episode_steps;      /* envs/manipulation_env.py:28 */
+    int32_t  success_threshold;      /* 3, envs/manipulation_env.py:336 */
+    int32_t  auto_reset;             /* 1: an env that finishes an episode is reset in the same launch */
+    int32_t  respawn;                /* auto-reset mode: 1 fresh env (evaluator.py:91), 0 reused env keeps position (:160-161) */
+    int32_t  success_is_terminated;  /* 1: evaluator.py:156-158; 0: episode_utils.py:52 (always False) */
+    int32_t  loop_max_steps;         /* caller's loop bound (evaluator.py:135, episode_utils.py:38); <=0: none */
+    int32_t  num_groups;             /* rows of the group table */
+    uint64_t seed;                   /* Philox key */
+    int64_t  env_gid0;               /* global id of env 0 of this shard (multi-GPU: rank offset) */
+} DexsimParams;
+
+/* One CurriculumConfig (experiments/config.py:17-42) + one robustness cell's noise levels
+ * (evaluation/robustness_tests.py:145-164).  Staged in shared memory by the kernels. */
+typedef struct DexsimGroup {
+    double  size, mass, friction;
+    double  size_lo, size_hi;  int32_t size_ranged;  int32_t pad0_;
+    double  mass_lo, mass_hi;  int32_t mass_ranged;  int32_t pad1_;
+    double  fric_lo, fric_hi;  int32_t fric_ranged;  int32_t pad2_;
+    double  spawn_lo[3], spawn_hi[3];
+    float   sigma_obs, sigma_dyn;
+} DexsimGroup;
+
+/* Inputs / outputs of one batched step (all device pointers, SoA with the state's ld). */
+typedef struct DexsimStepIO {
+    const float* action;        /* [15, ld] (layout 0) or [n, 15] (layout 1); required for dexsim_step */
+    int32_t      action_layout; /* 0 = SoA [15, ld], 1 = AoS [n, 15] (the reference's per-env layout) */
+    int32_t      pad_;
+    const float* dyn_noise;     /* [15, ld] pre-drawn float32 N(0, sigma_dyn) or NULL (robustness_tests.py:180-187) */
+    const float* obs_noise;     /* [45, ld] pre-drawn float32 N(0, sigma_obs) or NULL (:204-205) */
+    float*       noisy_obs;     /* [45, ld] out: obs + noise; required iff obs noise is on */
+    float*       reward;        /* [ld] out, float32(total) */
+    float*       reward_comps;  /* [4, ld] out (distance, contact, closure, stability) or NULL */
+    uint8_t*     terminated;    /* [ld] out 0/1 */
+    uint8_t*     truncated;     /* [ld] out 0/1 */
+    uint8_t*     num_contacts;  /* [ld] out 0..5, info["num_contacts"] */
+    uint8_t*     finished;      /* [ld] out 0/1: episode ended this step and the env was auto-reset; or NULL */
+    int64_t*     counters;      /* [num_groups, DEXSIM_NCOUNTERS] accumulated; or NULL */
+    double*      ret_sums;      /* [num_groups, 2] sum and sum of squares of episode returns; or NULL */
+} DexsimStepIO;
+
+/* ---- library ---------------------------------------------------------------------------- */
+int         dexsim_version(void);            /* DEXSIM_ABI_VERSION */
+const char* dexsim_error_string(int code);
+int         dexsim_sizeof_state(void);
+int         dexsim_sizeof_params(void);
+int         dexsim_sizeof_group(void);
+int         dexsim_sizeof_step_io(void);
+/* SM count and max resident CTAs per SM of the step kernel on the current device */
+int         dexsim_device_info(int* sm_count, int* step_ctas_per_sm, int* rollout_ctas_per_sm);
+
+/* ---- reset: replaces DexterousManipulationEnv.reset, envs/manipulation_env.py:124-182 ------ */
+/* Host-sampled draws (exactly the reference's PCG64 draws when the Python face samples them):
+ * jp0 [15, ld]; size/mass/friction [ld] float64; pos [3, ld] float32 or NULL = keep the current
+ * position cast to float32 (:160-161).  mask [ld] 0/1 or NULL = all envs. */
+int dexsim_reset_predrawn(const DexsimState* st, const DexsimParams* p, const uint8_t* mask,
+                          const float* jp0, const double* size, const double* mass,
+                          const double* friction, const float* pos, void* stream);
+/* Device-sampled draws: Philox4x32-10 keyed by p->seed, counter (env gid, episode, 0, stream 0),
+ * same draw order and distributions as :143-161 + experiments/config.py:44-113. */
+int dexsim_reset_philox(const DexsimState* st, const DexsimParams* p, const DexsimGroup* groups,
+                        const uint16_t* group_of_env, const uint8_t* mask, int32_t respawn,
+                        void* stream);
+
+/* ---- step: replaces DexterousManipulationEnv.step, envs/manipulation_env.py:184-252,
+ *      RewardShaping.compute / SparseReward.compute (rewards/reward_shaping.py:50-99,205-242)
+ *      and CombinedNoiseWrapper.step (evaluation/robustness_tests.py:177-207) ---------------- */
+int dexsim_step(const DexsimState* st, const DexsimParams* p, const DexsimGroup* groups,
+                const uint16_t* group_of_env, const DexsimStepIO* io, void* stream);
+
+/* ---- fused rollout: replaces the caller loops training/episode_utils.py:42-53,
+ *      evaluation/evaluator.py:135-158, evaluation/robustness_tests.py:292-304 with the policy
+ *      (policies/random_policy.py:40 / policies/heuristic_policy.py:55-62) generated in-kernel.
+ *      k_steps env-steps per env in ONE launch, state in registers, episodes auto-reset. ------ */
+int dexsim_rollout(const DexsimState* st, const DexsimParams* p, const DexsimGroup* groups,
+                   const uint16_t* group_of_env, int32_t k_steps, int32_t policy_kind,
+                   const float* actions /* [k, 15, ld] for DEXSIM_POLICY_EXTERNAL, else NULL */,
+                   const float* dyn_noise /* [k, 15, ld] pre-drawn, or NULL = Philox when sigma_dyn > 0 */,
+                   int64_t* counters /* [num_groups, DEXSIM_NCOUNTERS] */,
+                   double* ret_sums /* [num_groups, 2] or NULL */, void* stream);
+
+/* ---- RNG exposure (so tests can pre-draw exactly what the fused kernels draw) ---------------- */
+int dexsim_fill_policy_actions(const DexsimState* st, const DexsimParams* p, int32_t policy_kind,
+                               float* actions /* [15, ld] for each env's CURRENT (episode, step) */,
+                               void* stream);
+int dexsim_fill_normal(const DexsimState* st, const DexsimParams* p, int32_t rng_stream /* 2 dyn, 3 obs */,
+                       int32_t rows /* 15 or 45 */, float sigma, float* out /* [rows, ld] */, void* stream);
+
+/* ---- failure labels from episode summaries: replaces EvaluationMetrics.classify_failure
+ *      (evaluation/metrics.py:39-96) and FailureClassifier.classify
+ *      (evaluation/failure_taxonomy.py:156-239).  HOST function (pure integer/IEEE arithmetic). -- */
+typedef struct DexsimEpisodeSummary {
+    int32_t success, episode_steps, num_contacts, final_contacts;
+    int32_t hist_len;          /* len(contact_history) */
+    int32_t max_count, sum_counts, sum_sq_counts;
+    int32_t first5_sum, last5_sum;
+} DexsimEpisodeSummary;
+int dexsim_classify_summary(const DexsimEpisodeSummary* s, int32_t max_steps, int32_t success_threshold,
+                            int32_t* label_metrics, int32_t* label_taxonomy, int32_t* var_tie);
+
+/* ---- host-buffer step (end-to-end path): actions in HOST memory -> device -> step ->
+ *      obs / reward / flags back to HOST memory, synchronous on return.  Pinned buffers make the
+ *      copies asynchronous DMA; pageable buffers work but stage through the driver. ------------- */
+int dexsim_step_host(const DexsimState* st, const DexsimParams* p, const DexsimGroup* groups,
+                     const uint16_t* group_of_env, const DexsimStepIO* io /* device scratch */,
+                     const float* h_action /* host [n, 15] (layout 1) or [15, ld] (layout 0) */,
+                     float* h_obs /* host [45, ld] or NULL */, float* h_reward /* host [ld] */,
+                     uint8_t* h_terminated, uint8_t* h_truncated, uint8_t* h_num_contacts /* host [ld] or NULL */,
+                     void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DEXSIM_H */

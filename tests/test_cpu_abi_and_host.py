@@ -1,0 +1,162 @@
+"""CPU-side checks of the product: the C-ABI library loads and exports every symbol that
+include/dexsim.h declares, struct layouts agree, argument errors are reported without touching
+CUDA, the host-side label entry point matches the reference's classifiers on the golden
+episodes, and the host logic (config -> group table, sharding, counter summaries) is right.
+No compute kernels are launched here."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+import dexterous_rl_manipulation_b200 as dx
+from dexterous_rl_manipulation_b200 import _lib
+
+ROOT = os.path.abspath(os.path.join(os.path.dirname(__file__), ".."))
+
+
+def _header_functions():
+    src = open(os.path.join(ROOT, "include", "dexsim.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(dexsim_[a-z_0-9]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol():
+    names = _header_functions()
+    assert len(names) >= 15
+    L = C.CDLL(_lib.LIB_PATH)
+    for n in names:
+        assert hasattr(L, n), f"{n} declared in include/dexsim.h but not exported"
+    assert sorted(_lib.EXPORTS) == names
+    assert L.dexsim_version() == _lib.ABI_VERSION
+
+
+def test_struct_layouts():
+    L = _lib.lib()
+    assert L.dexsim_sizeof_state() == C.sizeof(_lib.DexsimState) == 14 * 8
+    assert L.dexsim_sizeof_params() == C.sizeof(_lib.DexsimParams)
+    assert L.dexsim_sizeof_group() == C.sizeof(_lib.DexsimGroup) == 152
+    assert L.dexsim_sizeof_step_io() == C.sizeof(_lib.DexsimStepIO)
+
+
+def test_argument_errors_without_cuda():
+    L = _lib.lib()
+    st, p, io = _lib.DexsimState(), _lib.DexsimParams(), _lib.DexsimStepIO()
+    assert L.dexsim_step(None, C.byref(p), None, None, C.byref(io), None) == -1001
+    st.n, st.ld = 10, 8
+    assert L.dexsim_step(C.byref(st), C.byref(p), None, None, C.byref(io), None) == -1002     # ld < n
+    st.n, st.ld = 10, 48
+    assert L.dexsim_step(C.byref(st), C.byref(p), None, None, C.byref(io), None) == -1002     # ld % 32
+    st.ld = 32
+    assert L.dexsim_step(C.byref(st), C.byref(p), None, None, C.byref(io), None) == -1001     # NULL arrays
+    assert L.dexsim_rollout(C.byref(st), C.byref(p), None, None, 0, 1, None, None, None, None, None) == -1001
+    assert b"NULL" in L.dexsim_error_string(-1001) and b"size" in L.dexsim_error_string(-1002)
+    with pytest.raises(dx.DexsimError):
+        _lib.check(-1004, "x")
+    with pytest.raises(dx.DexsimError):
+        dx.BatchedManipulationEnv(4, num_fingers=4)                   # unsupported geometry
+    with pytest.raises(RuntimeError):
+        dx.BatchedManipulationEnv(4, device="cpu")                    # no CPU path
+
+
+def _summary(counts):
+    c = np.asarray(counts, np.int64)
+    n = len(c)
+    return dict(hist_len=n, max_count=int(c.max()) if n else 0, sum_counts=int(c.sum()), sum_sq_counts=int((c * c).sum()),
+                first5_sum=int(c[:5].sum()), last5_sum=int(c[-5:].sum()) if n else 0)
+
+
+def test_summary_classifier_matches_reference_labels(golden_dir):
+    """dexsim_classify_summary (the arithmetic the kernels run at episode end) vs labels produced
+    by the unmodified reference classifiers; exact variance ties must be flagged, not guessed."""
+    with np.load(os.path.join(golden_dir, "labels.npz")) as z:
+        g = {k: z[k] for k in z.files}
+    ties = mism = 0
+    for i in range(g["length"].shape[0]):
+        c = g["counts"][i, :g["length"][i]]
+        a, b, tie = dx.classify_summary(g["success"][i], g["steps"][i], g["num"][i], g["final"][i],
+                                        max_steps=int(g["max_steps"]), **_summary(c))
+        ea = 255 if g["label_metrics"][i] < 0 else int(g["label_metrics"][i])
+        eb = 255 if g["label_taxonomy"][i] < 0 else int(g["label_taxonomy"][i])
+        if tie:
+            ties += 1
+            continue
+        mism += (a, b) != (ea, eb)
+    assert mism == 0
+    assert ties < 0.05 * g["length"].shape[0]
+
+
+def test_summary_classifier_known_answers(golden_dir):
+    import json
+    with open(os.path.join(golden_dir, "anchors.json")) as fh:
+        anchors = json.load(fh)
+    for ka in anchors["known_answers"]:
+        a, b, _ = dx.classify_summary(False, ka["episode_steps"], ka["num_contacts"], ka["final_contacts"],
+                                      **_summary(ka["counts"]))
+        if "metrics" in ka:
+            assert dx.LABELS_METRICS[a] in ka["metrics"], ka["src"]
+        if "taxonomy" in ka:
+            assert dx.LABELS_TAXONOMY[b] in ka["taxonomy"], ka["src"]
+
+
+def test_trend_tie_uses_ieee_division():
+    # first5 = 11, last5 = 6 gives 6/5 - 11/5 = -1.0000000000000002 < -1.0 (True),
+    # although (6 - 11)/5 == -1 exactly; an integer restatement would get this wrong.
+    counts = [3, 2, 2, 2, 2] + [1] * 6 + [2, 1, 1, 1, 1]
+    assert sum(counts[:5]) == 11 and sum(counts[-5:]) == 6
+    a, b, tie = dx.classify_summary(False, 50, 1, 1, **_summary(counts))
+    assert dx.LABELS_METRICS[a] == "slippage" and dx.LABELS_TAXONOMY[b] == "slippage"
+
+
+def test_group_table_from_configs():
+    CC = dx.CurriculumConfig
+    cfg = CC(object_size_range=(0.03, 0.07), friction_range=(0.3, 0.7))
+    t = dx.group_table([CC.easy(), cfg], sigma_obs=[0.0, 0.05], sigma_dyn=0.1)
+    assert (t[0].size, t[0].mass, t[0].friction, t[0].size_ranged) == (0.08, 0.05, 0.8, 0)
+    assert (t[1].size_ranged, t[1].mass_ranged, t[1].fric_ranged) == (1, 0, 1)
+    assert (t[1].size_lo, t[1].size_hi, t[1].fric_lo, t[1].fric_hi) == (0.03, 0.07, 0.3, 0.7)
+    assert list(t[1].spawn_lo) == [-0.1, -0.1, 0.05] and list(t[1].spawn_hi) == [0.1, 0.1, 0.2]
+    assert abs(t[1].sigma_obs - 0.05) < 1e-9 and abs(t[0].sigma_dyn - 0.1) < 1e-7
+    with pytest.raises(ValueError):
+        dx.group_table([])
+
+
+def test_curriculum_config_presets_and_samplers():
+    CC = dx.CurriculumConfig
+    assert (CC.easy().object_size, CC.medium().object_mass, CC.hard().friction_coefficient) == (0.08, 0.1, 0.3)
+    rng = np.random.Generator(np.random.PCG64(np.random.SeedSequence(7)))
+    twin = np.random.Generator(np.random.PCG64(np.random.SeedSequence(7)))
+    cfg = CC(object_size_range=(0.03, 0.07), object_mass_range=(0.05, 0.15), friction_range=(0.3, 0.7))
+    got = (cfg.get_object_size(rng), cfg.get_object_mass(rng), cfg.get_friction_coefficient(rng), cfg.get_spawn_position(rng))
+    exp = (float(twin.uniform(0.03, 0.07)), float(twin.uniform(0.05, 0.15)), float(twin.uniform(0.3, 0.7)),
+           (float(twin.uniform(-0.1, 0.1)), float(twin.uniform(-0.1, 0.1)), float(twin.uniform(0.05, 0.2))))
+    assert got == exp
+    fixed = CC.hard()
+    state = rng.bit_generator.state
+    assert fixed.get_object_size(rng) == 0.03 and rng.bit_generator.state == state      # no draw when not ranged
+    assert CC.from_dict(cfg.to_dict()) == cfg
+
+
+def test_shard_ranges_cover_and_balance():
+    for N in (0, 1, 7, 4096, 1_048_576, 1_000_003):
+        for W in (1, 2, 3, 4, 8):
+            r = [dx.distributed.shard_range(N, k, W) for k in range(W)]
+            assert r[0][0] == 0 and r[-1][1] == N
+            assert all(r[k][1] == r[k + 1][0] for k in range(W - 1))
+            sizes = [hi - lo for lo, hi in r]
+            assert max(sizes) - min(sizes) <= 1
+
+
+def test_summarize_counters_schema():
+    import torch
+    c = torch.zeros(2, dx.NCOUNTERS, dtype=torch.int64)
+    c[0, dx.CNT_EPISODES], c[0, dx.CNT_SUCCESSES], c[0, dx.CNT_SUM_STEPS], c[0, dx.CNT_SUM_STEPS_SQ] = 10, 6, 500, 30000
+    c[0, dx.CNT_LABEL_METRICS + 3] = 4
+    rs = torch.tensor([[20.0, 50.0], [0.0, 0.0]], dtype=torch.float64)
+    m = dx.distributed.summarize_counters(c, rs)
+    assert m[1] == {}
+    assert m[0]["grasp_success_rate"] == 0.6 and m[0]["mean_episode_length"] == 50.0
+    assert m[0]["failure_type_frequency"]["timeout"] == {"count": 4, "frequency": 0.4}
+    assert m[0]["failed_episodes"] == 4 and m[0]["mean_reward"] == 2.0
+    assert abs(m[0]["std_episode_length"] - (3000 - 2500) ** 0.5) < 1e-9
