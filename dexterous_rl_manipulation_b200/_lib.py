@@ -7,7 +7,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libdexsim_b200.so")
+LIB_PATH = os.environ.get("DEXSIM_LIB_PATH") or os.path.join(HERE, "libdexsim_b200.so")   # env override: kernel experiments only
 
 ABI_VERSION = 1
 NJ, NF, OBS = 15, 5, 45
@@ -69,7 +69,7 @@ class DexsimEpisodeSummary(C.Structure):
 
 EXPORTS = (
     "dexsim_version", "dexsim_error_string", "dexsim_sizeof_state", "dexsim_sizeof_params",
-    "dexsim_sizeof_group", "dexsim_sizeof_step_io", "dexsim_device_info", "dexsim_reset_predrawn",
+    "dexsim_sizeof_group", "dexsim_sizeof_step_io", "dexsim_device_info", "dexsim_set_step_impl", "dexsim_reset_predrawn",
     "dexsim_reset_philox", "dexsim_step", "dexsim_rollout", "dexsim_fill_policy_actions",
     "dexsim_fill_normal", "dexsim_classify_summary", "dexsim_step_host",
 )
@@ -101,6 +101,7 @@ def lib():
     for name in ("dexsim_sizeof_state", "dexsim_sizeof_params", "dexsim_sizeof_group", "dexsim_sizeof_step_io"):
         getattr(L, name).restype = C.c_int
     L.dexsim_device_info.argtypes = [C.POINTER(C.c_int)] * 3
+    L.dexsim_set_step_impl.argtypes = [C.c_int]
     L.dexsim_reset_predrawn.argtypes = [C.POINTER(DexsimState), C.POINTER(DexsimParams), vp, vp, vp, vp, vp, vp, vp]
     L.dexsim_reset_philox.argtypes = [C.POINTER(DexsimState), C.POINTER(DexsimParams), vp, vp, vp, i32, vp]
     L.dexsim_step.argtypes = [C.POINTER(DexsimState), C.POINTER(DexsimParams), vp, vp, C.POINTER(DexsimStepIO), vp]
@@ -124,6 +125,12 @@ def lib():
     _ = i64
     _lib = L
     return L
+
+
+def set_step_impl(impl):
+    """'auto' | 'register' | 'tma' -- which step kernel dexsim_step launches (tests / profiling)."""
+    code = {"auto": 0, "register": 1, "tma": 2}[impl]
+    check(lib().dexsim_set_step_impl(code), "dexsim_set_step_impl")
 
 
 def check(code, where):

@@ -10,12 +10,16 @@
 //   reset_*_kernel   episode (re)initialisation from pre-drawn or Philox draws.
 // No CPU fallback exists: every entry point launches CUDA work or returns an error code.
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 #include "dexsim_core.cuh"
 
 namespace dexsim {
 
+#ifndef DEXSIM_STEP_MIN_BLOCKS
+#define DEXSIM_STEP_MIN_BLOCKS 2
+#endif
 constexpr int STEP_THREADS = 256;
 constexpr int SMEM_GROUPS_MAX = 64;     // group table + block counters are staged in smem up to this many groups
 
@@ -141,16 +145,34 @@ __device__ __forceinline__ void finish_and_reset(EnvRegs& e, const DexsimParams&
     es.w0 = 0u; es.w1 = 0u;
 }
 
+}  // namespace dexsim
+
+#include "dexsim_step_tma.cuh"
+
+namespace dexsim {
+
 // ---- step kernel -----------------------------------------------------------------------------------
 // DENSE: reward type.  AOS: action is [n, 15] (reference layout) and is transposed through shared
 // memory with coalesced float4 reads (15 is odd, so the per-thread reads are bank-conflict free).
 // EXTRAS: noise, reward components, episode tracking, auto-reset -- the plain path carries none
 // of their registers or branches.
 template <bool DENSE, bool AOS, bool EXTRAS>
-__global__ void __launch_bounds__(STEP_THREADS, 2)
+__global__ void __launch_bounds__(STEP_THREADS, DEXSIM_STEP_MIN_BLOCKS)
 step_kernel(const DexsimState st, const DexsimParams p, const DexsimGroup* __restrict__ groups,
             const uint16_t* __restrict__ group_of_env, const DexsimStepIO io) {
     __shared__ __align__(16) float sh_act[AOS ? STEP_THREADS * NJ : 4];
+    // Finished episodes are counted per CTA in shared memory and flushed with one global atomic per
+    // non-zero counter at the end: thousands of episodes end per step and would otherwise serialise
+    // on the same 18 L2 addresses.
+    __shared__ unsigned long long sh_cnt[EXTRAS ? SMEM_GROUPS_MAX * DEXSIM_NCOUNTERS : 1];
+    __shared__ double sh_rs[EXTRAS ? SMEM_GROUPS_MAX * 2 : 1];
+    const bool count_episodes = EXTRAS && p.auto_reset && io.counters != nullptr && st.ep_return != nullptr;
+    const bool staged = count_episodes && p.num_groups <= SMEM_GROUPS_MAX;
+    if (EXTRAS && staged) {
+        for (int w = threadIdx.x; w < p.num_groups * DEXSIM_NCOUNTERS; w += STEP_THREADS) sh_cnt[w] = 0ull;
+        for (int w = threadIdx.x; w < p.num_groups * 2; w += STEP_THREADS) sh_rs[w] = 0.0;
+        __syncthreads();
+    }
     const int64_t n = st.n, ld = st.ld;
     for (int64_t base = (int64_t)blockIdx.x * STEP_THREADS; base < n; base += (int64_t)gridDim.x * STEP_THREADS) {
         const int64_t i = base + threadIdx.x;
@@ -224,9 +246,12 @@ step_kernel(const DexsimState st, const DexsimParams p, const DexsimGroup* __res
             const int g = group_index(group_of_env, i, gid, p.num_groups);
             uint32_t episode = st.episode[i];
             double size, mass, friction;
-            unsigned long long* cnt = (io.counters && tracking)
-                ? reinterpret_cast<unsigned long long*>(io.counters) + (int64_t)g * DEXSIM_NCOUNTERS : nullptr;
-            double* rs = io.ret_sums ? io.ret_sums + 2 * g : nullptr;
+            unsigned long long* cnt = nullptr;
+            double* rs = nullptr;
+            if (count_episodes) {
+                cnt = (staged ? sh_cnt : reinterpret_cast<unsigned long long*>(io.counters)) + (int64_t)g * DEXSIM_NCOUNTERS;
+                if (io.ret_sums) rs = (staged ? sh_rs : io.ret_sums) + 2 * g;
+            }
             finish_and_reset(e, p, groups[g], (uint32_t)gid, episode, ep_return, es, r.terminated, r.n_c,
                              cnt, rs, size, mass, friction);
             st.episode[i] = episode;
@@ -261,6 +286,15 @@ step_kernel(const DexsimState st, const DexsimParams p, const DexsimGroup* __res
                 out[(DEXSIM_ROW_CONTACT + f) * ld + i] =
                     __fadd_rn(((e.cmask >> f) & 1u) ? 1.0f : 0.0f, __ldg(nz + (DEXSIM_ROW_CONTACT + f) * ld + i));
         }
+    }
+    if (EXTRAS && staged) {
+        __syncthreads();
+        unsigned long long* gc = reinterpret_cast<unsigned long long*>(io.counters);
+        for (int w = threadIdx.x; w < p.num_groups * DEXSIM_NCOUNTERS; w += STEP_THREADS)
+            if (sh_cnt[w]) atomicAdd(&gc[w], sh_cnt[w]);
+        if (io.ret_sums)
+            for (int w = threadIdx.x; w < p.num_groups * 2; w += STEP_THREADS)
+                if (sh_rs[w] != 0.0) atomicAdd(&io.ret_sums[w], sh_rs[w]);
     }
 }
 
@@ -503,6 +537,72 @@ static void launch_step_variant(bool extras, int grid, cudaStream_t s, const Dex
     else        step_kernel<DENSE, AOS, false><<<grid, STEP_THREADS, 0, s>>>(st, p, groups, goe, io);
 }
 
+template <bool DENSE, bool AOS, bool TRACK, int STAGES>
+static int launch_tma_variant(int sm_count, cudaStream_t s, const DexsimState& st, const DexsimParams& p,
+                              const DexsimGroup* groups, const uint16_t* goe, const DexsimStepIO& io,
+                              const StepMaps& maps, int num_tiles) {
+    auto kern = step_tma_kernel<DENSE, AOS, TRACK, STAGES>;
+    const size_t smem = (size_t)STAGES * STAGE_BYTES + 2 * STAGES * sizeof(uint64_t) +
+                        (TRACK ? TMA_GROUPS_MAX * (DEXSIM_NCOUNTERS * sizeof(unsigned long long) + 2 * sizeof(double)) : 0);
+    static thread_local int ctas_per_sm = 0;        // per template instantiation
+    if (ctas_per_sm == 0) {
+        cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (err != cudaSuccess) return -(int)err;
+        err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, kern, TMA_THREADS, smem);
+        if (err != cudaSuccess) return -(int)err;
+        if (ctas_per_sm < 1) ctas_per_sm = 1;
+    }
+    int grid = sm_count * ctas_per_sm;
+    if (grid > num_tiles) grid = num_tiles;
+    kern<<<grid, TMA_THREADS, smem, s>>>(st, p, groups, goe, io, maps, num_tiles);
+    return cuda_rc(cudaGetLastError());
+}
+
+// 0 = auto (TMA pipeline when eligible), 1 = register-resident kernel only, 2 = TMA pipeline required.
+// Initialised from DEXSIM_STEP_IMPL (v1 | v2), changeable at run time with dexsim_set_step_impl().
+static int g_step_impl = -1;
+static int step_impl_choice() {
+    if (g_step_impl < 0) {
+        const char* e = getenv("DEXSIM_STEP_IMPL");
+        g_step_impl = (e && !strcmp(e, "v1")) ? 1 : (e && !strcmp(e, "v2")) ? 2 : 0;
+    }
+    return g_step_impl;
+}
+static int tma_stage_choice() {
+    static int stages = -1;
+    if (stages < 0) {
+        const char* e = getenv("DEXSIM_TMA_STAGES");
+        stages = (e && atoi(e) == 3) ? 3 : 2;
+    }
+    return stages;
+}
+
+static int launch_step_tma(const DexsimState* st, const DexsimParams* p, const DexsimGroup* groups, const uint16_t* goe,
+                           const DexsimStepIO* io, cudaStream_t s, bool track, int sm_count) {
+    StepMaps maps;
+    memset(&maps, 0, sizeof(maps));
+    const bool aos = io->action_layout == 1;
+    bool ok = make_map_2d(&maps.obs_jpjv, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, st->obs, st->n, st->ld, DEXSIM_OBS, 30) &&
+              make_map_2d(&maps.obs_ov, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, st->obs, st->n, st->ld, DEXSIM_OBS, 3) &&
+              make_map_2d(&maps.op64, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 8, st->op64, st->n, st->ld, 3, 3);
+    if (ok && !aos)
+        ok = make_map_2d(&maps.act_soa, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(io->action), st->n, st->ld, NJ, NJ);
+    if (!ok) return 1;                               // caller falls back to the register-resident kernel
+    const int num_tiles = (int)((st->n + TILE - 1) / TILE);
+    const bool dense = p->reward_type == 1;
+    const int stages = tma_stage_choice();
+#define DEXSIM_TMA_CASE(D, A, T)                                                                              \
+    if (dense == D && aos == A && track == T)                                                                 \
+        return stages == 3 ? launch_tma_variant<D, A, T, 3>(sm_count, s, *st, *p, groups, goe, *io, maps, num_tiles) \
+                           : launch_tma_variant<D, A, T, 2>(sm_count, s, *st, *p, groups, goe, *io, maps, num_tiles);
+    DEXSIM_TMA_CASE(true, true, true) DEXSIM_TMA_CASE(true, true, false)
+    DEXSIM_TMA_CASE(true, false, true) DEXSIM_TMA_CASE(true, false, false)
+    DEXSIM_TMA_CASE(false, true, true) DEXSIM_TMA_CASE(false, true, false)
+    DEXSIM_TMA_CASE(false, false, true) DEXSIM_TMA_CASE(false, false, false)
+#undef DEXSIM_TMA_CASE
+    return 1;
+}
+
 static int launch_step(const DexsimState* st, const DexsimParams* p, const DexsimGroup* groups,
                        const uint16_t* goe, const DexsimStepIO* io, cudaStream_t s) {
     int rc = check_state(st);
@@ -518,6 +618,23 @@ static int launch_step(const DexsimState* st, const DexsimParams* p, const Dexsi
     DeviceInfo di;
     rc = device_info_cached(di);
     if (rc) return rc;
+    // TMA pipeline: everything except the noise / reward-component outputs; needs 16-byte aligned bases
+    const int impl = step_impl_choice();
+    const bool track = extras;
+    const bool tma_ok = !io->dyn_noise && !io->obs_noise && !io->reward_comps && (!track || st->ep_return != nullptr) &&
+                        st->n >= TILE && st->n < (int64_t)0x7FFFFF00 &&
+                        !(reinterpret_cast<uintptr_t>(io->action) & 15u) && !(reinterpret_cast<uintptr_t>(io->reward) & 15u) &&
+                        !(reinterpret_cast<uintptr_t>(st->thr) & 15u) && !(reinterpret_cast<uintptr_t>(st->damp) & 15u) &&
+                        !(reinterpret_cast<uintptr_t>(st->step_count) & 15u) && !(reinterpret_cast<uintptr_t>(st->cmask) & 15u) &&
+                        !(reinterpret_cast<uintptr_t>(io->terminated) & 15u) && !(reinterpret_cast<uintptr_t>(io->truncated) & 15u) &&
+                        !(reinterpret_cast<uintptr_t>(io->num_contacts) & 15u) &&
+                        (!track || (!(reinterpret_cast<uintptr_t>(st->ep_return) & 15u) && !(reinterpret_cast<uintptr_t>(st->ep_stats) & 15u) &&
+                                    !(reinterpret_cast<uintptr_t>(io->finished) & 15u)));
+    if (impl != 1 && tma_ok) {
+        rc = launch_step_tma(st, p, groups, goe, io, s, track, di.sm_count);
+        if (rc <= 0) return rc;                      // launched (0) or CUDA error (< 0); 1 = not available
+    }
+    if (impl == 2) return DEXSIM_E_PARAM;            // TMA pipeline was demanded but is not eligible
     const int grid = grid_for(st->n, STEP_THREADS, di.step_ctas, di.sm_count);
     const bool dense = p->reward_type == 1, aos = io->action_layout == 1;
     if (dense) { if (aos) launch_step_variant<true, true>(extras, grid, s, *st, *p, groups, goe, *io);
@@ -548,6 +665,12 @@ const char* dexsim_error_string(int code) {
     }
     if (code < 0 && code > -1000) return cudaGetErrorString((cudaError_t)(-code));
     return "dexsim: unknown error code";
+}
+
+int dexsim_set_step_impl(int impl) {
+    if (impl < 0 || impl > 2) return DEXSIM_E_PARAM;
+    g_step_impl = impl;
+    return 0;
 }
 
 int dexsim_sizeof_state(void) { return (int)sizeof(DexsimState); }

@@ -24,18 +24,15 @@ import torch
 from ._lib import CNT_EPISODES, CNT_SUCCESSES, CNT_SUM_STEPS
 
 
+def spread_flag(k: int, episodes: int, successes: int) -> bool:
+    """Element k of the length-``episodes`` boolean sequence that spreads ``successes`` Trues evenly
+    (Bresenham): the deterministic stand-in for the unknowable order of parallel episodes.  O(1),
+    so a poll never materialises millions of flags."""
+    return ((k + 1) * successes) // episodes > (k * successes) // episodes
+
+
 def spread_successes(episodes: int, successes: int):
-    """Boolean sequence of length ``episodes`` with ``successes`` Trues spread evenly
-    (Bresenham); deterministic stand-in for the unknowable order of parallel episodes."""
-    out, acc = [], 0
-    for _ in range(episodes):
-        acc += successes
-        if acc >= episodes and successes > 0:
-            acc -= episodes
-            out.append(True)
-        else:
-            out.append(False)
-    return out
+    return [spread_flag(k, episodes, successes) for k in range(episodes)]
 
 
 class BatchedCurriculumDriver:
@@ -52,25 +49,23 @@ class BatchedCurriculumDriver:
         if episodes <= 0:
             return 0
         sch = self.scheduler
-        base, rem = divmod(int(steps), int(episodes))
-        flags = None
+        episodes, successes = int(episodes), int(successes)
+        base, rem = divmod(int(steps), episodes)
         progressed = 0
         k = 0
         if getattr(sch, "current_difficulty_level", 1.0) < 1.0:
-            flags = spread_successes(episodes, successes)
             limit = min(episodes, self.max_sequential_updates)
             while k < limit and sch.current_difficulty_level < 1.0:
-                if sch.update(bool(flags[k]), base + (1 if k < rem else 0)):
+                if sch.update(spread_flag(k, episodes, successes), base + (1 if k < rem else 0)):
                     progressed += 1
                 k += 1
         if k < episodes:
-            # bulk tail: no progression can happen any more (or the sequential budget is spent)
+            # bulk tail: no progression can happen any more (or the sequential budget is spent);
+            # the scheduler's totals stay exact, its per-episode lists get a bounded tail
             rest = episodes - k
-            rest_succ = successes - (sum(flags[:k]) if flags is not None else 0)
             rest_steps = int(steps) - (base * k + min(k, rem))
             keep = min(rest, int(getattr(sch, "window_size", 20)))
-            tail = spread_successes(rest, rest_succ)[-keep:]
-            sch.episode_successes.extend(tail)
+            sch.episode_successes.extend(spread_flag(j, episodes, successes) for j in range(episodes - keep, episodes))
             sch.episode_steps.extend([base] * keep)
             sch.total_steps += rest_steps
             sch.total_episodes += rest

@@ -188,10 +188,19 @@ class BatchedManipulationEnv:
         self._io = _lib.DexsimStepIO()
         self._refresh_structs()
         self._sync_groups()
-        # persistent output views (batch first)
+        # persistent output views (batch first) and ctypes references for the allocation-free hot path
         self._obs_view = self._obs[:, :n].t()
         self._info = None
         self._did_reset = False
+        self._n15 = n * 15
+        self._noisy_env = self.observation_noise_std > 0.0 or self.dynamics_noise_std > 0.0
+        self._io_has_noise = False
+        self._state_ref, self._params_ref, self._io_ref = C.byref(self._state), C.byref(self._params), C.byref(self._io)
+        self._goe_ptr = self._ptr(self._goe)
+        self._step_out = None
+        if not self.single:
+            self._step_out = (self._obs_view, self._reward[:n], self._terminated[:n].view(torch.bool),
+                              self._truncated[:n].view(torch.bool), self._make_info())
 
     # ------------------------------------------------------------------ plumbing
     @staticmethod
@@ -240,6 +249,7 @@ class BatchedManipulationEnv:
         if group_of_env is not None:
             self._goe = torch.zeros(self.ld, dtype=torch.int16, device=self.device)
             self._goe[:self.num_envs] = torch.as_tensor(group_of_env).to(torch.int16).to(self.device)
+            self._goe_ptr = self._goe.data_ptr()
         self._groups_dirty = True
 
     @property
@@ -264,6 +274,7 @@ class BatchedManipulationEnv:
             self.ret_sums = torch.zeros(G, 2, dtype=torch.float64, device=self.device)
         self._params.num_groups = G
         self._io.counters, self._io.ret_sums = self._ptr(self.counters), self._ptr(self.ret_sums)
+        self._groups_ptr = self._groups_dev.data_ptr()
         self._groups_dirty = False
 
     def _stream(self):
@@ -430,47 +441,76 @@ class BatchedManipulationEnv:
         them, ``dynamics_noise_std`` / ``observation_noise_std`` > 0 draw Philox normals on the device."""
         if not self._did_reset:
             raise RuntimeError("call reset() before step()")
-        with torch.cuda.device(self.device):
+        if self._groups_dirty:
             self._sync_groups()
+        plain = (dyn_noise is None and obs_noise is None and not self._noisy_env and not self.single
+                 and isinstance(action, torch.Tensor) and action.is_cuda and action.dtype is torch.float32
+                 and action.is_contiguous() and action.numel() == self._n15 and not (action.data_ptr() & 15))
+        if plain and torch.cuda.current_device() == self.device.index:
+            # hot path: one ctypes call, persistent output views, no allocation
             io = self._io
-            a = self._ingest_action(action)
-            io.action, io.action_layout = a.data_ptr(), 1
-            keep = [a]
-            want_dyn = dyn_noise is not None or self.dynamics_noise_std > 0.0
-            want_obs = obs_noise is not None or self.observation_noise_std > 0.0
-            io.dyn_noise = io.obs_noise = io.noisy_obs = None
-            if want_dyn or want_obs:
-                self._noise_buffers()
-            if want_dyn:
-                if dyn_noise is not None:
-                    dn = self._soa(dyn_noise, 15)
-                else:
-                    dn = self._dyn_noise
-                    _lib.check(self._lib.dexsim_fill_normal(
-                        C.byref(self._state), C.byref(self._params), _L.RNG_STREAM_DYN, 15,
-                        C.c_float(self.dynamics_noise_std), dn.data_ptr(), self._stream()), "dexsim_fill_normal")
-                io.dyn_noise = dn.data_ptr(); keep.append(dn)
-            if obs_noise is not None:
-                on = self._soa(obs_noise, 45)
-                io.obs_noise, io.noisy_obs = on.data_ptr(), self._noisy_obs.data_ptr()
-                keep.append(on)
-            _lib.check(self._lib.dexsim_step(C.byref(self._state), C.byref(self._params), self._ptr(self._groups_dev),
-                                             self._ptr(self._goe), C.byref(io), self._stream()), "dexsim_step")
-            if want_obs and obs_noise is None:
-                # Philox observation noise is keyed by (episode, step count AFTER the step), so it is
-                # drawn once the step has run (evaluation/robustness_tests.py:204-205)
+            io.action, io.action_layout = action.data_ptr(), 1
+            if self._io_has_noise:
+                io.dyn_noise = io.obs_noise = io.noisy_obs = None
+                self._io_has_noise = False
+            rc = self._lib.dexsim_step(self._state_ref, self._params_ref, self._groups_ptr, self._goe_ptr,
+                                       self._io_ref, torch.cuda.current_stream().cuda_stream)
+            if rc:
+                raise _lib.DexsimError(rc, "dexsim_step")
+            return self._step_out
+        with torch.cuda.device(self.device):
+            return self._step_general(action, dyn_noise, obs_noise)
+
+    def _step_general(self, action, dyn_noise, obs_noise):
+        io = self._io
+        a = self._ingest_action(action)
+        io.action, io.action_layout = a.data_ptr(), 1
+        keep = [a]
+        want_dyn = dyn_noise is not None or self.dynamics_noise_std > 0.0
+        want_obs = obs_noise is not None or self.observation_noise_std > 0.0
+        io.dyn_noise = io.obs_noise = io.noisy_obs = None
+        self._io_has_noise = want_dyn or obs_noise is not None
+        if want_dyn or want_obs:
+            self._noise_buffers()
+        if want_dyn:
+            if dyn_noise is not None:
+                dn = self._soa(dyn_noise, 15)
+            else:
+                dn = self._dyn_noise
                 _lib.check(self._lib.dexsim_fill_normal(
-                    C.byref(self._state), C.byref(self._params), _L.RNG_STREAM_OBS, 45,
-                    C.c_float(self.observation_noise_std), self._obs_noise.data_ptr(), self._stream()), "dexsim_fill_normal")
-                torch.add(self._obs, self._obs_noise, out=self._noisy_obs)
-            obs = self._emit_obs(noisy=want_obs)
-            n = self.num_envs
-            if self.single:
-                vals = torch.stack([self._reward[0].to(torch.float64), self._terminated[0].to(torch.float64),
-                                    self._truncated[0].to(torch.float64)]).cpu().numpy()
-                return obs, float(vals[0]), bool(vals[1]), bool(vals[2]), self._make_info()
-            return (obs, self._reward[:n], self._terminated[:n].view(torch.bool), self._truncated[:n].view(torch.bool),
-                    self._make_info())
+                    self._state_ref, self._params_ref, _L.RNG_STREAM_DYN, 15,
+                    C.c_float(self.dynamics_noise_std), dn.data_ptr(), self._stream()), "dexsim_fill_normal")
+            io.dyn_noise = dn.data_ptr(); keep.append(dn)
+        if obs_noise is not None:
+            on = self._soa(obs_noise, 45)
+            io.obs_noise, io.noisy_obs = on.data_ptr(), self._noisy_obs.data_ptr()
+            keep.append(on)
+        _lib.check(self._lib.dexsim_step(self._state_ref, self._params_ref, self._groups_ptr, self._goe_ptr,
+                                         self._io_ref, self._stream()), "dexsim_step")
+        if want_obs and obs_noise is None:
+            # Philox observation noise is keyed by (episode, step count AFTER the step), so it is
+            # drawn once the step has run (evaluation/robustness_tests.py:204-205)
+            _lib.check(self._lib.dexsim_fill_normal(
+                self._state_ref, self._params_ref, _L.RNG_STREAM_OBS, 45,
+                C.c_float(self.observation_noise_std), self._obs_noise.data_ptr(), self._stream()), "dexsim_fill_normal")
+            torch.add(self._obs, self._obs_noise, out=self._noisy_obs)
+        obs = self._emit_obs(noisy=want_obs)
+        n = self.num_envs
+        if self.single:
+            vals = torch.stack([self._reward[0].to(torch.float64), self._terminated[0].to(torch.float64),
+                                self._truncated[0].to(torch.float64)]).cpu().numpy()
+            return obs, float(vals[0]), bool(vals[1]), bool(vals[2]), self._make_info()
+        return (obs, self._reward[:n], self._terminated[:n].view(torch.bool), self._truncated[:n].view(torch.bool),
+                self._make_info())
+
+    def _step_soa(self, action_soa):
+        """Step with actions already in the device layout [15, ld] (tests / internal callers)."""
+        io = self._io
+        io.action, io.action_layout = action_soa.data_ptr(), 0
+        io.dyn_noise = io.obs_noise = io.noisy_obs = None
+        _lib.check(self._lib.dexsim_step(self._state_ref, self._params_ref, self._groups_ptr, self._goe_ptr,
+                                         self._io_ref, self._stream()), "dexsim_step")
+        return self._step_out
 
     def _emit_obs(self, reset=False, noisy=False):
         n = self.num_envs

@@ -158,6 +158,11 @@ int         dexsim_sizeof_group(void);
 int         dexsim_sizeof_step_io(void);
 /* SM count and max resident CTAs per SM of the step kernel on the current device */
 int         dexsim_device_info(int* sm_count, int* step_ctas_per_sm, int* rollout_ctas_per_sm);
+/* Which step kernel dexsim_step uses: 0 = auto (TMA/mbarrier pipeline when eligible, else the
+ * register-resident kernel), 1 = register-resident only, 2 = TMA pipeline required (dexsim_step
+ * returns DEXSIM_E_PARAM when a call is not eligible).  Both produce identical results; the switch
+ * exists for tests and profiling.  Process-wide. */
+int         dexsim_set_step_impl(int impl);
 
 /* ---- reset: replaces DexterousManipulationEnv.reset, envs/manipulation_env.py:124-182 ------ */
 /* Host-sampled draws (exactly the reference's PCG64 draws when the Python face samples them):

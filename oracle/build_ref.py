@@ -2,7 +2,7 @@
 
 The reference is pure Python, and /root/reference does not exist on the GPU box.  This
 recipe compiles each module from the sources where they lie (read-only) into sourceless
-``.pyc`` files under ``oracle/_ref/`` (git-ignored, shipped with the gpurun snapshot like a
+byte-code files (``*.refbc``) under ``oracle/_ref/`` (git-ignored, shipped with the gpurun snapshot like a
 built ``.so``).  No reference source text is copied into the repository.  ``bench.py --impl
 reference`` and ``cpu_baseline`` import it (under oracle/gym_stub) to time the reference's
 own Python loop on the GPU box's host cores; tests use it to re-validate goldens when present.
@@ -13,6 +13,9 @@ import py_compile
 import shutil
 import sys
 
+# gpurun's snapshot drops *.pyc, so the byte-code files carry their own suffix; oracle/ref_harness.py
+# installs a finder that loads them with importlib's SourcelessFileLoader.
+BC_SUFFIX = ".refbc"
 PACKAGES = ["envs", "rewards", "policies", "experiments", "training", "evaluation"]
 
 
@@ -38,7 +41,7 @@ def main():
                     continue
                 dst_dir = os.path.join(args.out, rel)
                 os.makedirs(dst_dir, exist_ok=True)
-                py_compile.compile(os.path.join(root, f), cfile=os.path.join(dst_dir, f + "c"),
+                py_compile.compile(os.path.join(root, f), cfile=os.path.join(dst_dir, f[:-3] + BC_SUFFIX),
                                    dfile=os.path.join("<reference>", rel, f), doraise=True,
                                    invalidation_mode=py_compile.PycInvalidationMode.UNCHECKED_HASH)
                 n += 1

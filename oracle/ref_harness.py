@@ -5,6 +5,8 @@ Search order: ``/root/reference`` (build container), then ``oracle/_ref`` (byte-
 either exists; nothing in the GPU tests or smoke() requires it.
 """
 import importlib
+import importlib.abc
+import importlib.machinery
 import os
 import sys
 
@@ -14,11 +16,32 @@ _CANDIDATES = ["/root/reference", os.path.join(_HERE, "_ref")]
 _REF_PACKAGES = ("envs", "rewards", "policies", "experiments", "training", "evaluation")
 
 
+BC_SUFFIX = ".refbc"
+
+
 def reference_root():
-    for c in _CANDIDATES:
-        if os.path.isdir(os.path.join(c, "envs")):
-            return c
+    if os.path.isfile(os.path.join(_CANDIDATES[0], "envs", "__init__.py")):
+        return _CANDIDATES[0]
+    if os.path.isfile(os.path.join(_CANDIDATES[1], "envs", "__init__" + BC_SUFFIX)):
+        return _CANDIDATES[1]
     return None
+
+
+class _ByteCodeFinder(importlib.abc.MetaPathFinder):
+    """Resolves the reference's packages from oracle/_ref/**/*.refbc (sourceless byte code)."""
+
+    def __init__(self, root):
+        self.root = root
+
+    def find_spec(self, fullname, path=None, target=None):
+        if fullname.split(".")[0] not in _REF_PACKAGES:
+            return None
+        for entry in ([self.root] if path is None else list(path)):
+            finder = importlib.machinery.FileFinder(entry, (importlib.machinery.SourcelessFileLoader, [BC_SUFFIX]))
+            spec = finder.find_spec(fullname)
+            if spec is not None:
+                return spec
+        return None
 
 
 def available():
@@ -47,8 +70,11 @@ def load():
     except ImportError:
         if _STUB not in sys.path:
             sys.path.insert(0, _STUB)
-    if root not in sys.path:
-        sys.path.insert(0, root)
+    if root == _CANDIDATES[0]:
+        if root not in sys.path:
+            sys.path.insert(0, root)
+    elif not any(isinstance(f, _ByteCodeFinder) for f in sys.meta_path):
+        sys.meta_path.insert(0, _ByteCodeFinder(root))
 
     class _NS:
         pass

@@ -122,15 +122,19 @@ def _random_draws(rng, n, ragged=True):
     return jp0, size, mass, fric, pos
 
 
-@pytest.mark.parametrize("n,dense", [(1, True), (33, False), (1000, True), (4096, True)])
-def test_step_matches_oracle(dx, n, dense):
+@pytest.mark.parametrize("n,dense,comps", [(1, True, True), (33, False, True), (1000, True, True), (4096, True, True),
+                                           (1000, True, False), (4096, False, False), (20000, True, False)])
+def test_step_matches_oracle(dx, n, dense, comps):
     """Ragged batch sizes (1, 33, 1000 are not multiples of the warp / CTA size) vs the oracle."""
     from oracle import oracle
     rng = np.random.default_rng(n)
     jp0, size, mass, fric, pos = _random_draws(rng, n)
     ob = oracle.OracleBatch(n, dense=dense, max_episode_steps=60)
     o0 = ob.reset_predrawn(jp0, size, mass, fric, pos)
-    env = _make_env(dx, n, dense, 60) if n > 1 else None
+    env = None
+    if n > 1:       # comps=False keeps the call eligible for the TMA pipeline kernel (n >= 128)
+        env = dx.BatchedManipulationEnv(n, "cuda", max_episode_steps=60, reward_type="dense" if dense else "sparse",
+                                        reward_components=comps)
     if n == 1:
         env = dx.BatchedManipulationEnv(1, "cuda", max_episode_steps=60, reward_type="dense", reward_components=True)
     g0, _ = env.reset_from_draws(jp0, size, mass, fric, pos)
@@ -369,3 +373,45 @@ def test_unmodified_reference_callers_when_available(dx):
         assert e0["contact_history"] == e1["contact_history"] and e0["final_contacts"] == e1["final_contacts"]
         assert e1["episode_reward"] == pytest.approx(e0["episode_reward"], rel=1e-5)
         assert e0["object_size"] == e1["object_size"] and e0["friction_coefficient"] == e1["friction_coefficient"]
+
+
+@pytest.mark.parametrize("n,track,dense", [(128, False, True), (1000, False, False), (4096 + 77, True, True),
+                                            (65536, True, True), (200_000, False, True)])
+def test_tma_pipeline_equals_register_kernel(dx, n, track, dense):
+    """The TMA/mbarrier step kernel and the register-resident one must agree bit for bit on every
+    array (full and ragged last tiles, AoS and SoA actions, with and without tracking/auto-reset)."""
+    from dexterous_rl_manipulation_b200 import _lib
+    CC = dx.CurriculumConfig
+    kw = dict(max_episode_steps=25, reward_type="dense" if dense else "sparse", seed=3, groups=[CC.easy(), CC.hard()])
+    if track:
+        kw.update(auto_reset=True, respawn=True, loop_max_steps=25, track_episodes=True)
+    envs = {}
+    try:
+        for impl in ("register", "tma"):
+            env = dx.BatchedManipulationEnv(n, "cuda", **kw)
+            env.reset(seed=3)
+            envs[impl] = env
+        gen = torch.Generator(device="cuda").manual_seed(5)
+        soa = torch.zeros(15, envs["tma"].ld, device="cuda")
+        for t in range(60):
+            a = torch.rand(n, 15, device="cuda", generator=gen) * 2.6 - 1.3
+            outs = {}
+            for impl, env in envs.items():
+                _lib.set_step_impl(impl)
+                if t % 2:
+                    soa[:, :n] = a.t()
+                    o = env._step_soa(soa)
+                else:
+                    o = env.step(a)
+                outs[impl] = [x.clone() for x in o[:4]] + [o[4]["num_contacts"].clone()]
+            for x, y in zip(outs["register"], outs["tma"]):
+                assert torch.equal(x, y), t
+        a, b = envs["register"], envs["tma"]
+        for name in ("_obs", "_op64", "_thr", "_damp", "_step_count", "_cmask", "_size", "_mass", "_friction", "_episode"):
+            assert torch.equal(getattr(a, name), getattr(b, name)), name
+        if track:
+            assert torch.equal(a._ep_stats, b._ep_stats) and torch.equal(a._ep_return, b._ep_return)
+            assert torch.equal(a.counters, b.counters) and int(a.counters[:, 0].sum()) > 0
+            torch.testing.assert_close(a.ret_sums, b.ret_sums, rtol=1e-9, atol=0)
+    finally:
+        _lib.set_step_impl("auto")

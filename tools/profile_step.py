@@ -1,0 +1,36 @@
+"""Short, deterministic launch sequence for ncu (never a source of bench numbers).
+
+    python tools/profile_step.py [num_envs] [variant]
+
+variant: api (step kernel, plain), api_track (step kernel with auto-reset + tracking, the bench
+path), fused (rollout kernel).  8 warm-up launches, then 6 profiled-range launches.
+"""
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.abspath(os.path.join(os.path.dirname(__file__), "..")))
+
+import dexterous_rl_manipulation_b200 as dx
+
+n = int(sys.argv[1]) if len(sys.argv) > 1 else 1 << 20
+variant = sys.argv[2] if len(sys.argv) > 2 else "api_track"
+CC = dx.CurriculumConfig
+kw = dict(max_episode_steps=200, reward_type="dense", curriculum_config=CC.hard(), seed=42)
+if variant == "api":
+    env = dx.BatchedManipulationEnv(n, "cuda", **kw)
+elif variant == "api_track":
+    env = dx.BatchedManipulationEnv(n, "cuda", auto_reset=True, respawn=True, loop_max_steps=200, track_episodes=True, **kw)
+else:
+    env = dx.BatchedManipulationEnv(n, "cuda", track_episodes=True, **kw)
+env.reset(seed=42)
+g = torch.Generator(device="cuda").manual_seed(0)
+pool = [torch.rand(n, 15, device="cuda", generator=g) * 2 - 1 for _ in range(4)]
+for t in range(14):
+    if variant == "fused":
+        env.rollout(20, policy="random")
+    else:
+        env.step(pool[t % 4])
+torch.cuda.synchronize()
+print("done", variant, n)
