@@ -53,7 +53,9 @@ def parse_args():
     ap.add_argument("--no-sweep", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="target CPU time of the cpu_baseline sample")
-    ap.add_argument("--ref-steps-per-proc", type=int, default=2000, help="reference arm: env-steps per process per bench step")
+    ap.add_argument("--ref-steps-per-proc", type=int, default=0,
+                    help="reference arm: env-steps per process per bench step (0 = size from --ref-budget-seconds)")
+    ap.add_argument("--ref-budget-seconds", type=float, default=120.0, help="reference arm: target wall time of the whole run")
     ap.add_argument("--ref-procs", type=int, default=0, help="reference arm: processes (0 = all host cores)")
     return ap.parse_args()
 
@@ -78,6 +80,7 @@ def _ref_worker(conn, steps_per_call, seed):
             msg = conn.recv()
             if msg == "stop":
                 break
+            steps_per_call = int(msg[1])
             t0 = time.perf_counter()
             for _ in range(steps_per_call):
                 obs, r, term, trunc, info = env.step(policy.select_action(obs))
@@ -109,6 +112,7 @@ def _oracle_port_worker(conn, steps_per_call, seed):
             msg = conn.recv()
             if msg == "stop":
                 break
+            steps_per_call = int(msg[1])
             t0 = time.perf_counter()
             ob.rollout(grp, max(steps_per_call // n, 1), seed, policy_kind=1, respawn=True, loop_max_steps=MAX_EPISODE_STEPS)
             conn.send(("done", time.perf_counter() - t0))
@@ -127,12 +131,11 @@ def run_reference(args, n_gpus):
     kind = "reference" if ref_harness.available() else "port"
     ctx = mp.get_context("fork")
     procs = args.ref_procs or (os.cpu_count() or 1)
-    spc = args.ref_steps_per_proc
     target = _ref_worker if kind == "reference" else _oracle_port_worker
     workers = []
     for k in range(procs):
         a, b = ctx.Pipe()
-        p = ctx.Process(target=target, args=(b, spc, SEED + k), daemon=True)
+        p = ctx.Process(target=target, args=(b, 0, SEED + k), daemon=True)
         p.start()
         workers.append((p, a))
     form = None
@@ -143,19 +146,29 @@ def run_reference(args, n_gpus):
             return 0
         form = val
 
-    def one_step():
+    def one_step(k):
         for _, c in workers:
-            c.send("go")
+            c.send(("go", k))
         for _, c in workers:
             tag, val = c.recv()
             if tag != "done":
                 raise RuntimeError(val)
 
+    # size the per-step sample so that the whole --steps/--warmup run ends within a few minutes
+    if args.ref_steps_per_proc > 0:
+        spc = args.ref_steps_per_proc
+    else:
+        probe = 256
+        t0 = time.perf_counter()
+        one_step(probe)
+        tau = (time.perf_counter() - t0) / probe                  # seconds per env-step per process
+        budget = args.ref_budget_seconds / max(args.steps + args.warmup, 1)
+        spc = int(max(256 if kind == "port" else 16, min(20000, budget / max(tau, 1e-9))))
     for _ in range(args.warmup):
-        one_step()
+        one_step(spc)
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        one_step()
+        one_step(spc)
     dt = time.perf_counter() - t0
     for p, c in workers:
         c.send("stop")
@@ -306,18 +319,10 @@ def run_b200(args):
     value = E * n_gpus * args.steps / (ms * 1e-3)
     launches = args.steps
 
-    # ---- kernel-only roofline: the step kernel alone, CUDA events on its stream --------------------
-    for t in range(5):
-        env.step(pool[t % 4])
-    torch.cuda.synchronize(dev)
-    reps = 40
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for t in range(reps):
-        env.step(pool[t % 4])
-    e1.record()
-    torch.cuda.synchronize(dev)
-    k_ms = e0.elapsed_time(e1) / reps
+    # ---- roofline of the dominant kernel: algorithmic bytes per launch / average launch duration over
+    #      the timed region (CUDA events on the launching stream; one launch per step, GPU-bound at this
+    #      size, so region time / steps is the kernel's average duration including reset waves) ----------
+    k_ms = ms / args.steps
     peaks = {}
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
@@ -326,11 +331,19 @@ def run_b200(args):
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
     achieved = ALGO_BYTES_PER_ENV_STEP * E / (k_ms * 1e-3) / 1e9
-    roofline = {"bound": "hbm", "kernel": "dexsim::step_kernel<dense, AoS action, extras>", "achieved": achieved,
-                "peak": peak, "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s",
-                "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+    traffic = None
+    try:
+        with open(os.path.join(ROOT, "profiles", "step_kernel_traffic.json")) as fh:
+            tr = json.load(fh)
+        if int(tr.get("envs", 0)) == E:
+            traffic = tr["dram_bytes_per_launch"]
+    except (OSError, ValueError, KeyError):
+        pass
+    roofline = {"bound": "hbm", "kernel": "dexsim::step_tma_kernel<dense, AoS action, track, 2 stages>", "achieved": achieved,
+                "peak": peak, "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if peaks else "fallback 6650 GB/s",
+                "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                 "algorithmic_bytes_per_env_step": ALGO_BYTES_PER_ENV_STEP, "envs_per_launch": E,
-                "kernel_ms": k_ms}
+                "kernel_ms": k_ms, "how": "timed-region average per launch (includes auto-reset waves and 1 curriculum poll per 100 steps)"}
 
     # ---- end to end: pinned host actions in, obs / reward / flags out ------------------------------
     h_pool = [torch.rand(E, 15).mul_(2).sub_(1).pin_memory() for _ in range(2)]
@@ -415,7 +428,7 @@ def run_b200(args):
 def measure_cpu_baseline(args):
     """cpu_baseline leg: the reference arm on a bounded sample, in a subprocess (never shares the
     CUDA context).  Sized from a 1-step probe to take about --cpu-seconds."""
-    cmd = [sys.executable, os.path.abspath(__file__), "--impl", "reference", "--ref-steps-per-proc", "500"]
+    cmd = [sys.executable, os.path.abspath(__file__), "--impl", "reference", "--ref-steps-per-proc", "500"]   # 500 env-steps x P procs per step
     try:
         probe = subprocess.run(cmd + ["--steps", "1", "--warmup", "1"], capture_output=True, text=True, timeout=180)
         line = json.loads(probe.stdout.strip().splitlines()[-1])

@@ -13,8 +13,8 @@
  *     (the Python side allocates them as torch tensors); the *_host entry points take HOST
  *     pointers (pinned for full speed) and are documented as such.
  *   - `stream` is a cudaStream_t passed as void* (0 = legacy default stream).  Calls are
- *     asynchronous on that stream unless stated; no hidden global state, no allocation
- *     (except dexsim_host_ctx_create) => thread-safe per (device, stream).
+ *     asynchronous on that stream unless stated; no allocation and no per-call global state
+ *     (the only process-wide switch is dexsim_set_step_impl) => thread-safe per (device, stream).
  *   - Return value: 0 = ok; negative cudaError_t (-e) for CUDA failures; DEXSIM_E_* for
  *     argument errors.  No exceptions cross the boundary.  dexsim_error_string() explains.
  *   - Per-env arrays are structure-of-arrays with leading dimension `ld` (>= n, multiple of

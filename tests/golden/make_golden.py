@@ -11,6 +11,7 @@ Outputs (committed):
     noise.npz    CombinedNoiseWrapper trajectories with the wrapper's normal draws recorded
     labels.npz   both failure classifiers on synthetic episodes (ties included)
     episodes.npz Evaluator.evaluate_episode / run_episode records with the policy's actions
+    scheduler.npz CurriculumScheduler decisions on random success streams
     anchors.json scalar anchors quoted in SURVEY.md 8c and the reference tests' known answers
 """
 import json
@@ -349,7 +350,33 @@ def gen_anchors():
     print("anchors.json written")
 
 
+def gen_scheduler():
+    """experiments/curriculum_scheduler.py:141-222,77-139: progression decisions and interpolated
+    configs for random success streams (the batched driver must reproduce them)."""
+    rng = np.random.default_rng(99)
+    recs = {k: [] for k in ("kw", "success", "steps", "progressed", "level", "size", "mass", "friction")}
+    for trial in range(12):
+        kw = [float(rng.choice([0.3, 0.5, 0.7])), int(rng.choice([5, 20, 50])), int(rng.choice([5, 15, 20])),
+              int(rng.choice([3, 5, 7]))]
+        sch = R.CurriculumScheduler(CC.easy(), CC.hard(), success_rate_threshold=kw[0],
+                                    min_episodes_before_progression=kw[1], window_size=kw[2], progression_steps=kw[3])
+        p = rng.uniform(0.2, 0.9)
+        succ = rng.random(300) < p
+        steps = rng.integers(1, 200, 300)
+        prog, lvl, sz, ms, fr = [], [], [], [], []
+        for a, b in zip(succ, steps):
+            prog.append(sch.update(bool(a), int(b)))
+            c = sch.get_current_config()
+            lvl.append(sch.current_difficulty_level); sz.append(c.object_size); ms.append(c.object_mass)
+            fr.append(c.friction_coefficient)
+        recs["kw"].append(kw); recs["success"].append(succ); recs["steps"].append(steps); recs["progressed"].append(prog)
+        recs["level"].append(lvl); recs["size"].append(sz); recs["mass"].append(ms); recs["friction"].append(fr)
+    np.savez_compressed(os.path.join(HERE, "scheduler.npz"), **{k: np.asarray(v) for k, v in recs.items()})
+    print("scheduler.npz: 12 streams x 300 episodes; progressions:", int(np.sum(recs["progressed"])))
+
+
 if __name__ == "__main__":
+    gen_scheduler()
     gen_traj()
     gen_noise()
     gen_labels()

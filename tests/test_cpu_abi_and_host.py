@@ -160,3 +160,50 @@ def test_summarize_counters_schema():
     assert m[0]["failure_type_frequency"]["timeout"] == {"count": 4, "frequency": 0.4}
     assert m[0]["failed_episodes"] == 4 and m[0]["mean_reward"] == 2.0
     assert abs(m[0]["std_episode_length"] - (3000 - 2500) ** 0.5) < 1e-9
+
+
+def test_scheduler_standin_matches_reference_decisions(golden_dir):
+    with np.load(os.path.join(golden_dir, "scheduler.npz")) as z:
+        g = {k: z[k] for k in z.files}
+    CC = dx.CurriculumConfig
+    for t in range(g["kw"].shape[0]):
+        thr, mn, win, ps = g["kw"][t]
+        sch = dx.CurriculumScheduler(CC.easy(), CC.hard(), success_rate_threshold=float(thr),
+                                     min_episodes_before_progression=int(mn), window_size=int(win), progression_steps=int(ps))
+        for e in range(g["success"].shape[1]):
+            assert sch.update(bool(g["success"][t, e]), int(g["steps"][t, e])) == bool(g["progressed"][t, e])
+            c = sch.get_current_config()
+            assert (sch.current_difficulty_level, c.object_size, c.object_mass, c.friction_coefficient) == \
+                   (g["level"][t, e], g["size"][t, e], g["mass"][t, e], g["friction"][t, e])
+
+
+class _FakeEnv:
+    curriculum_config = None
+
+
+def test_curriculum_driver_feeds_scheduler_and_pushes_config():
+    import torch
+    from dexterous_rl_manipulation_b200.curriculum import spread_flag, spread_successes
+    CC = dx.CurriculumConfig
+    for E, S in ((10, 0), (10, 10), (7, 3), (1000, 371)):
+        f = spread_successes(E, S)
+        assert len(f) == E and sum(f) == S and all(f[k] == spread_flag(k, E, S) for k in range(E))
+    env = _FakeEnv()
+    sch = dx.CurriculumScheduler(CC.easy(), CC.hard(), success_rate_threshold=0.3, min_episodes_before_progression=20,
+                                 window_size=15, progression_steps=5)
+    drv = dx.BatchedCurriculumDriver(env, sch)
+    assert env.curriculum_config.object_size == 0.08
+    assert drv.feed(10, 9, 150) == 0 and sch.total_episodes == 10 and sch.total_steps == 150
+    # 5,000,000 mostly successful episodes in one poll: reaches the target level after a handful of
+    # sequential updates, the rest is folded in bulk (must be fast and keep totals exact)
+    prog = drv.feed(5_000_000, 4_500_000, 75_000_000)
+    assert prog == 5 and sch.current_difficulty_level == 1.0
+    assert abs(env.curriculum_config.object_size - 0.03) < 1e-12 and abs(env.curriculum_config.friction_coefficient - 0.3) < 1e-12
+    assert sch.total_episodes == 5_000_010 and sch.total_steps == 75_000_150
+    assert len(sch.episode_successes) < 200
+    # poll() reads deltas from a counter table
+    c = torch.zeros(2, dx.NCOUNTERS, dtype=torch.int64)
+    c[0, dx.CNT_EPISODES], c[0, dx.CNT_SUCCESSES], c[0, dx.CNT_SUM_STEPS] = 100, 20, 15000
+    drv2 = dx.BatchedCurriculumDriver(_FakeEnv(), dx.CurriculumScheduler(CC.easy(), CC.hard()))
+    drv2.poll(c); drv2.poll(c)
+    assert drv2.scheduler.total_episodes == 100 and drv2.scheduler.total_steps == 15000
