@@ -360,7 +360,8 @@ def run_b200(args):
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         e2e_s = float(tt.item())
     e2e = {"value": E * n_gpus * args.e2e_steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": E * 15 * 4,
-           "d2h_bytes_per_step": env.ld * 45 * 4 + E * (4 + 3), "steps": args.e2e_steps,
+           "d2h_bytes_per_step": env.ld * 41 * 4 + E * (4 + 3), "steps": args.e2e_steps,
+           "note": "obs rows 33-36 (constant quaternion) are not re-copied; 8 chunks, H2D / kernel / D2H overlapped",
            "api": "BatchedManipulationEnv.step_host -> dexsim_step_host"}
     launches += args.e2e_steps
 

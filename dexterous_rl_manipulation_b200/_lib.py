@@ -19,6 +19,7 @@ LABEL_NONE = 255
 CNT_EPISODES, CNT_SUCCESSES, CNT_SUM_STEPS, CNT_SUM_FINAL_CONTACTS = 0, 1, 2, 3
 CNT_LABEL_METRICS, CNT_LABEL_TAXONOMY, CNT_VAR_TIES, CNT_SUM_STEPS_SQ = 4, 10, 16, 17
 RNG_STREAM_DYN, RNG_STREAM_OBS = 2, 3
+HOST_SKIP_QUAT = 1
 
 # value strings of FailureType (evaluation/metrics.py:15-22) / FailureMode
 # (evaluation/failure_taxonomy.py:14-26) in enum declaration order = device label codes
@@ -111,7 +112,7 @@ def lib():
     L.dexsim_classify_summary.argtypes = [C.POINTER(DexsimEpisodeSummary), i32, i32, C.POINTER(i32),
                                           C.POINTER(i32), C.POINTER(i32)]
     L.dexsim_step_host.argtypes = [C.POINTER(DexsimState), C.POINTER(DexsimParams), vp, vp, C.POINTER(DexsimStepIO),
-                                   vp, vp, vp, vp, vp, vp, vp]
+                                   vp, vp, vp, vp, vp, vp, i32, i32, vp]
     for name in EXPORTS:
         fn = getattr(L, name)          # raises AttributeError if a declared symbol is not exported
         if name not in ("dexsim_error_string",):

@@ -797,36 +797,124 @@ int dexsim_classify_summary(const DexsimEpisodeSummary* s, int32_t max_steps, in
     return 0;
 }
 
+// ---- host-buffer step: chunked so that H2D of chunk c+1, the kernel of chunk c and D2H of chunk c-1
+//      overlap (separate copy engines per direction).  Internal streams/events are created once per
+//      device and fork from / join into the caller's stream, so the call stays stream-ordered. ----------
+namespace {
+constexpr int HOST_STREAMS = 3;
+struct HostPipe {
+    bool ready = false;
+    cudaStream_t streams[HOST_STREAMS];
+    cudaEvent_t fork_ev;
+    cudaEvent_t join_ev[HOST_STREAMS];
+};
+HostPipe g_pipes[64];
+
+int get_pipe(HostPipe** out) {
+    int dev = 0;
+    cudaError_t err = cudaGetDevice(&dev);
+    if (err != cudaSuccess) return -(int)err;
+    if (dev < 0 || dev >= 64) return DEXSIM_E_PARAM;
+    HostPipe& hp = g_pipes[dev];
+    if (!hp.ready) {
+        for (int k = 0; k < HOST_STREAMS; ++k) {
+            err = cudaStreamCreateWithFlags(&hp.streams[k], cudaStreamNonBlocking);
+            if (err != cudaSuccess) return -(int)err;
+            err = cudaEventCreateWithFlags(&hp.join_ev[k], cudaEventDisableTiming);
+            if (err != cudaSuccess) return -(int)err;
+        }
+        err = cudaEventCreateWithFlags(&hp.fork_ev, cudaEventDisableTiming);
+        if (err != cudaSuccess) return -(int)err;
+        hp.ready = true;
+    }
+    *out = &hp;
+    return 0;
+}
+}  // namespace
+
 int dexsim_step_host(const DexsimState* st, const DexsimParams* p, const DexsimGroup* groups,
                      const uint16_t* group_of_env, const DexsimStepIO* io, const float* h_action, float* h_obs,
                      float* h_reward, uint8_t* h_terminated, uint8_t* h_truncated, uint8_t* h_num_contacts,
-                     void* stream) {
+                     int32_t chunks, int32_t flags, void* stream) {
     int rc = check_state(st);
     if (rc) return rc;
     if (!p || !io || !io->action || !h_action || !h_reward || !h_terminated || !h_truncated) return DEXSIM_E_NULL;
-    cudaStream_t s = (cudaStream_t)stream;
+    if (io->dyn_noise || io->obs_noise || io->noisy_obs) return DEXSIM_E_PARAM;   // noise: use dexsim_step
+    cudaStream_t user = (cudaStream_t)stream;
     const int64_t n = st->n, ld = st->ld;
-    const size_t act_bytes = (io->action_layout == 1 ? (size_t)n * NJ : (size_t)ld * NJ) * sizeof(float);
-    cudaError_t err = cudaMemcpyAsync(const_cast<float*>(io->action), h_action, act_bytes, cudaMemcpyHostToDevice, s);
-    if (err != cudaSuccess) return -(int)err;
-    rc = launch_step(st, p, groups, group_of_env, io, s);
-    if (rc) return rc;
-    if (h_obs) {
-        const float* src = (io->noisy_obs && io->obs_noise) ? io->noisy_obs : st->obs;
-        err = cudaMemcpyAsync(h_obs, src, (size_t)ld * NOBS * sizeof(float), cudaMemcpyDeviceToHost, s);
+    if (n == 0) return 0;
+    const bool aos = io->action_layout == 1;
+    // chunk boundaries are multiples of 1024 envs (tile- and alignment-friendly)
+    int64_t per = ((n + (chunks > 0 ? chunks : 1) - 1) / (chunks > 0 ? chunks : 1) + 1023) / 1024 * 1024;
+    const int nchunks = (int)((n + per - 1) / per);
+    HostPipe* hp = nullptr;
+    if (nchunks > 1) {
+        rc = get_pipe(&hp);
+        if (rc) return rc;
+        cudaError_t err = cudaEventRecord(hp->fork_ev, user);
         if (err != cudaSuccess) return -(int)err;
+        for (int k = 0; k < HOST_STREAMS && k < nchunks; ++k) {
+            err = cudaStreamWaitEvent(hp->streams[k], hp->fork_ev, 0);
+            if (err != cudaSuccess) return -(int)err;
+        }
     }
-    err = cudaMemcpyAsync(h_reward, io->reward, (size_t)n * sizeof(float), cudaMemcpyDeviceToHost, s);
-    if (err != cudaSuccess) return -(int)err;
-    err = cudaMemcpyAsync(h_terminated, io->terminated, (size_t)n, cudaMemcpyDeviceToHost, s);
-    if (err != cudaSuccess) return -(int)err;
-    err = cudaMemcpyAsync(h_truncated, io->truncated, (size_t)n, cudaMemcpyDeviceToHost, s);
-    if (err != cudaSuccess) return -(int)err;
-    if (h_num_contacts) {
-        err = cudaMemcpyAsync(h_num_contacts, io->num_contacts, (size_t)n, cudaMemcpyDeviceToHost, s);
+    for (int c = 0; c < nchunks; ++c) {
+        const int64_t lo = (int64_t)c * per, hi = (lo + per < n) ? lo + per : n, m = hi - lo;
+        cudaStream_t s = nchunks > 1 ? hp->streams[c % HOST_STREAMS] : user;
+        DexsimState sub = *st;
+        sub.n = m;
+        sub.obs += lo; sub.op64 += lo; sub.thr += lo; sub.damp += lo; sub.step_count += lo; sub.cmask += lo;
+        sub.size += lo; sub.mass += lo; sub.friction += lo; sub.episode += lo;
+        if (sub.ep_return) sub.ep_return += lo;
+        if (sub.ep_stats) sub.ep_stats += lo;
+        DexsimParams sp = *p;
+        sp.env_gid0 = p->env_gid0 + lo;
+        DexsimStepIO sio = *io;
+        float* d_action = const_cast<float*>(io->action) + (aos ? lo * NJ : lo);
+        sio.action = d_action;
+        sio.reward += lo; sio.terminated += lo; sio.truncated += lo; sio.num_contacts += lo;
+        if (sio.reward_comps) sio.reward_comps += lo;
+        if (sio.finished) sio.finished += lo;
+        cudaError_t err;
+        if (aos) err = cudaMemcpyAsync(d_action, h_action + lo * NJ, (size_t)m * NJ * sizeof(float), cudaMemcpyHostToDevice, s);
+        else err = cudaMemcpy2DAsync(d_action, (size_t)ld * 4, h_action + lo, (size_t)ld * 4, (size_t)m * 4, NJ, cudaMemcpyHostToDevice, s);
         if (err != cudaSuccess) return -(int)err;
+        rc = launch_step(&sub, &sp, groups, group_of_env ? group_of_env + lo : nullptr, &sio, s);
+        if (rc) return rc;
+        if (h_obs) {
+            if (flags & DEXSIM_HOST_SKIP_QUAT) {     // rows 33-36 are the constant (1,0,0,0): caller keeps them
+                err = cudaMemcpy2DAsync(h_obs + lo, (size_t)ld * 4, st->obs + lo, (size_t)ld * 4, (size_t)m * 4,
+                                        DEXSIM_ROW_QUAT, cudaMemcpyDeviceToHost, s);
+                if (err != cudaSuccess) return -(int)err;
+                err = cudaMemcpy2DAsync(h_obs + (size_t)DEXSIM_ROW_OV * ld + lo, (size_t)ld * 4,
+                                        st->obs + (size_t)DEXSIM_ROW_OV * ld + lo, (size_t)ld * 4, (size_t)m * 4,
+                                        DEXSIM_OBS - DEXSIM_ROW_OV, cudaMemcpyDeviceToHost, s);
+            } else {
+                err = cudaMemcpy2DAsync(h_obs + lo, (size_t)ld * 4, st->obs + lo, (size_t)ld * 4, (size_t)m * 4, DEXSIM_OBS,
+                                        cudaMemcpyDeviceToHost, s);
+            }
+            if (err != cudaSuccess) return -(int)err;
+        }
+        err = cudaMemcpyAsync(h_reward + lo, io->reward + lo, (size_t)m * sizeof(float), cudaMemcpyDeviceToHost, s);
+        if (err != cudaSuccess) return -(int)err;
+        err = cudaMemcpyAsync(h_terminated + lo, io->terminated + lo, (size_t)m, cudaMemcpyDeviceToHost, s);
+        if (err != cudaSuccess) return -(int)err;
+        err = cudaMemcpyAsync(h_truncated + lo, io->truncated + lo, (size_t)m, cudaMemcpyDeviceToHost, s);
+        if (err != cudaSuccess) return -(int)err;
+        if (h_num_contacts) {
+            err = cudaMemcpyAsync(h_num_contacts + lo, io->num_contacts + lo, (size_t)m, cudaMemcpyDeviceToHost, s);
+            if (err != cudaSuccess) return -(int)err;
+        }
     }
-    return cuda_rc(cudaStreamSynchronize(s));
+    if (nchunks > 1) {
+        for (int k = 0; k < HOST_STREAMS && k < nchunks; ++k) {
+            cudaError_t err = cudaEventRecord(hp->join_ev[k], hp->streams[k]);
+            if (err != cudaSuccess) return -(int)err;
+            err = cudaStreamWaitEvent(user, hp->join_ev[k], 0);
+            if (err != cudaSuccess) return -(int)err;
+        }
+    }
+    return cuda_rc(cudaStreamSynchronize(user));
 }
 
 }  // extern "C"

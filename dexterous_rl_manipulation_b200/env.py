@@ -572,18 +572,21 @@ class BatchedManipulationEnv:
         return self._info
 
     # ------------------------------------------------------------------ host-buffer step (end to end)
-    def step_host(self, action_host):
+    def step_host(self, action_host, chunks=None):
         """One step with HOST buffers: ``action_host`` is a float32 [num_envs, 15] NumPy array or CPU
         tensor (pinned memory makes the copies true DMA); returns CPU tensors
         ``(obs [num_envs,45], reward, terminated, truncated, info)`` living in pinned buffers that
         the next call overwrites.  One C-ABI call (dexsim_step_host): H2D copy of the actions, the
-        step kernel, D2H copies of observation / reward / flags, stream synchronize."""
+        step kernel, D2H copies of observation / reward / flags, stream synchronize.  Large batches are
+        split into ``chunks`` ranges (default: one per 65,536 envs, at most 8) so that the upload of one
+        range overlaps the kernel and the download of the others."""
         if not self._did_reset:
             raise RuntimeError("call reset() before step_host()")
         n, ld = self.num_envs, self.ld
         if getattr(self, "_h_obs", None) is None:
             pin = lambda *shape, dtype: torch.zeros(*shape, dtype=dtype).pin_memory()
             self._h_obs = pin(45, ld, dtype=torch.float32)
+            self._h_obs[_L.ROW_QUAT].fill_(1.0)          # constant quaternion rows are never re-copied
             self._h_reward = pin(ld, dtype=torch.float32)
             self._h_term, self._h_trunc, self._h_nc = (pin(ld, dtype=torch.uint8) for _ in range(3))
             self._h_info = {"num_contacts": self._h_nc[:n]}
@@ -598,7 +601,9 @@ class BatchedManipulationEnv:
             _lib.check(self._lib.dexsim_step_host(
                 C.byref(self._state), C.byref(self._params), self._ptr(self._groups_dev), self._ptr(self._goe),
                 C.byref(io), a.data_ptr(), self._h_obs.data_ptr(), self._h_reward.data_ptr(), self._h_term.data_ptr(),
-                self._h_trunc.data_ptr(), self._h_nc.data_ptr(), self._stream()), "dexsim_step_host")
+                self._h_trunc.data_ptr(), self._h_nc.data_ptr(),
+                int(chunks) if chunks is not None else max(1, min(8, n // 65536)), _L.HOST_SKIP_QUAT,
+                self._stream()), "dexsim_step_host")
         return (self._h_obs[:, :n].t(), self._h_reward[:n], self._h_term[:n].view(torch.bool),
                 self._h_trunc[:n].view(torch.bool), self._h_info)
 

@@ -215,13 +215,18 @@ int dexsim_classify_summary(const DexsimEpisodeSummary* s, int32_t max_steps, in
 
 /* ---- host-buffer step (end-to-end path): actions in HOST memory -> device -> step ->
  *      obs / reward / flags back to HOST memory, synchronous on return.  Pinned buffers make the
- *      copies asynchronous DMA; pageable buffers work but stage through the driver. ------------- */
+ *      copies asynchronous DMA; pageable buffers work but stage through the driver.  With chunks > 1
+ *      the envs are split into that many ranges whose H2D copy, kernel and D2H copies overlap on
+ *      internal streams (created once per device, forked from / joined into `stream`).
+ *      This is what a caller that keeps NumPy-side policies uses in place of
+ *      `obs, r, term, trunc, info = env.step(action)` (envs/manipulation_env.py:184). ------------------ */
+#define DEXSIM_HOST_SKIP_QUAT 1   /* do not copy obs rows 33-36 (constant quaternion, already in h_obs) */
 int dexsim_step_host(const DexsimState* st, const DexsimParams* p, const DexsimGroup* groups,
                      const uint16_t* group_of_env, const DexsimStepIO* io /* device scratch */,
                      const float* h_action /* host [n, 15] (layout 1) or [15, ld] (layout 0) */,
                      float* h_obs /* host [45, ld] or NULL */, float* h_reward /* host [ld] */,
                      uint8_t* h_terminated, uint8_t* h_truncated, uint8_t* h_num_contacts /* host [ld] or NULL */,
-                     void* stream);
+                     int32_t chunks, int32_t flags, void* stream);
 
 #ifdef __cplusplus
 }

@@ -415,3 +415,28 @@ def test_tma_pipeline_equals_register_kernel(dx, n, track, dense):
             torch.testing.assert_close(a.ret_sums, b.ret_sums, rtol=1e-9, atol=0)
     finally:
         _lib.set_step_impl("auto")
+
+
+@pytest.mark.parametrize("n,chunks,track", [(5000, 3, True), (4096, 1, False), (70_000, 8, True)])
+def test_step_host_matches_device_step(dx, n, chunks, track):
+    """The end-to-end entry (host buffers, chunked copy/compute overlap) equals the device-tensor API."""
+    CC = dx.CurriculumConfig
+    kw = dict(max_episode_steps=20, reward_type="dense", seed=8, groups=[CC.easy(), CC.hard()])
+    if track:
+        kw.update(auto_reset=True, respawn=True, loop_max_steps=20, track_episodes=True)
+    a_env = dx.BatchedManipulationEnv(n, "cuda", **kw)
+    b_env = dx.BatchedManipulationEnv(n, "cuda", **kw)
+    a_env.reset(seed=8); b_env.reset(seed=8)
+    rng = np.random.default_rng(1)
+    for t in range(45):
+        act = rng.uniform(-1.2, 1.2, (n, 15)).astype(np.float32)
+        o1, r1, te1, tr1, i1 = a_env.step(torch.from_numpy(act).cuda())
+        o2, r2, te2, tr2, i2 = b_env.step_host(torch.from_numpy(act).pin_memory(), chunks=chunks)
+        assert not o2.is_cuda
+        assert torch.equal(o1.cpu(), o2) and torch.equal(r1.cpu(), r2), t
+        assert torch.equal(te1.cpu(), te2) and torch.equal(tr1.cpu(), tr2)
+        assert torch.equal(i1["num_contacts"].cpu(), i2["num_contacts"])
+    assert torch.equal(a_env._obs, b_env._obs) and torch.equal(a_env._op64, b_env._op64)
+    assert torch.equal(a_env._episode, b_env._episode)
+    if track:
+        assert torch.equal(a_env.counters, b_env.counters) and int(a_env.counters[:, 0].sum()) > 0
