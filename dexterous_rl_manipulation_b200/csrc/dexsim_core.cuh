@@ -31,6 +31,11 @@ constexpr int NOBS = DEXSIM_OBS;
 #define DEXSIM_D inline
 #endif
 
+#if defined(__CUDACC__)
+// n_c / num_fingers for n_c = 0..5, rounded once like the reference's int / int true division
+__constant__ double kContactReward[6] = {0.0 / 5.0, 1.0 / 5.0, 2.0 / 5.0, 3.0 / 5.0, 4.0 / 5.0, 5.0 / 5.0};
+#endif
+
 struct EnvRegs {
     float    jp[NJ];
     float    jv[NJ];
@@ -58,11 +63,24 @@ DEXSIM_D double clip_f64(double x, double lo, double hi) {
     return (y > hi) ? hi : y;
 }
 
-// envs/manipulation_env.py:285-310.  Returns the contact mask, count and min distance.
+// envs/manipulation_env.py:285-310.  Returns the contact mask and count; with NEED_DMIN also the
+// minimum fingertip distance (rewards/reward_shaping.py:111-113).
+//
+// The reference tests RN(sqrt(sq)) < thr in float64.  sqrt is monotone and correctly rounded, so
+//   sq < thr^2 (1 - 2^-50)  =>  sqrt(sq) < thr (1 - 2^-52) <= pred(thr)  =>  contact
+//   sq > thr^2 (1 + 2^-50)  =>  sqrt(sq) > thr                           =>  no contact
+// (thr^2 itself carries one rounding, 2^-53, absorbed by the 2^-50 margins).  Only inside that band --
+// relative width 2^-49, the "contact branch" -- is the square root evaluated; the decision is
+// bit-identical to the reference's everywhere.  Likewise min_i RN(sqrt(sq_i)) == RN(sqrt(min_i sq_i)),
+// so the dense reward needs one square root, not five.
+template <bool NEED_DMIN>
 DEXSIM_D unsigned update_contacts(const EnvRegs& e, int& n_c, double& dmin) {
     unsigned mask = 0u;
     n_c = 0;
-    dmin = 0.0;
+    const double thr2 = __dmul_rn(e.thr, e.thr);
+    const double lo2 = __dmul_rn(thr2, 1.0 - 0x1p-50), hi2 = __dmul_rn(thr2, 1.0 + 0x1p-50);
+    const bool thr_pos = e.thr > 0.0;                              // d >= 0 can never be below thr <= 0
+    double sqmin = 0.0;
 #pragma unroll
     for (int f = 0; f < NF; ++f) {
         // :301-302 float32 sequential sum of 3 joints, "* 0.1" stays float32, then widened (:300)
@@ -73,12 +91,16 @@ DEXSIM_D unsigned update_contacts(const EnvRegs& e, int& n_c, double& dmin) {
         const double dy = __dsub_rn(tip, e.op[1]);
         const double dz = __dsub_rn(tip, e.op[2]);
         const double sq = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
-        const double d = __dsqrt_rn(sq);
-        const bool c = d < e.thr;                                  // :310
+        bool c;
+        if (sq < lo2) c = true;
+        else if (sq > hi2) c = false;
+        else c = __dsqrt_rn(sq) < e.thr;                           // tie band (and NaN): exact test, :310
+        c = c && thr_pos;
         mask |= (c ? 1u : 0u) << f;
         n_c += c ? 1 : 0;
-        dmin = (f == 0) ? d : ((d < dmin) ? d : dmin);             // np.min, reward_shaping.py:112
+        if (NEED_DMIN) sqmin = (f == 0) ? sq : ((sq < sqmin || sq != sq) ? sq : sqmin);   // np.min propagates NaN
     }
+    dmin = NEED_DMIN ? __dsqrt_rn(sqmin) : 0.0;
     return mask;
 }
 
@@ -97,7 +119,7 @@ DEXSIM_D void env_reset(EnvRegs& e, const float* jp0, double size, double fricti
     e.damp = (float)__dsub_rn(1.0, __dmul_rn(__dmul_rn(friction, 0.1), 0.01)); // :215
     e.sc = 0;
     int n_c; double dmin;
-    e.cmask = update_contacts(e, n_c, dmin);                                 // :176
+    e.cmask = update_contacts<false>(e, n_c, dmin);                          // :176
 }
 
 // envs/manipulation_env.py:184-252 + rewards/reward_shaping.py (compute)
@@ -135,11 +157,11 @@ DEXSIM_D void env_step(EnvRegs& e, const float* a, const DexsimParams& p, StepRe
     // :238
     double dmin;
     const unsigned prev = e.cmask;
-    e.cmask = update_contacts(e, r.n_c, dmin);
+    e.cmask = update_contacts<DENSE>(e, r.n_c, dmin);
     // :241
     if (DENSE) {
         r.distance = exp(__dmul_rn(-5.0, dmin));                              // reward_shaping.py:116
-        r.contact = __ddiv_rn((double)r.n_c, 5.0);                            // :134
+        r.contact = kContactReward[r.n_c];                                    // :134 n_c / 5 (correctly rounded constants)
         float msum = -0.0f;                                                   // :149-162
 #pragma unroll
         for (int f = 0; f < NF; ++f) {
@@ -196,7 +218,8 @@ DEXSIM_D U4 rng_block(uint64_t seed, uint32_t gid, uint32_t episode, uint32_t st
 
 DEXSIM_D float u24(uint32_t x) { return (float)(x >> 8) * 5.9604644775390625e-08f; }
 DEXSIM_D double u53(uint32_t a, uint32_t b) {
-    return __ddiv_rn(__dadd_rn(__dmul_rn((double)(a >> 5), 67108864.0), (double)(b >> 6)), 9007199254740992.0);
+    // division by 2^53 == multiplication by 2^-53 (exact power-of-two scaling)
+    return __dmul_rn(__dadd_rn(__dmul_rn((double)(a >> 5), 67108864.0), (double)(b >> 6)), 0x1p-53);
 }
 DEXSIM_D double lerp_rn(double lo, double hi, double u) {   // low + (high - low) * u, as Generator.uniform
     return __dadd_rn(lo, __dmul_rn(__dsub_rn(hi, lo), u));

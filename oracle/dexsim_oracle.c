@@ -101,7 +101,7 @@ static void compute_reward(dexo_env* e, const dexo_params* p, const double dist[
     }
     /* _compute_distance_reward :101-118 (same float64 distances as _update_contacts) */
     double dmin = dist[0];
-    for (int f = 1; f < DEXO_NF; ++f) dmin = (dist[f] < dmin) ? dist[f] : dmin;
+    for (int f = 1; f < DEXO_NF; ++f) dmin = (dist[f] < dmin || isnan(dist[f])) ? dist[f] : dmin;   /* np.min propagates NaN */
     r->distance = exp(-5.0 * dmin);
     /* _compute_contact_reward :120-136 */
     r->contact = (double)n_c / (double)DEXO_NF;
