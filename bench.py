@@ -287,17 +287,24 @@ def run_b200(args):
         return [torch.rand(n, 15, device=dev, generator=g) * 2 - 1 for _ in range(k)]
 
     def timed_api(env, drv, pool, steps, warmup, poll_every):
+        # the scheduler reacts per episode in the reference; while it can still progress the counters are
+        # polled every 10 steps (one tiny D2H), afterwards every `poll_every` steps
+        def maybe_poll(t):
+            if not poll_every:
+                return
+            period = 10 if drv.scheduler.current_difficulty_level < 1.0 else poll_every
+            if (t + 1) % period == 0:
+                drv.poll()
+
         for t in range(warmup):
             env.step(pool[t % len(pool)])
-            if poll_every and (t + 1) % poll_every == 0:
-                drv.poll()
+            maybe_poll(t)
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for t in range(steps):
             env.step(pool[t % len(pool)])
-            if poll_every and (t + 1) % poll_every == 0:
-                drv.poll()
+            maybe_poll(t)
         e1.record()
         barrier()
         ms = e0.elapsed_time(e1)
@@ -386,7 +393,8 @@ def run_b200(args):
                  "launches": nl, "policy": "random (Philox, in-kernel)", "note": "state in registers across the launch"}
         del env2
 
-    # ---- sweep over env counts (API mode, no curriculum polling) -------------------------------------
+    # ---- sweep over env counts: API mode (one launch per step) and the fused rollout (50 steps per
+    #      launch); these sizes are L2-resident and launch/latency-bound, see DESIGN.md section 7 ----------
     sweep = []
     if not args.no_sweep and world == 1:
         for n in (4096, 65536, 131072):
@@ -394,12 +402,24 @@ def run_b200(args):
                 continue
             env_s, _, drv_s = make_env(n)
             pool_s = action_pool(n)
-            s_ms = timed_api(env_s, drv_s, pool_s, 300, 30, 0)
+            s_ms = timed_api(env_s, drv_s, pool_s, 300, 120, 100)
             v = n * 300 / (s_ms * 1e-3)
+            env_f = dx.BatchedManipulationEnv(n, dev, max_episode_steps=MAX_EPISODE_STEPS, reward_type="dense",
+                                              curriculum_config=CC.hard(), track_episodes=True, seed=SEED)
+            env_f.reset(seed=SEED)
+            env_f.rollout(50, policy="random")
+            torch.cuda.synchronize(dev)
+            f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            f0.record()
+            for _ in range(8):
+                env_f.rollout(50, policy="random")
+            f1.record()
+            torch.cuda.synchronize(dev)
+            fv = n * 400 / (f0.elapsed_time(f1) * 1e-3)
             sweep.append({"envs": n, "value": v, "ms_per_step": s_ms / 300,
-                          "roofline_frac": v * ALGO_BYTES_PER_ENV_STEP / 1e9 / peak,
-                          "note": "state is L2-resident at this size; launch/latency-bound"})
-            del env_s, pool_s
+                          "roofline_frac": v * ALGO_BYTES_PER_ENV_STEP / 1e9 / peak, "fused_rollout_value": fv,
+                          "note": "API mode is bound by the ~8.5 us host launch path at this size (state is L2-resident)"})
+            del env_s, pool_s, env_f
 
     if rank == 0:
         line = {

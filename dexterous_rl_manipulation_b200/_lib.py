@@ -6,6 +6,8 @@ product raises.  Nothing here touches ``oracle/``.
 import ctypes as C
 import os
 
+import numpy as _np
+
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("DEXSIM_LIB_PATH") or os.path.join(HERE, "libdexsim_b200.so")   # env override: kernel experiments only
 
@@ -19,6 +21,9 @@ LABEL_NONE = 255
 CNT_EPISODES, CNT_SUCCESSES, CNT_SUM_STEPS, CNT_SUM_FINAL_CONTACTS = 0, 1, 2, 3
 CNT_LABEL_METRICS, CNT_LABEL_TAXONOMY, CNT_VAR_TIES, CNT_SUM_STEPS_SQ = 4, 10, 16, 17
 RNG_STREAM_DYN, RNG_STREAM_OBS = 2, 3
+EPISODE_RECORD_DTYPE = _np.dtype([("env_gid", "u4"), ("episode", "u4"), ("steps", "i4"), ("success", "u1"),
+                                  ("final_contacts", "u1"), ("label_metrics", "u1"), ("label_taxonomy", "u1"),
+                                  ("episode_reward", "f8"), ("t_end", "u4"), ("var_tie", "u4")])
 HOST_SKIP_QUAT = 1
 
 # value strings of FailureType (evaluation/metrics.py:15-22) / FailureMode
@@ -61,6 +66,19 @@ class DexsimStepIO(C.Structure):
                 ("counters", C.c_void_p), ("ret_sums", C.c_void_p)]
 
 
+class DexsimEpisodeRecord(C.Structure):
+    _fields_ = [("env_gid", C.c_uint32), ("episode", C.c_uint32), ("steps", C.c_int32), ("success", C.c_uint8),
+                ("final_contacts", C.c_uint8), ("label_metrics", C.c_uint8), ("label_taxonomy", C.c_uint8),
+                ("episode_reward", C.c_double), ("t_end", C.c_uint32), ("var_tie", C.c_uint32)]
+
+
+class DexsimRolloutIO(C.Structure):
+    _fields_ = [("actions", C.c_void_p), ("dyn_noise", C.c_void_p), ("counters", C.c_void_p), ("ret_sums", C.c_void_p),
+                ("ep_log", C.c_void_p), ("ep_log_count", C.c_void_p), ("ep_log_capacity", C.c_int64),
+                ("hist", C.c_void_p), ("hist_steps", C.c_int64), ("step_base", C.c_int64),
+                ("one_episode", C.c_int32), ("pad_", C.c_int32)]
+
+
 class DexsimEpisodeSummary(C.Structure):
     _fields_ = [("success", C.c_int32), ("episode_steps", C.c_int32), ("num_contacts", C.c_int32),
                 ("final_contacts", C.c_int32), ("hist_len", C.c_int32), ("max_count", C.c_int32),
@@ -70,7 +88,8 @@ class DexsimEpisodeSummary(C.Structure):
 
 EXPORTS = (
     "dexsim_version", "dexsim_error_string", "dexsim_sizeof_state", "dexsim_sizeof_params",
-    "dexsim_sizeof_group", "dexsim_sizeof_step_io", "dexsim_device_info", "dexsim_set_step_impl", "dexsim_reset_predrawn",
+    "dexsim_sizeof_group", "dexsim_sizeof_step_io", "dexsim_sizeof_rollout_io", "dexsim_sizeof_episode_record",
+    "dexsim_device_info", "dexsim_set_step_impl", "dexsim_reset_predrawn",
     "dexsim_reset_philox", "dexsim_step", "dexsim_rollout", "dexsim_fill_policy_actions",
     "dexsim_fill_normal", "dexsim_classify_summary", "dexsim_step_host",
 )
@@ -99,14 +118,16 @@ def lib():
     L.dexsim_version.restype = C.c_int
     L.dexsim_error_string.restype = C.c_char_p
     L.dexsim_error_string.argtypes = [C.c_int]
-    for name in ("dexsim_sizeof_state", "dexsim_sizeof_params", "dexsim_sizeof_group", "dexsim_sizeof_step_io"):
+    for name in ("dexsim_sizeof_state", "dexsim_sizeof_params", "dexsim_sizeof_group", "dexsim_sizeof_step_io",
+                 "dexsim_sizeof_rollout_io", "dexsim_sizeof_episode_record"):
         getattr(L, name).restype = C.c_int
     L.dexsim_device_info.argtypes = [C.POINTER(C.c_int)] * 3
     L.dexsim_set_step_impl.argtypes = [C.c_int]
     L.dexsim_reset_predrawn.argtypes = [C.POINTER(DexsimState), C.POINTER(DexsimParams), vp, vp, vp, vp, vp, vp, vp]
     L.dexsim_reset_philox.argtypes = [C.POINTER(DexsimState), C.POINTER(DexsimParams), vp, vp, vp, i32, vp]
     L.dexsim_step.argtypes = [C.POINTER(DexsimState), C.POINTER(DexsimParams), vp, vp, C.POINTER(DexsimStepIO), vp]
-    L.dexsim_rollout.argtypes = [C.POINTER(DexsimState), C.POINTER(DexsimParams), vp, vp, i32, i32, vp, vp, vp, vp, vp]
+    L.dexsim_rollout.argtypes = [C.POINTER(DexsimState), C.POINTER(DexsimParams), vp, vp, i32, i32,
+                                 C.POINTER(DexsimRolloutIO), vp]
     L.dexsim_fill_policy_actions.argtypes = [C.POINTER(DexsimState), C.POINTER(DexsimParams), i32, vp, vp]
     L.dexsim_fill_normal.argtypes = [C.POINTER(DexsimState), C.POINTER(DexsimParams), i32, i32, C.c_float, vp, vp]
     L.dexsim_classify_summary.argtypes = [C.POINTER(DexsimEpisodeSummary), i32, i32, C.POINTER(i32),
@@ -123,6 +144,8 @@ def lib():
     assert L.dexsim_sizeof_params() == C.sizeof(DexsimParams)
     assert L.dexsim_sizeof_group() == C.sizeof(DexsimGroup)
     assert L.dexsim_sizeof_step_io() == C.sizeof(DexsimStepIO)
+    assert L.dexsim_sizeof_rollout_io() == C.sizeof(DexsimRolloutIO)
+    assert L.dexsim_sizeof_episode_record() == C.sizeof(DexsimEpisodeRecord) == 32
     _ = i64
     _lib = L
     return L

@@ -119,24 +119,48 @@ __device__ __forceinline__ void record_episode(unsigned long long* cnt, double* 
     if (rs) { atomicAdd(&rs[0], ret); atomicAdd(&rs[1], __dmul_rn(ret, ret)); }
 }
 
+// Optional per-episode log of a launch (rollout kernel).
+struct EpisodeLog {
+    DexsimEpisodeRecord* rec = nullptr;
+    unsigned long long* count = nullptr;
+    long long capacity = 0;
+    uint32_t t_end = 0;
+};
+
 // Episode end shared by the step kernel's auto-reset and the rollout kernel
 // (loop shape of evaluation/evaluator.py:135-173 / training/episode_utils.py:42-55).
+__device__ __forceinline__ void finish_episode(const EnvRegs& e, const DexsimParams& p, uint32_t gid, uint32_t episode,
+                                               double ep_return, const EpStats& es, bool terminated, int n_c,
+                                               unsigned long long* cnt, double* rs, const EpisodeLog* log) {
+    if (!(cnt || (log && log->rec))) return;
+    DexsimEpisodeSummary s;
+    s.success = p.success_is_terminated ? (terminated ? 1 : 0) : 0;
+    s.episode_steps = e.sc; s.num_contacts = n_c; s.final_contacts = n_c; s.hist_len = e.sc;
+    int sum, sq, f5, l5, mx;
+    epstats_unpack(es, sum, sq, f5, l5, mx);
+    s.max_count = mx; s.sum_counts = sum; s.sum_sq_counts = sq; s.first5_sum = f5; s.last5_sum = l5;
+    int la, lb, tie;
+    classify_summary(s, p.loop_max_steps > 0 ? p.loop_max_steps : p.max_episode_steps, p.success_threshold, la, lb, tie);
+    if (cnt) record_episode(cnt, rs, s.success, e.sc, n_c, la, lb, tie, ep_return);
+    if (log && log->rec) {
+        const unsigned long long slot = atomicAdd(log->count, 1ull);
+        if ((long long)slot < log->capacity) {
+            DexsimEpisodeRecord r;
+            r.env_gid = gid; r.episode = episode; r.steps = e.sc;
+            r.success = (uint8_t)s.success; r.final_contacts = (uint8_t)n_c;
+            r.label_metrics = (uint8_t)la; r.label_taxonomy = (uint8_t)lb;
+            r.episode_reward = ep_return; r.t_end = log->t_end; r.var_tie = (uint32_t)tie;
+            log->rec[slot] = r;
+        }
+    }
+}
+
 __device__ __forceinline__ void finish_and_reset(EnvRegs& e, const DexsimParams& p, const DexsimGroup& grp,
                                                  uint32_t gid, uint32_t& episode, double& ep_return, EpStats& es,
                                                  bool terminated, int n_c, unsigned long long* cnt, double* rs,
-                                                 double& size, double& mass, double& friction) {
-    if (cnt) {
-        DexsimEpisodeSummary s;
-        s.success = p.success_is_terminated ? (terminated ? 1 : 0) : 0;
-        s.episode_steps = e.sc; s.num_contacts = n_c; s.final_contacts = n_c; s.hist_len = e.sc;
-        int sum, sq, f5, l5, mx;
-        epstats_unpack(es, sum, sq, f5, l5, mx);
-        s.max_count = mx; s.sum_counts = sum; s.sum_sq_counts = sq; s.first5_sum = f5; s.last5_sum = l5;
-        int la, lb, tie;
-        classify_summary(s, p.loop_max_steps > 0 ? p.loop_max_steps : p.max_episode_steps, p.success_threshold,
-                         la, lb, tie);
-        record_episode(cnt, rs, s.success, e.sc, n_c, la, lb, tie, ep_return);
-    }
+                                                 double& size, double& mass, double& friction,
+                                                 const EpisodeLog* log = nullptr) {
+    finish_episode(e, p, gid, episode, ep_return, es, terminated, n_c, cnt, rs, log);
     episode += 1u;
     float jp0[NJ], pos[3];
     reset_draws(p.seed, gid, episode, grp, jp0, size, mass, friction, pos);
@@ -354,8 +378,11 @@ template <bool DENSE>
 __global__ void __launch_bounds__(STEP_THREADS, 2)
 rollout_kernel(const DexsimState st, const DexsimParams p, const DexsimGroup* __restrict__ groups,
                const uint16_t* __restrict__ group_of_env, const int k_steps, const int policy_kind,
-               const float* __restrict__ actions, const float* __restrict__ dyn_noise,
-               int64_t* __restrict__ counters, double* __restrict__ ret_sums) {
+               const DexsimRolloutIO rio) {
+    const float* __restrict__ actions = rio.actions;
+    const float* __restrict__ dyn_noise = rio.dyn_noise;
+    int64_t* __restrict__ counters = rio.counters;
+    double* __restrict__ ret_sums = rio.ret_sums;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int G = p.num_groups;
     const bool staged = G <= SMEM_GROUPS_MAX;
@@ -418,10 +445,18 @@ rollout_kernel(const DexsimState st, const DexsimParams p, const DexsimGroup* __
             env_step<DENSE>(e, a, p, r);
             ep_return = __dadd_rn(ep_return, r.total);
             epstats_push(es, e.sc - 1, r.n_c);
+            if (rio.hist && rio.step_base + t < rio.hist_steps) rio.hist[(rio.step_base + t) * ld + i] = (uint8_t)r.n_c;
             const bool done = r.terminated || r.truncated || (p.loop_max_steps > 0 && e.sc >= p.loop_max_steps);
             if (done) {
+                EpisodeLog log;
+                log.rec = rio.ep_log; log.count = reinterpret_cast<unsigned long long*>(rio.ep_log_count);
+                log.capacity = rio.ep_log_capacity; log.t_end = (uint32_t)(rio.step_base + t);
+                if (rio.one_episode) {          // run_episode semantics: stop here, the caller resets
+                    finish_episode(e, p, gid, episode, ep_return, es, r.terminated, r.n_c, cnt, rs, &log);
+                    break;
+                }
                 finish_and_reset(e, p, grp, gid, episode, ep_return, es, r.terminated, r.n_c, cnt, rs,
-                                 size, mass, friction);
+                                 size, mass, friction, &log);
                 params_dirty = true;
             }
         }
@@ -677,6 +712,8 @@ int dexsim_sizeof_state(void) { return (int)sizeof(DexsimState); }
 int dexsim_sizeof_params(void) { return (int)sizeof(DexsimParams); }
 int dexsim_sizeof_group(void) { return (int)sizeof(DexsimGroup); }
 int dexsim_sizeof_step_io(void) { return (int)sizeof(DexsimStepIO); }
+int dexsim_sizeof_rollout_io(void) { return (int)sizeof(DexsimRolloutIO); }
+int dexsim_sizeof_episode_record(void) { return (int)sizeof(DexsimEpisodeRecord); }
 
 int dexsim_device_info(int* sm_count, int* step_ctas_per_sm, int* rollout_ctas_per_sm) {
     DeviceInfo di;
@@ -726,17 +763,20 @@ int dexsim_step(const DexsimState* st, const DexsimParams* p, const DexsimGroup*
 }
 
 int dexsim_rollout(const DexsimState* st, const DexsimParams* p, const DexsimGroup* groups,
-                   const uint16_t* group_of_env, int32_t k_steps, int32_t policy_kind, const float* actions,
-                   const float* dyn_noise, int64_t* counters, double* ret_sums, void* stream) {
+                   const uint16_t* group_of_env, int32_t k_steps, int32_t policy_kind, const DexsimRolloutIO* rio,
+                   void* stream) {
     int rc = check_state(st);
     if (rc) return rc;
     rc = check_params(p, true, groups);
     if (rc) return rc;
+    if (!rio) return DEXSIM_E_NULL;
     if (k_steps < 1) return DEXSIM_E_SIZE;
     if (policy_kind < DEXSIM_POLICY_EXTERNAL || policy_kind > DEXSIM_POLICY_HEURISTIC) return DEXSIM_E_PARAM;
-    if (policy_kind == DEXSIM_POLICY_EXTERNAL && !actions) return DEXSIM_E_NULL;
-    if (ret_sums && !counters) return DEXSIM_E_NULL;
-    if (counters && !st->ep_return) return DEXSIM_E_NULL;   // labels need the per-env history summary
+    if (policy_kind == DEXSIM_POLICY_EXTERNAL && !rio->actions) return DEXSIM_E_NULL;
+    if (rio->ret_sums && !rio->counters) return DEXSIM_E_NULL;
+    if ((rio->counters || rio->ep_log) && !st->ep_return) return DEXSIM_E_NULL;   // labels need the per-env history summary
+    if (rio->ep_log && (!rio->ep_log_count || rio->ep_log_capacity < 0)) return DEXSIM_E_NULL;
+    if (rio->hist && rio->hist_steps < 0) return DEXSIM_E_SIZE;
     if (st->n == 0) return 0;
     DeviceInfo di;
     rc = device_info_cached(di);
@@ -753,11 +793,9 @@ int dexsim_rollout(const DexsimState* st, const DexsimParams* p, const DexsimGro
         ? (size_t)G * (sizeof(DexsimGroup) + DEXSIM_NCOUNTERS * sizeof(unsigned long long) + 2 * sizeof(double)) : 0;
     cudaStream_t s = (cudaStream_t)stream;
     if (p->reward_type == 1)
-        rollout_kernel<true><<<(int)blocks, threads, smem, s>>>(*st, *p, groups, group_of_env, k_steps, policy_kind,
-                                                                actions, dyn_noise, counters, ret_sums);
+        rollout_kernel<true><<<(int)blocks, threads, smem, s>>>(*st, *p, groups, group_of_env, k_steps, policy_kind, *rio);
     else
-        rollout_kernel<false><<<(int)blocks, threads, smem, s>>>(*st, *p, groups, group_of_env, k_steps, policy_kind,
-                                                                 actions, dyn_noise, counters, ret_sums);
+        rollout_kernel<false><<<(int)blocks, threads, smem, s>>>(*st, *p, groups, group_of_env, k_steps, policy_kind, *rio);
     return cuda_rc(cudaGetLastError());
 }
 

@@ -192,6 +192,7 @@ class BatchedManipulationEnv:
         self._obs_view = self._obs[:, :n].t()
         self._info = None
         self._did_reset = False
+        self._rollout_steps = 0
         self._n15 = n * 15
         self._noisy_env = self.observation_noise_std > 0.0 or self.dynamics_noise_std > 0.0
         self._io_has_noise = False
@@ -364,6 +365,12 @@ class BatchedManipulationEnv:
                     self._ptr(mask), int(respawn), self._stream()), "dexsim_reset_philox")
             self._spawned = True
             self._did_reset = True
+            if mask is None:
+                self._rollout_steps = 0
+                if getattr(self, "_ep_log_count", None) is not None:
+                    self._ep_log_count.zero_()
+                if self.rng_mode == "numpy":
+                    self._episode.zero_()
             obs = self._emit_obs(reset=True)
             return obs, self._make_info(after_reset=True)
 
@@ -608,11 +615,41 @@ class BatchedManipulationEnv:
                 self._h_trunc[:n].view(torch.bool), self._h_info)
 
     # ------------------------------------------------------------------ fused rollout
+    def enable_episode_log(self, capacity):
+        """Allocate a device log of finished episodes (one 32-byte record each, the per-episode dict of
+        evaluation/evaluator.py:163-173); ``read_episode_log()`` returns it.  Records beyond the capacity
+        are counted but dropped."""
+        self._ep_log = torch.zeros(int(capacity) * 32, dtype=torch.uint8, device=self.device)
+        self._ep_log_count = torch.zeros(1, dtype=torch.int64, device=self.device)
+        self._ep_log_capacity = int(capacity)
+
+    def enable_history(self, steps):
+        """Allocate a device buffer [steps, ld] of per-step contact COUNTS (the contact_history of
+        evaluation/evaluator.py:148-150 is count-encoded) written by rollout()."""
+        self._hist = torch.zeros(int(steps), self.ld, dtype=torch.uint8, device=self.device)
+        self._hist_steps = int(steps)
+
+    def read_episode_log(self, sort=True):
+        """Finished episodes as a NumPy structured array (fields of DexsimEpisodeRecord), ordered by
+        (t_end, env_gid) -- the order a sequential caller would have seen them in."""
+        if getattr(self, "_ep_log", None) is None:
+            raise RuntimeError("enable_episode_log() first")
+        produced = int(self._ep_log_count.item())
+        kept = min(produced, self._ep_log_capacity)
+        raw = self._ep_log[:kept * 32].cpu().numpy()
+        rec = raw.view(_L.EPISODE_RECORD_DTYPE).copy()
+        if sort and kept:
+            rec = rec[np.lexsort((rec["env_gid"], rec["t_end"]))]
+        self.episode_log_overflow = produced - kept
+        return rec
+
     def rollout(self, k_steps, policy="random", actions=None, dyn_noise=None, loop_max_steps=None,
-                success_is_terminated=None, respawn=True, zero_counters=False):
+                success_is_terminated=None, respawn=True, zero_counters=False, one_episode=False):
         """k env-steps per env in ONE kernel launch with the policy generated in-kernel
         (caller loops of training/episode_utils.py:42-53 / evaluation/evaluator.py:135-158).
-        Returns (counters [G, 18] int64, ret_sums [G, 2] float64) device tensors (accumulated)."""
+        Returns (counters [G, 18] int64, ret_sums [G, 2] float64) device tensors (accumulated).
+        ``one_episode=True``: every env stops at the end of its first episode and is left un-reset
+        (run_episode / evaluate_episode semantics); otherwise finished episodes auto-reset."""
         if not self._did_reset:
             raise RuntimeError("call reset() before rollout()")
         if self._ep_return is None:
@@ -627,20 +664,29 @@ class BatchedManipulationEnv:
             p.success_is_terminated = int(self.success_is_terminated if success_is_terminated is None else success_is_terminated)
             p.respawn = int(respawn)
             keep = []
-            a_ptr = n_ptr = None
+            rio = _lib.DexsimRolloutIO()
             if kind == _L.POLICY_EXTERNAL:
                 a = torch.as_tensor(actions, dtype=torch.float32, device=self.device).reshape(k_steps, self.num_envs, 15)
                 buf = torch.zeros(k_steps, 15, self.ld, dtype=torch.float32, device=self.device)
                 buf[:, :, :self.num_envs] = a.permute(0, 2, 1)
-                a_ptr = buf.data_ptr(); keep.append(buf)
+                rio.actions = buf.data_ptr(); keep.append(buf)
             if dyn_noise is not None:
                 d = torch.as_tensor(dyn_noise, dtype=torch.float32, device=self.device).reshape(k_steps, self.num_envs, 15)
                 nbuf = torch.zeros(k_steps, 15, self.ld, dtype=torch.float32, device=self.device)
                 nbuf[:, :, :self.num_envs] = d.permute(0, 2, 1)
-                n_ptr = nbuf.data_ptr(); keep.append(nbuf)
+                rio.dyn_noise = nbuf.data_ptr(); keep.append(nbuf)
+            rio.counters, rio.ret_sums = self._ptr(self.counters), self._ptr(self.ret_sums)
+            if getattr(self, "_ep_log", None) is not None:
+                rio.ep_log, rio.ep_log_count = self._ep_log.data_ptr(), self._ep_log_count.data_ptr()
+                rio.ep_log_capacity = self._ep_log_capacity
+            if getattr(self, "_hist", None) is not None:
+                rio.hist, rio.hist_steps = self._hist.data_ptr(), self._hist_steps
+            rio.step_base = self._rollout_steps
+            rio.one_episode = int(bool(one_episode))
             _lib.check(self._lib.dexsim_rollout(
                 C.byref(self._state), C.byref(p), self._ptr(self._groups_dev), self._ptr(self._goe), int(k_steps), kind,
-                a_ptr, n_ptr, self._ptr(self.counters), self._ptr(self.ret_sums), self._stream()), "dexsim_rollout")
+                C.byref(rio), self._stream()), "dexsim_rollout")
+            self._rollout_steps += int(k_steps)
             self._spawned = True
         return self.counters, self.ret_sums
 

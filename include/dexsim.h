@@ -156,6 +156,8 @@ int         dexsim_sizeof_state(void);
 int         dexsim_sizeof_params(void);
 int         dexsim_sizeof_group(void);
 int         dexsim_sizeof_step_io(void);
+int         dexsim_sizeof_rollout_io(void);
+int         dexsim_sizeof_episode_record(void);
 /* SM count and max resident CTAs per SM of the step kernel on the current device */
 int         dexsim_device_info(int* sm_count, int* step_ctas_per_sm, int* rollout_ctas_per_sm);
 /* Which step kernel dexsim_step uses: 0 = auto (TMA/mbarrier pipeline when eligible, else the
@@ -187,12 +189,40 @@ int dexsim_step(const DexsimState* st, const DexsimParams* p, const DexsimGroup*
  *      evaluation/evaluator.py:135-158, evaluation/robustness_tests.py:292-304 with the policy
  *      (policies/random_policy.py:40 / policies/heuristic_policy.py:55-62) generated in-kernel.
  *      k_steps env-steps per env in ONE launch, state in registers, episodes auto-reset. ------ */
+
+/* One finished episode = the per-episode dict of evaluation/evaluator.py:163-173 (32 bytes). */
+typedef struct DexsimEpisodeRecord {
+    uint32_t env_gid;          /* global env id */
+    uint32_t episode;          /* which episode of that env finished (0 = first after reset(seed)) */
+    int32_t  steps;            /* "episode_steps" */
+    uint8_t  success;          /* "success" (terminated, or 0 when success_is_terminated == 0) */
+    uint8_t  final_contacts;   /* "num_contacts" == "final_contacts" */
+    uint8_t  label_metrics;    /* evaluation/metrics.py label code or DEXSIM_LABEL_NONE */
+    uint8_t  label_taxonomy;   /* evaluation/failure_taxonomy.py label code or DEXSIM_LABEL_NONE */
+    double   episode_reward;   /* "episode_reward", float64 running sum */
+    uint32_t t_end;            /* step_base + index of the step that ended the episode */
+    uint32_t var_tie;          /* 1: a variance threshold was hit exactly (label resolved as in exact arithmetic) */
+} DexsimEpisodeRecord;
+
+typedef struct DexsimRolloutIO {
+    const float* actions;      /* [k, 15, ld] for DEXSIM_POLICY_EXTERNAL, else NULL */
+    const float* dyn_noise;    /* [k, 15, ld] pre-drawn, or NULL = Philox when the group's sigma_dyn > 0 */
+    int64_t*     counters;     /* [num_groups, DEXSIM_NCOUNTERS] accumulated, or NULL */
+    double*      ret_sums;     /* [num_groups, 2] or NULL */
+    DexsimEpisodeRecord* ep_log;   /* [ep_log_capacity] or NULL */
+    uint64_t*    ep_log_count; /* device scalar: records produced so far; records beyond capacity are dropped */
+    int64_t      ep_log_capacity;
+    uint8_t*     hist;         /* [hist_steps, ld] per-step contact counts (evaluator.py:148-150) or NULL */
+    int64_t      hist_steps;   /* rows of hist; steps with step_base + t >= hist_steps are not recorded */
+    int64_t      step_base;    /* index of this launch's first step (for t_end and hist rows) */
+    int32_t      one_episode;  /* 1: an env stops at the end of its first episode of this launch and is NOT reset
+                                * (run_episode / evaluate_episode semantics: the caller resets it) */
+    int32_t      pad_;
+} DexsimRolloutIO;
+
 int dexsim_rollout(const DexsimState* st, const DexsimParams* p, const DexsimGroup* groups,
                    const uint16_t* group_of_env, int32_t k_steps, int32_t policy_kind,
-                   const float* actions /* [k, 15, ld] for DEXSIM_POLICY_EXTERNAL, else NULL */,
-                   const float* dyn_noise /* [k, 15, ld] pre-drawn, or NULL = Philox when sigma_dyn > 0 */,
-                   int64_t* counters /* [num_groups, DEXSIM_NCOUNTERS] */,
-                   double* ret_sums /* [num_groups, 2] or NULL */, void* stream);
+                   const DexsimRolloutIO* rio, void* stream);
 
 /* ---- RNG exposure (so tests can pre-draw exactly what the fused kernels draw) ---------------- */
 int dexsim_fill_policy_actions(const DexsimState* st, const DexsimParams* p, int32_t policy_kind,

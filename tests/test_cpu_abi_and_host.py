@@ -50,7 +50,7 @@ def test_argument_errors_without_cuda():
     assert L.dexsim_step(C.byref(st), C.byref(p), None, None, C.byref(io), None) == -1002     # ld % 32
     st.ld = 32
     assert L.dexsim_step(C.byref(st), C.byref(p), None, None, C.byref(io), None) == -1001     # NULL arrays
-    assert L.dexsim_rollout(C.byref(st), C.byref(p), None, None, 0, 1, None, None, None, None, None) == -1001
+    assert L.dexsim_rollout(C.byref(st), C.byref(p), None, None, 0, 1, C.byref(_lib.DexsimRolloutIO()), None) == -1001
     assert b"NULL" in L.dexsim_error_string(-1001) and b"size" in L.dexsim_error_string(-1002)
     with pytest.raises(dx.DexsimError):
         _lib.check(-1004, "x")

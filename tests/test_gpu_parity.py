@@ -440,3 +440,116 @@ def test_step_host_matches_device_step(dx, n, chunks, track):
     assert torch.equal(a_env._episode, b_env._episode)
     if track:
         assert torch.equal(a_env.counters, b_env.counters) and int(a_env.counters[:, 0].sum()) > 0
+
+
+class _PatternPolicy:
+    """Deterministic, observation-independent policy (step-indexed pattern) usable on both sides."""
+
+    def __init__(self, T):
+        t = np.arange(T, dtype=np.float32)[:, None]
+        j = np.arange(15, dtype=np.float32)[None, :]
+        self.table = (-0.55 + 0.5 * np.sin(0.37 * t + 0.9 * j)).astype(np.float32)
+        self.t = 0
+
+    def reset(self):
+        self.t = 0
+
+    def select_action(self, obs):
+        a = self.table[self.t]
+        self.t += 1
+        return a
+
+
+def test_batched_evaluator_front_end_matches_reference(dx):
+    """evaluate_heldout_set_batched (one fused launch for all objects x episodes) against the UNMODIFIED
+    Evaluator.evaluate_heldout_set, and the reference's metrics code running on the batched output."""
+    from oracle import ref_harness
+    if not ref_harness.available():
+        pytest.skip("reference (source or byte-compiled) not present")
+    R = ref_harness.load()
+    T, n_eps = 60, 3
+    train = R.CurriculumConfig(object_size_range=(0.03, 0.07), object_mass_range=(0.05, 0.15), friction_range=(0.3, 0.7))
+    held = R.heldout_objects.HeldOutObjectSet(train_config=train, eval_size_range=(0.025, 0.09), num_heldout_objects=6, seed=5)
+    pol = _PatternPolicy(T)
+    for reward_type in ("dense", "sparse"):
+        ref = R.evaluator.Evaluator(pol, held, reward_type=reward_type, max_episode_steps=T).evaluate_heldout_set(n_eps, seed=42)
+        n = 6 * n_eps
+        actions = np.broadcast_to(pol.table[:, None, :], (T, n, 15)).copy()
+        got = dx.evaluation.evaluate_heldout_set_batched(held, policy="external", actions=actions, num_episodes_per_object=n_eps,
+                                                         seed=42, reward_type=reward_type, max_episode_steps=T)
+        assert len(ref["all_episodes"]) == len(got["all_episodes"]) == n
+        assert any(not e["success"] for e in ref["all_episodes"]) and any(e["success"] for e in ref["all_episodes"])
+        for e0, e1 in zip(ref["all_episodes"], got["all_episodes"]):
+            for k in ("episode_steps", "success", "num_contacts", "final_contacts", "contact_history", "object_size",
+                      "object_mass", "friction_coefficient", "object_idx", "episode"):
+                assert e0[k] == e1[k], k
+            assert e1["episode_reward"] == pytest.approx(e0["episode_reward"], rel=1e-12, abs=1e-12)
+        for k, v in ref["metrics"].items():
+            assert got["metrics"][k] == (pytest.approx(v) if isinstance(v, float) else v), k
+        assert got["overall_stats"]["overall_success_rate"] == ref["overall_stats"]["overall_success_rate"]
+        assert got["overall_stats"]["mean_reward"] == pytest.approx(ref["overall_stats"]["mean_reward"], rel=1e-12)
+        for o in ref["per_object_results"]:
+            assert got["per_object_results"][o]["success_rate"] == ref["per_object_results"][o]["success_rate"]
+            assert got["per_object_metrics"][o]["failure_type_frequency"] == ref["per_object_metrics"][o]["failure_type_frequency"]
+        # the reference's own analysis code runs unchanged on the batched output
+        again = R.metrics.EvaluationMetrics(3).compute_aggregate_metrics(got["all_episodes"], max_steps=T)
+        assert again["failure_type_frequency"] == got["metrics"]["failure_type_frequency"]
+        assert again["grasp_success_rate"] == got["metrics"]["grasp_success_rate"]
+        assert isinstance(R.metrics.format_metrics_report(got["metrics"]), str)
+
+
+def test_batched_robustness_front_end_matches_reference(dx):
+    """evaluate_with_noise_batched with zero noise (deterministic) against RobustnessTester.evaluate_with_noise:
+    one reused env object, reset(seed + episode), the object keeps its position after the first episode."""
+    from oracle import ref_harness
+    if not ref_harness.available():
+        pytest.skip("reference (source or byte-compiled) not present")
+    R = ref_harness.load()
+    T, n_ep = 50, 6
+    cfg = R.CurriculumConfig(object_size=0.045, object_mass=0.1, friction_coefficient=0.4)
+    pol = _PatternPolicy(T)
+    ref = R.robustness_tests.RobustnessTester(pol, cfg, reward_type="dense", max_episode_steps=T).evaluate_with_noise(
+        0.0, 0.0, num_episodes=n_ep, seed=7)
+
+    class _Ext:          # the front-end takes fused policies; feed the same table through a tiny shim
+        pass
+
+    import dexterous_rl_manipulation_b200.evaluation as ev
+    orig = ev._first_episode_records_kw
+    table = torch.from_numpy(np.broadcast_to(pol.table[:, None, :], (T, 2, 15)).copy())
+    ev._first_episode_records_kw = lambda env, k, policy, respawn, lm, hist, kw: orig(env, k, "external", respawn, lm, hist,
+                                                                                   {"actions": table})
+    try:
+        got = dx.evaluation.evaluate_with_noise_batched(cfg, "heuristic", 0.0, 0.0, num_episodes=n_ep, seed=7,
+                                                        reward_type="dense", max_episode_steps=T)
+    finally:
+        ev._first_episode_records_kw = orig
+    assert len(got["episodes"]) == len(ref["episodes"]) == n_ep
+    for e0, e1 in zip(ref["episodes"], got["episodes"]):
+        for k in ("success", "episode_steps", "num_contacts", "final_contacts", "contact_history"):
+            assert e0[k] == e1[k], k
+        assert e1["episode_reward"] == pytest.approx(e0["episode_reward"], rel=1e-12, abs=1e-12)
+    for k in ("grasp_success_rate", "mean_episode_length", "failure_type_frequency", "total_episodes"):
+        assert got["metrics"][k] == ref["metrics"][k]
+    # noisy cells: schema + sanity (dynamics noise is Philox, so only statistics are comparable)
+    sweep = dx.evaluation.run_robustness_sweep_batched(cfg, [0.0, 0.05], [0.0, 0.1], policy="heuristic", num_episodes=4,
+                                                       seed=3, max_episode_steps=T, num_replicas=8)
+    assert set(sweep) == {"baseline", "observation_noise", "dynamics_noise", "combined_noise"}
+    assert set(sweep["combined_noise"]) == {"obs_0.000_dyn_0.100", "obs_0.050_dyn_0.000", "obs_0.050_dyn_0.100"}
+    assert sweep["dynamics_noise"][0.1]["metrics"]["total_episodes"] == 32
+    assert sweep["dynamics_noise"][0.1]["noise_levels"] == {"observation_noise_std": 0.0, "dynamics_noise_std": 0.1}
+
+
+def test_seed_variance_front_end_feeds_reference_statistics(dx):
+    from oracle import ref_harness
+    if not ref_harness.available():
+        pytest.skip("reference (source or byte-compiled) not present")
+    R = ref_harness.load()
+    train = R.CurriculumConfig(object_size_range=(0.03, 0.07), object_mass_range=(0.05, 0.15), friction_range=(0.3, 0.7))
+    held = R.heldout_objects.HeldOutObjectSet(train_config=train, eval_size_range=(0.03, 0.08), num_heldout_objects=5, seed=9)
+    per_seed = dx.evaluation.evaluate_seeds_batched(held, [42, 123, 456], policy="heuristic", num_episodes_per_object=3,
+                                                    max_episode_steps=80)
+    analyzer = R.seed_variance.SeedVarianceAnalyzer(policy=None, heldout_set=held, reward_type="dense", max_episode_steps=80)
+    stats = analyzer.compute_variance_statistics(per_seed)          # the reference's statistics, unchanged
+    assert isinstance(stats, dict) and len(stats) > 0
+    assert set(per_seed) == {42, 123, 456} and all(r["metrics"]["total_episodes"] == 15 for r in per_seed.values())
