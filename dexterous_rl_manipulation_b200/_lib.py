@@ -16,7 +16,7 @@ NJ, NF, OBS = 15, 5, 45
 NCOUNTERS = 18
 MAX_GROUPS = 256
 ROW_JP, ROW_JV, ROW_OP, ROW_QUAT, ROW_OV, ROW_CONTACT = 0, 15, 30, 33, 37, 40
-POLICY_EXTERNAL, POLICY_RANDOM, POLICY_HEURISTIC = 0, 1, 2
+POLICY_EXTERNAL, POLICY_RANDOM, POLICY_HEURISTIC, POLICY_LEARNER = 0, 1, 2, 3
 LABEL_NONE = 255
 CNT_EPISODES, CNT_SUCCESSES, CNT_SUM_STEPS, CNT_SUM_FINAL_CONTACTS = 0, 1, 2, 3
 CNT_LABEL_METRICS, CNT_LABEL_TAXONOMY, CNT_VAR_TIES, CNT_SUM_STEPS_SQ = 4, 10, 16, 17
@@ -76,7 +76,10 @@ class DexsimRolloutIO(C.Structure):
     _fields_ = [("actions", C.c_void_p), ("dyn_noise", C.c_void_p), ("counters", C.c_void_p), ("ret_sums", C.c_void_p),
                 ("ep_log", C.c_void_p), ("ep_log_count", C.c_void_p), ("ep_log_capacity", C.c_int64),
                 ("hist", C.c_void_p), ("hist_steps", C.c_int64), ("step_base", C.c_int64),
-                ("one_episode", C.c_int32), ("pad_", C.c_int32)]
+                ("one_episode", C.c_int32), ("pad_", C.c_int32),
+                ("learner_mean", C.c_void_p), ("learner_best", C.c_void_p), ("learner_act_noise", C.c_void_p),
+                ("learner_upd_noise", C.c_void_p), ("learner_exploration", C.c_float), ("learner_lr", C.c_float),
+                ("learner_clip", C.c_float), ("pad2_", C.c_int32)]
 
 
 class DexsimEpisodeSummary(C.Structure):

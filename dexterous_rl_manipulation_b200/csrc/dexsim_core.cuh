@@ -209,7 +209,8 @@ DEXSIM_D U4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, ui
     return U4{c0, c1, c2, c3};
 }
 
-enum : uint32_t { STREAM_RESET = 0, STREAM_POLICY = 1, STREAM_DYN = 2, STREAM_OBS = 3, STREAM_LEARNER = 4 };
+enum : uint32_t { STREAM_RESET = 0, STREAM_POLICY = 1, STREAM_DYN = 2, STREAM_OBS = 3, STREAM_LEARNER_ACT = 4,
+                  STREAM_LEARNER_UPD = 5 };
 
 DEXSIM_D U4 rng_block(uint64_t seed, uint32_t gid, uint32_t episode, uint32_t step, uint32_t stream,
                       uint32_t block) {

@@ -374,7 +374,7 @@ reset_philox_kernel(const DexsimState st, const DexsimParams p, const DexsimGrou
 }
 
 // ---- fused rollout ------------------------------------------------------------------------------------
-template <bool DENSE>
+template <bool DENSE, bool LEARNER>
 __global__ void __launch_bounds__(STEP_THREADS, 2)
 rollout_kernel(const DexsimState st, const DexsimParams p, const DexsimGroup* __restrict__ groups,
                const uint16_t* __restrict__ group_of_env, const int k_steps, const int policy_kind,
@@ -422,10 +422,27 @@ rollout_kernel(const DexsimState st, const DexsimParams p, const DexsimGroup* __
         if (tracking) { es.w0 = st.ep_stats[i]; es.w1 = st.ep_stats[ld + i]; }
         double size = st.size[i], mass = st.mass[i], friction = st.friction[i];
         bool params_dirty = false;
+        float lmean[LEARNER ? NJ : 1];
+        double lbest = 0.0;
+        if (LEARNER) {
+#pragma unroll
+            for (int j = 0; j < NJ; ++j) lmean[j] = rio.learner_mean[j * ld + i];
+            lbest = rio.learner_best[i];
+        }
 
         for (int t = 0; t < k_steps; ++t) {
             float a[NJ];
-            if (policy_kind == DEXSIM_POLICY_EXTERNAL) {
+            if (LEARNER) {                                 // SimpleLearner.select_action, policies/simple_learner.py:60-69
+                float nz[NJ];
+                if (rio.learner_act_noise) {
+#pragma unroll
+                    for (int j = 0; j < NJ; ++j) nz[j] = __ldg(rio.learner_act_noise + ((int64_t)t * NJ + j) * ld + i);
+                } else {
+                    normal_rows<NJ>(p.seed, gid, episode, (uint32_t)e.sc, STREAM_LEARNER_ACT, rio.learner_exploration, nz);
+                }
+#pragma unroll
+                for (int j = 0; j < NJ; ++j) a[j] = clip_f32(__fadd_rn(lmean[j], nz[j]), -1.0f, 1.0f);
+            } else if (policy_kind == DEXSIM_POLICY_EXTERNAL) {
 #pragma unroll
                 for (int j = 0; j < NJ; ++j) a[j] = __ldg(actions + ((int64_t)t * NJ + j) * ld + i);
             } else {
@@ -442,12 +459,30 @@ rollout_kernel(const DexsimState st, const DexsimParams p, const DexsimGroup* __
                 for (int j = 0; j < NJ; ++j) a[j] = clip_f32(__fadd_rn(a[j], nz[j]), -1.0f, 1.0f);
             }
             StepResult r;
+            const uint32_t step_idx = (uint32_t)e.sc;
             env_step<DENSE>(e, a, p, r);
+            if (LEARNER && r.total > lbest) {              // SimpleLearner.update, policies/simple_learner.py:82-95
+                if (rio.learner_upd_noise) {
+#pragma unroll
+                    for (int j = 0; j < NJ; ++j) {
+                        const double adj = __ldg(rio.learner_upd_noise + ((int64_t)t * NJ + j) * ld + i);
+                        lmean[j] = clip_f32((float)__dadd_rn((double)lmean[j], adj), -rio.learner_clip, rio.learner_clip);
+                    }
+                } else {
+                    float nz[NJ];
+                    normal_rows<NJ>(p.seed, gid, episode, step_idx, STREAM_LEARNER_UPD, rio.learner_lr, nz);
+#pragma unroll
+                    for (int j = 0; j < NJ; ++j)
+                        lmean[j] = clip_f32((float)__dadd_rn((double)lmean[j], (double)nz[j]), -rio.learner_clip, rio.learner_clip);
+                }
+                lbest = r.total;
+            }
             ep_return = __dadd_rn(ep_return, r.total);
             epstats_push(es, e.sc - 1, r.n_c);
             if (rio.hist && rio.step_base + t < rio.hist_steps) rio.hist[(rio.step_base + t) * ld + i] = (uint8_t)r.n_c;
             const bool done = r.terminated || r.truncated || (p.loop_max_steps > 0 && e.sc >= p.loop_max_steps);
             if (done) {
+                if (LEARNER) lbest = -INFINITY;              // policy.reset() before the next episode
                 EpisodeLog log;
                 log.rec = rio.ep_log; log.count = reinterpret_cast<unsigned long long*>(rio.ep_log_count);
                 log.capacity = rio.ep_log_capacity; log.t_end = (uint32_t)(rio.step_base + t);
@@ -467,6 +502,11 @@ rollout_kernel(const DexsimState st, const DexsimParams p, const DexsimGroup* __
             st.ep_stats[i] = es.w0; st.ep_stats[ld + i] = es.w1;
         }
         if (params_dirty) { st.size[i] = size; st.mass[i] = mass; st.friction[i] = friction; }
+        if (LEARNER) {
+#pragma unroll
+            for (int j = 0; j < NJ; ++j) rio.learner_mean[j * ld + i] = lmean[j];
+            rio.learner_best[i] = lbest;
+        }
     }
     if (staged && counters) {
         __syncthreads();
@@ -513,7 +553,7 @@ static int query_device(DeviceInfo& d) {
     if (err != cudaSuccess) return -(int)err;
     err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&d.step_ctas, step_kernel<true, false, false>, STEP_THREADS, 0);
     if (err != cudaSuccess) return -(int)err;
-    err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&d.rollout_ctas, rollout_kernel<true>, STEP_THREADS, 0);
+    err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&d.rollout_ctas, rollout_kernel<true, false>, STEP_THREADS, 0);
     if (err != cudaSuccess) return -(int)err;
     d.valid = true;
     return 0;
@@ -771,8 +811,9 @@ int dexsim_rollout(const DexsimState* st, const DexsimParams* p, const DexsimGro
     if (rc) return rc;
     if (!rio) return DEXSIM_E_NULL;
     if (k_steps < 1) return DEXSIM_E_SIZE;
-    if (policy_kind < DEXSIM_POLICY_EXTERNAL || policy_kind > DEXSIM_POLICY_HEURISTIC) return DEXSIM_E_PARAM;
+    if (policy_kind < DEXSIM_POLICY_EXTERNAL || policy_kind > DEXSIM_POLICY_LEARNER) return DEXSIM_E_PARAM;
     if (policy_kind == DEXSIM_POLICY_EXTERNAL && !rio->actions) return DEXSIM_E_NULL;
+    if (policy_kind == DEXSIM_POLICY_LEARNER && (!rio->learner_mean || !rio->learner_best)) return DEXSIM_E_NULL;
     if (rio->ret_sums && !rio->counters) return DEXSIM_E_NULL;
     if ((rio->counters || rio->ep_log) && !st->ep_return) return DEXSIM_E_NULL;   // labels need the per-env history summary
     if (rio->ep_log && (!rio->ep_log_count || rio->ep_log_capacity < 0)) return DEXSIM_E_NULL;
@@ -792,10 +833,11 @@ int dexsim_rollout(const DexsimState* st, const DexsimParams* p, const DexsimGro
     const size_t smem = G <= SMEM_GROUPS_MAX
         ? (size_t)G * (sizeof(DexsimGroup) + DEXSIM_NCOUNTERS * sizeof(unsigned long long) + 2 * sizeof(double)) : 0;
     cudaStream_t s = (cudaStream_t)stream;
-    if (p->reward_type == 1)
-        rollout_kernel<true><<<(int)blocks, threads, smem, s>>>(*st, *p, groups, group_of_env, k_steps, policy_kind, *rio);
-    else
-        rollout_kernel<false><<<(int)blocks, threads, smem, s>>>(*st, *p, groups, group_of_env, k_steps, policy_kind, *rio);
+    const bool dense = p->reward_type == 1, learner = policy_kind == DEXSIM_POLICY_LEARNER;
+    if (dense && learner) rollout_kernel<true, true><<<(int)blocks, threads, smem, s>>>(*st, *p, groups, group_of_env, k_steps, policy_kind, *rio);
+    else if (dense) rollout_kernel<true, false><<<(int)blocks, threads, smem, s>>>(*st, *p, groups, group_of_env, k_steps, policy_kind, *rio);
+    else if (learner) rollout_kernel<false, true><<<(int)blocks, threads, smem, s>>>(*st, *p, groups, group_of_env, k_steps, policy_kind, *rio);
+    else rollout_kernel<false, false><<<(int)blocks, threads, smem, s>>>(*st, *p, groups, group_of_env, k_steps, policy_kind, *rio);
     return cuda_rc(cudaGetLastError());
 }
 

@@ -629,6 +629,21 @@ class BatchedManipulationEnv:
         self._hist = torch.zeros(int(steps), self.ld, dtype=torch.uint8, device=self.device)
         self._hist_steps = int(steps)
 
+    def enable_learner(self, learning_rate=0.01, exploration_noise=0.3, action_clip_range=0.5):
+        """One independent SimpleLearner per env (policies/simple_learner.py:27-47): ``learner_mean``
+        [num_envs, 15] starts at zero, ``learner_best`` at -inf; ``rollout(policy="learner")`` trains them."""
+        self._learner_mean = torch.zeros(15, self.ld, dtype=torch.float32, device=self.device)
+        self._learner_best = torch.full((self.ld,), float("-inf"), dtype=torch.float64, device=self.device)
+        self._learner_hp = (float(exploration_noise), float(learning_rate), float(action_clip_range))
+
+    @property
+    def learner_mean(self):
+        return self._learner_mean[:, :self.num_envs].t()
+
+    @property
+    def learner_best(self):
+        return self._learner_best[:self.num_envs]
+
     def read_episode_log(self, sort=True):
         """Finished episodes as a NumPy structured array (fields of DexsimEpisodeRecord), ordered by
         (t_end, env_gid) -- the order a sequential caller would have seen them in."""
@@ -644,7 +659,8 @@ class BatchedManipulationEnv:
         return rec
 
     def rollout(self, k_steps, policy="random", actions=None, dyn_noise=None, loop_max_steps=None,
-                success_is_terminated=None, respawn=True, zero_counters=False, one_episode=False):
+                success_is_terminated=None, respawn=True, zero_counters=False, one_episode=False,
+                learner_act_noise=None, learner_upd_noise=None):
         """k env-steps per env in ONE kernel launch with the policy generated in-kernel
         (caller loops of training/episode_utils.py:42-53 / evaluation/evaluator.py:135-158).
         Returns (counters [G, 18] int64, ret_sums [G, 2] float64) device tensors (accumulated).
@@ -654,7 +670,10 @@ class BatchedManipulationEnv:
             raise RuntimeError("call reset() before rollout()")
         if self._ep_return is None:
             raise RuntimeError("rollout() needs track_episodes=True (per-env history summaries)")
-        kind = {"external": _L.POLICY_EXTERNAL, "random": _L.POLICY_RANDOM, "heuristic": _L.POLICY_HEURISTIC}[policy]
+        kind = {"external": _L.POLICY_EXTERNAL, "random": _L.POLICY_RANDOM, "heuristic": _L.POLICY_HEURISTIC,
+                "learner": _L.POLICY_LEARNER}[policy]
+        if kind == _L.POLICY_LEARNER and getattr(self, "_learner_mean", None) is None:
+            self.enable_learner()
         with torch.cuda.device(self.device):
             self._sync_groups()
             if zero_counters:
@@ -676,6 +695,16 @@ class BatchedManipulationEnv:
                 nbuf[:, :, :self.num_envs] = d.permute(0, 2, 1)
                 rio.dyn_noise = nbuf.data_ptr(); keep.append(nbuf)
             rio.counters, rio.ret_sums = self._ptr(self.counters), self._ptr(self.ret_sums)
+            if kind == _L.POLICY_LEARNER:
+                rio.learner_mean, rio.learner_best = self._learner_mean.data_ptr(), self._learner_best.data_ptr()
+                rio.learner_exploration, rio.learner_lr, rio.learner_clip = self._learner_hp
+                for name, src, dt in (("learner_act_noise", learner_act_noise, torch.float32),
+                                      ("learner_upd_noise", learner_upd_noise, torch.float64)):
+                    if src is not None:         # pre-drawn [k, n, 15] (parity runs)
+                        d = torch.as_tensor(src, dtype=dt, device=self.device).reshape(k_steps, self.num_envs, 15)
+                        b = torch.zeros(k_steps, 15, self.ld, dtype=dt, device=self.device)
+                        b[:, :, :self.num_envs] = d.permute(0, 2, 1)
+                        setattr(rio, name, b.data_ptr()); keep.append(b)
             if getattr(self, "_ep_log", None) is not None:
                 rio.ep_log, rio.ep_log_count = self._ep_log.data_ptr(), self._ep_log_count.data_ptr()
                 rio.ep_log_capacity = self._ep_log_capacity

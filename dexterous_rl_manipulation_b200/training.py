@@ -1,0 +1,53 @@
+"""Batched counterpart of the reference's learner training loops:
+``train_with_config`` (evaluation/component_ablation.py:80-195), ``train_with_curriculum`` /
+``train_without_curriculum`` (evaluation/curriculum_ablation.py:25-134) -- each of them is
+``for episode: run_episode(env, SimpleLearner)`` on one reused env object.
+
+Here every env of the batch is one such independent training run (its own SimpleLearner, its own
+reused env object): ``num_runs`` runs x ``num_episodes`` episodes execute as fused rollouts with the
+learner in-kernel, and the per-episode records come back from the device log.
+"""
+from typing import Dict
+
+import numpy as np
+
+from .env import BatchedManipulationEnv
+
+
+def train_learners_batched(num_runs: int, num_episodes: int, curriculum_config=None, reward_type: str = "dense",
+                           max_episode_steps: int = 200, learning_rate: float = 0.01, exploration_noise: float = 0.3,
+                           action_clip_range: float = 0.5, seed: int = 42, device="cuda", env_gid0: int = 0,
+                           success_is_terminated: bool = False, scheduler=None) -> Dict:
+    """Returns per-run arrays shaped [num_runs, num_episodes]: ``episode_rewards``, ``episode_steps``,
+    ``successes`` (always False with the reference's run_episode semantics unless
+    ``success_is_terminated=True``) and the final ``mean_action`` [num_runs, 15].
+
+    ``scheduler``: an (unchanged) CurriculumScheduler driven from the finished-episode stream in
+    (step, env) order; its current config is applied to later resets of every run."""
+    from .curriculum import BatchedCurriculumDriver
+    n = max(int(num_runs), 2)
+    env = BatchedManipulationEnv(n, device, max_episode_steps=max_episode_steps, reward_type=reward_type,
+                                 curriculum_config=curriculum_config, track_episodes=True, seed=seed, env_gid0=env_gid0)
+    env.enable_learner(learning_rate, exploration_noise, action_clip_range)
+    env.enable_episode_log(capacity=n)
+    driver = BatchedCurriculumDriver(env, scheduler) if scheduler is not None else None
+    rewards = np.zeros((n, num_episodes))
+    steps = np.zeros((n, num_episodes), np.int32)
+    succ = np.zeros((n, num_episodes), bool)
+    for ep in range(int(num_episodes)):
+        # `for episode: run_episode(env, policy)`: one launch = one episode of every run.  The env object is
+        # reused, so only the first reset samples the spawn; later ones keep the object where it was left.
+        env.reset(seed=seed if ep == 0 else None)
+        env._ep_log_count.zero_()
+        env.rollout(max_episode_steps, policy="learner", respawn=False, loop_max_steps=max_episode_steps,
+                    success_is_terminated=success_is_terminated, one_episode=True)
+        log = env.read_episode_log()
+        if len(log) != n:
+            raise RuntimeError(f"episode {ep}: {n - len(log)} runs did not finish within {max_episode_steps} steps")
+        i = log["env_gid"].astype(np.int64) - env.env_gid0
+        rewards[i, ep], steps[i, ep], succ[i, ep] = log["episode_reward"], log["steps"], log["success"].astype(bool)
+        if driver is not None:
+            driver.poll()
+    k = int(num_runs)
+    return {"episode_rewards": rewards[:k], "episode_steps": steps[:k], "successes": succ[:k],
+            "mean_action": env.learner_mean[:k].cpu().numpy(), "env": env}

@@ -60,6 +60,7 @@ extern "C" {
 #define DEXSIM_POLICY_EXTERNAL 0
 #define DEXSIM_POLICY_RANDOM 1
 #define DEXSIM_POLICY_HEURISTIC 2
+#define DEXSIM_POLICY_LEARNER 3      /* per-env SimpleLearner, policies/simple_learner.py:13-95 */
 
 /* failure-label codes = enum declaration order of FailureType (evaluation/metrics.py:15-22)
  * and FailureMode (evaluation/failure_taxonomy.py:14-26) */
@@ -218,6 +219,16 @@ typedef struct DexsimRolloutIO {
     int32_t      one_episode;  /* 1: an env stops at the end of its first episode of this launch and is NOT reset
                                 * (run_episode / evaluate_episode semantics: the caller resets it) */
     int32_t      pad_;
+    /* DEXSIM_POLICY_LEARNER: one independent SimpleLearner per env (policies/simple_learner.py).
+     * action = clip(mean + float32 N(0, exploration)) (:60-69); after every step, if reward > best:
+     * mean = clip(float32(mean + float64 N(0, lr)), +-clip), best = reward (:82-95); best = -inf at
+     * every episode start (policy.reset(), training/episode_utils.py:35-36). */
+    float*       learner_mean;       /* [15, ld] float32 in/out */
+    double*      learner_best;       /* [ld] float64 in/out */
+    const float* learner_act_noise;  /* [k, 15, ld] pre-drawn (already scaled) or NULL = Philox stream 4 */
+    const double* learner_upd_noise; /* [k, 15, ld] pre-drawn float64 (already scaled) or NULL = Philox stream 5 */
+    float        learner_exploration, learner_lr, learner_clip;
+    int32_t      pad2_;
 } DexsimRolloutIO;
 
 int dexsim_rollout(const DexsimState* st, const DexsimParams* p, const DexsimGroup* groups,

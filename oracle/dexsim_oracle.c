@@ -431,7 +431,7 @@ void dexo_policy_action(uint64_t seed, uint32_t env_gid, uint32_t episode, uint3
 typedef struct {
     dexo_env* e; int64_t lo, hi, n; const dexo_params* p; const dexo_group* groups;
     const uint16_t* group_of_env; const dexo_rollout_cfg* cfg; const float* actions;
-    const float* dyn_noise; int64_t* counters; double* ret_sums;
+    const float* dyn_noise; int64_t* counters; double* ret_sums; const dexo_learner* learner;
 } rollout_job;
 
 static void finish_episode(dexo_env* e, const dexo_params* p, const dexo_rollout_cfg* cfg,
@@ -464,16 +464,30 @@ static void* rollout_worker(void* arg) {
         double* rs = j->ret_sums + (int64_t)g * 2;
         for (int t = 0; t < cfg->k_steps; ++t) {
             float a[DEXO_NJ];
-            if (cfg->policy_kind == 0) memcpy(a, j->actions + ((int64_t)t * j->n + i) * DEXO_NJ, sizeof a);
+            const dexo_learner* L = j->learner;
+            if (L) {                  /* SimpleLearner.select_action, policies/simple_learner.py:60-69 */
+                const float* nz = L->act_noise + ((int64_t)t * j->n + i) * DEXO_NJ;
+                for (int q = 0; q < DEXO_NJ; ++q) a[q] = clip_f32(L->mean[i * DEXO_NJ + q] + nz[q], -1.0f, 1.0f);
+            }
+            else if (cfg->policy_kind == 0) memcpy(a, j->actions + ((int64_t)t * j->n + i) * DEXO_NJ, sizeof a);
             else dexo_policy_action(cfg->seed, gid, e->episode, (uint32_t)e->step_count, cfg->policy_kind, a);
             const float* dn = j->dyn_noise ? j->dyn_noise + ((int64_t)t * j->n + i) * DEXO_NJ : NULL;
             dexo_reward r; int32_t te, tr;
             dexo_step_noisy(e, j->p, a, dn, NULL, NULL, &r, &te, &tr);
+            if (L && r.total > L->best[i]) {                         /* SimpleLearner.update, :82-95 */
+                const double* un = L->upd_noise + ((int64_t)t * j->n + i) * DEXO_NJ;
+                for (int q = 0; q < DEXO_NJ; ++q) {
+                    const float m = (float)((double)L->mean[i * DEXO_NJ + q] + un[q]);   /* float32 array += float64 array */
+                    L->mean[i * DEXO_NJ + q] = clip_f32(m, -L->clip_range, L->clip_range);
+                }
+                L->best[i] = r.total;
+            }
             e->ep_return += r.total;                                 /* evaluator.py:144 */
             if (e->ep_steps < DEXO_HIST_MAX) e->hist[e->ep_steps] = (uint8_t)e->num_contacts;
             e->ep_steps += 1;                                        /* evaluator.py:145 */
             if (te || tr || e->ep_steps >= cfg->loop_max_steps) {    /* evaluator.py:156, :135 */
                 finish_episode(e, j->p, cfg, te, cnt, rs);
+                if (L) L->best[i] = -INFINITY;                       /* policy.reset(), episode_utils.py:35-36 */
                 e->episode += 1;
                 float jp0[DEXO_NJ], pos[3]; double size, mass, fric;
                 dexo_reset_draws(cfg->seed, gid, e->episode, grp, jp0, &size, &mass, &fric, pos);
@@ -484,22 +498,21 @@ static void* rollout_worker(void* arg) {
     return NULL;
 }
 
-void dexo_rollout(dexo_env* e, int64_t n, const dexo_params* p, const dexo_group* groups,
-                  const uint16_t* group_of_env, const dexo_rollout_cfg* cfg, const float* actions,
-                  const float* dyn_noise, int64_t* counters, double* ret_sums) {
+static void rollout_impl(dexo_env* e, int64_t n, const dexo_params* p, const dexo_group* groups,
+                         const uint16_t* group_of_env, const dexo_rollout_cfg* cfg, const float* actions,
+                         const float* dyn_noise, const dexo_learner* learner, int64_t* counters, double* ret_sums) {
     int threads = cfg->threads < 1 ? 1 : cfg->threads;
     if (threads > 256) threads = 256;
     if ((int64_t)threads > n) threads = (int)(n > 0 ? n : 1);
     const int G = cfg->num_groups;
-    /* per-thread integer counters; the float64 return sums are accumulated in env order by
-     * ONE thread afterwards would change nothing for integers, but float sums depend on order,
-     * so ret_sums is only guaranteed reproducible with threads == 1. */
+    /* per-thread integer counters; the float64 return sums depend on the summation order, so
+     * ret_sums is only bit-reproducible with threads == 1. */
     int64_t* tc = (int64_t*)calloc((size_t)threads * G * DEXO_NCOUNTERS, sizeof(int64_t));
     double* tr = (double*)calloc((size_t)threads * G * 2, sizeof(double));
     rollout_job jobs[256]; pthread_t tid[256];
     for (int t = 0; t < threads; ++t) {
         rollout_job j = {e, n * t / threads, n * (t + 1) / threads, n, p, groups, group_of_env, cfg,
-                         actions, dyn_noise, tc + (size_t)t * G * DEXO_NCOUNTERS, tr + (size_t)t * G * 2};
+                         actions, dyn_noise, tc + (size_t)t * G * DEXO_NCOUNTERS, tr + (size_t)t * G * 2, learner};
         jobs[t] = j;
     }
     if (threads == 1) rollout_worker(&jobs[0]);
@@ -512,6 +525,18 @@ void dexo_rollout(dexo_env* e, int64_t n, const dexo_params* p, const dexo_group
         for (int k = 0; k < G * 2; ++k) ret_sums[k] += tr[(size_t)t * G * 2 + k];
     }
     free(tc); free(tr);
+}
+
+void dexo_rollout(dexo_env* e, int64_t n, const dexo_params* p, const dexo_group* groups,
+                  const uint16_t* group_of_env, const dexo_rollout_cfg* cfg, const float* actions,
+                  const float* dyn_noise, int64_t* counters, double* ret_sums) {
+    rollout_impl(e, n, p, groups, group_of_env, cfg, actions, dyn_noise, NULL, counters, ret_sums);
+}
+
+void dexo_rollout_learner(dexo_env* e, int64_t n, const dexo_params* p, const dexo_group* groups,
+                          const uint16_t* group_of_env, const dexo_rollout_cfg* cfg, const dexo_learner* L,
+                          int64_t* counters, double* ret_sums) {
+    rollout_impl(e, n, p, groups, group_of_env, cfg, NULL, NULL, L, counters, ret_sums);
 }
 
 int32_t dexo_sizeof_env(void) { return (int32_t)sizeof(dexo_env); }

@@ -141,6 +141,23 @@ void dexo_rollout(dexo_env* e, int64_t n, const dexo_params* p, const dexo_group
                   int64_t* counters /* [num_groups, DEXO_NCOUNTERS] accumulated */,
                   double* ret_sums /* [num_groups, 2]: sum, sum of squares of episode returns */);
 
+/* SimpleLearner (policies/simple_learner.py:13-95) as a per-env policy inside the rollout:
+ * mean[n,15] float32 and best[n] float64 persist across calls; the normal draws of select_action
+ * (:60-64, sigma = exploration noise, cast to float32) and update (:84-88, sigma = learning rate,
+ * float64 like the reference's) are PRE-DRAWN by the caller. */
+typedef struct {
+    float*  mean;              /* [n, 15] in/out */
+    double* best;              /* [n] in/out; -inf after policy.reset() */
+    const float* act_noise;    /* [k, n, 15] already scaled by exploration_noise */
+    const double* upd_noise;   /* [k, n, 15] float64, already scaled by learning_rate */
+    float   clip_range;        /* action_clip_range, :90-94 */
+    int32_t pad_;
+} dexo_learner;
+
+void dexo_rollout_learner(dexo_env* e, int64_t n, const dexo_params* p, const dexo_group* groups,
+                          const uint16_t* group_of_env, const dexo_rollout_cfg* cfg, const dexo_learner* L,
+                          int64_t* counters, double* ret_sums);
+
 int32_t dexo_sizeof_env(void);
 int32_t dexo_sizeof_group(void);
 

@@ -42,6 +42,9 @@ ENV_DTYPE = np.dtype([
     ("hist", "u1", (HIST_MAX,)),
 ], align=True)
 
+LEARNER_DTYPE = np.dtype([("mean", "u8"), ("best", "u8"), ("act_noise", "u8"), ("upd_noise", "u8"),
+                          ("clip_range", "f4"), ("pad_", "i4")], align=True)
+
 ROLLOUT_DTYPE = np.dtype([
     ("seed", "u8"), ("env_gid0", "i8"), ("k_steps", "i4"), ("policy_kind", "i4"), ("respawn", "i4"),
     ("success_is_terminated", "i4"), ("loop_max_steps", "i4"), ("num_groups", "i4"),
@@ -179,6 +182,30 @@ class OracleBatch:
         self.lib.dexo_rollout(_p(self.env), C.c_int64(self.n), _p(self.params), _p(groups), _p(group_of_env),
                               _p(cfg), _p(actions), _p(dyn_noise), _p(counters), _p(ret_sums))
         return counters, ret_sums
+
+
+def rollout_learner(batch, groups, k_steps, seed, mean, best, act_noise, upd_noise, clip_range=0.5, respawn=False,
+                    success_is_terminated=False, loop_max_steps=None, env_gid0=0, counters=None, ret_sums=None):
+    """SimpleLearner rollout (policies/simple_learner.py) on an OracleBatch; mean [n,15] float32 and best [n]
+    float64 are updated in place; act_noise [k, n, 15] float32 and upd_noise [k, n, 15] float64 are pre-drawn."""
+    groups = np.ascontiguousarray(groups)
+    G = groups.shape[0]
+    cfg = np.zeros(1, ROLLOUT_DTYPE)
+    cfg["seed"], cfg["env_gid0"], cfg["k_steps"], cfg["policy_kind"] = seed, env_gid0, k_steps, 3
+    cfg["respawn"], cfg["success_is_terminated"] = int(respawn), int(success_is_terminated)
+    cfg["loop_max_steps"] = int(batch.params["max_episode_steps"][0]) if loop_max_steps is None else loop_max_steps
+    cfg["num_groups"], cfg["threads"] = G, 1
+    counters = np.zeros((G, NCOUNTERS), np.int64) if counters is None else counters
+    ret_sums = np.zeros((G, 2), np.float64) if ret_sums is None else ret_sums
+    assert mean.dtype == np.float32 and mean.flags.c_contiguous and best.dtype == np.float64
+    act_noise = np.ascontiguousarray(act_noise, np.float32).reshape(k_steps, batch.n, NJ)
+    upd_noise = np.ascontiguousarray(upd_noise, np.float64).reshape(k_steps, batch.n, NJ)
+    L = np.zeros(1, LEARNER_DTYPE)
+    L["mean"], L["best"] = mean.ctypes.data, best.ctypes.data
+    L["act_noise"], L["upd_noise"], L["clip_range"] = act_noise.ctypes.data, upd_noise.ctypes.data, clip_range
+    batch.lib.dexo_rollout_learner(_p(batch.env), C.c_int64(batch.n), _p(batch.params), _p(groups), None, _p(cfg), _p(L),
+                                   _p(counters), _p(ret_sums))
+    return counters, ret_sums
 
 
 def reset_draws(seed, env_gid, episode, group):

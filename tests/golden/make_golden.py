@@ -11,6 +11,7 @@ Outputs (committed):
     noise.npz    CombinedNoiseWrapper trajectories with the wrapper's normal draws recorded
     labels.npz   both failure classifiers on synthetic episodes (ties included)
     episodes.npz Evaluator.evaluate_episode / run_episode records with the policy's actions
+    learner.npz  run_episode + SimpleLearner on a reused env, with the learner's normal draws recorded
     scheduler.npz CurriculumScheduler decisions on random success streams
     anchors.json scalar anchors quoted in SURVEY.md 8c and the reference tests' known answers
 """
@@ -375,7 +376,59 @@ def gen_scheduler():
     print("scheduler.npz: 12 streams x 300 episodes; progressions:", int(np.sum(recs["progressed"])))
 
 
+def gen_learner():
+    """run_episode (training/episode_utils.py:13-55) with SimpleLearner (policies/simple_learner.py) on ONE reused
+    env object, 4 consecutive episodes per case; the learner's np.random.normal draws are recorded so that they
+    can be replayed as pre-drawn tensors (select_action: sigma 0.3 -> float32; update: sigma lr, float64)."""
+    K, EPS = 60, 4
+    rec = {k: [] for k in ("dense", "jp0", "size", "mass", "friction", "pos", "act_noise", "upd_noise", "steps",
+                           "reward", "final_mean", "final_contacts")}
+    orig = np.random.normal
+    for cname in ("easy", "medium", "hard"):
+        cfg = getattr(CC, cname)()
+        for rtype in ("dense", "sparse"):
+            env = R.DexterousManipulationEnv(curriculum_config=cfg, reward_type=rtype, max_episode_steps=200)
+            pol = R.policies.SimpleLearner(env.action_space, learning_rate=0.01)
+            draws = []
+
+            def recorder(loc, scale, size=None):
+                x = orig(loc, scale, size=size)
+                draws.append((scale, np.array(x)))
+                return x
+
+            np.random.normal = recorder
+            np.random.seed(5)
+            jp0, pos, act, upd, steps, rew, fc = [], [], [], [], [], [], []
+            try:
+                for ep in range(EPS):
+                    env._np_random = np.random.Generator(np.random.PCG64(np.random.SeedSequence(11 + ep)))
+                    twin = R.DexterousManipulationEnv(curriculum_config=cfg)
+                    twin._np_random = np.random.Generator(np.random.PCG64(np.random.SeedSequence(11 + ep)))
+                    twin.reset()
+                    jp0.append(twin.joint_positions.copy()); pos.append(twin.object_position.astype(np.float32))
+                    before = len(draws)
+                    _, n_steps, total = R.episode_utils.run_episode(env, pol, max_steps=K)
+                    a = np.zeros((K, 15), np.float32); u = np.zeros((K, 15), np.float64); t = -1
+                    for scale, x in draws[before:]:
+                        if scale == 0.3:
+                            t += 1; a[t] = x.astype(np.float32)
+                        else:
+                            u[t] = x
+                    act.append(a); upd.append(u); steps.append(n_steps); rew.append(total)
+                    fc.append(int(np.sum(env.contacts > 0.5)))
+            finally:
+                np.random.normal = orig
+            rec["dense"].append(rtype == "dense"); rec["jp0"].append(jp0); rec["pos"].append(pos)
+            rec["size"].append(cfg.object_size); rec["mass"].append(cfg.object_mass); rec["friction"].append(cfg.friction_coefficient)
+            rec["act_noise"].append(act); rec["upd_noise"].append(upd); rec["steps"].append(steps); rec["reward"].append(rew)
+            rec["final_mean"].append(pol.mean_action.copy()); rec["final_contacts"].append(fc)
+    np.savez_compressed(os.path.join(HERE, "learner.npz"), loop_max_steps=np.int32(K),
+                        **{k: np.asarray(v) for k, v in rec.items()})
+    print("learner.npz:", len(rec["dense"]), "cases x", EPS, "episodes; steps:", rec["steps"])
+
+
 if __name__ == "__main__":
+    gen_learner()
     gen_scheduler()
     gen_traj()
     gen_noise()

@@ -553,3 +553,78 @@ def test_seed_variance_front_end_feeds_reference_statistics(dx):
     stats = analyzer.compute_variance_statistics(per_seed)          # the reference's statistics, unchanged
     assert isinstance(stats, dict) and len(stats) > 0
     assert set(per_seed) == {42, 123, 456} and all(r["metrics"]["total_episodes"] == 15 for r in per_seed.values())
+
+
+def test_fused_simple_learner_matches_reference_golden(dx, golden_dir):
+    """rollout(policy="learner") with the reference learner's own normal draws replayed as pre-drawn tensors:
+    episode length, final contacts, return and the learner's mean action equal run_episode + SimpleLearner."""
+    g = _load(golden_dir, "learner.npz")
+    K = int(g["loop_max_steps"])
+    for c in range(g["dense"].shape[0]):
+        env = dx.BatchedManipulationEnv(2, "cuda", max_episode_steps=200, reward_type="dense" if g["dense"][c] else "sparse",
+                                        track_episodes=True)
+        env.enable_learner(0.01, 0.3, 0.5)
+        env.enable_episode_log(64)
+        for ep in range(g["steps"].shape[1]):
+            n_steps = int(g["steps"][c, ep])
+            two = lambda a: np.stack([a, a])
+            env.reset_from_draws(two(g["jp0"][c, ep]), two(g["size"][c]), two(g["mass"][c]), two(g["friction"][c]),
+                                 two(g["pos"][c, ep]) if ep == 0 else None)
+            env._learner_best.fill_(float("-inf"))
+            env._ep_log_count.zero_()
+            act = np.repeat(g["act_noise"][c, ep, :K][:, None, :], 2, 1)
+            upd = np.repeat(g["upd_noise"][c, ep, :K][:, None, :], 2, 1)
+            env.rollout(K, policy="learner", respawn=False, loop_max_steps=K, success_is_terminated=False, one_episode=True,
+                        learner_act_noise=act, learner_upd_noise=upd)
+            log = env.read_episode_log()
+            assert len(log) == 2 and all(log["steps"] == n_steps) and all(log["success"] == 0)
+            assert all(log["final_contacts"] == g["final_contacts"][c, ep])
+            np.testing.assert_allclose(log["episode_reward"], g["reward"][c, ep], rtol=1e-12)
+        assert np.array_equal(env.learner_mean[0].cpu().numpy(), g["final_mean"][c])
+        assert np.array_equal(env.learner_mean[1].cpu().numpy(), g["final_mean"][c])
+
+
+def test_fused_simple_learner_matches_oracle_at_scale(dx):
+    """2,000 independent learners x 150 steps with auto-reset (reused env objects), pre-drawn normals."""
+    from oracle import oracle
+    CC = dx.CurriculumConfig
+    n, K, seed = 2000, 150, 21
+    cfg = CC.medium()
+    env = dx.BatchedManipulationEnv(n, "cuda", max_episode_steps=40, reward_type="dense", curriculum_config=cfg,
+                                    track_episodes=True, seed=seed)
+    env.enable_learner(0.01, 0.3, 0.5)
+    env.reset(seed=seed)
+    ob = oracle.OracleBatch(n, dense=True, max_episode_steps=40)
+    grp = oracle.make_group(cfg)
+    ob.reset_predrawn(env._obs[:15, :n].t().cpu().numpy(), env._size[:n].cpu().numpy(), env._mass[:n].cpu().numpy(),
+                      env._friction[:n].cpu().numpy(), env._obs[30:33, :n].t().cpu().numpy())
+    rng = np.random.default_rng(4)
+    act = rng.normal(0, 0.3, (K, n, 15)).astype(np.float32)
+    upd = rng.normal(0, 0.01, (K, n, 15))
+    env.rollout(K, policy="learner", respawn=False, loop_max_steps=40, success_is_terminated=False,
+                learner_act_noise=act, learner_upd_noise=upd)
+    mean = np.zeros((n, 15), np.float32); best = np.full(n, -np.inf)
+    cnt, rs = oracle.rollout_learner(ob, grp, K, seed, mean, best, act, upd, respawn=False, loop_max_steps=40)
+    got = env.counters.cpu().numpy()
+    assert got[0, 0] > n and np.array_equal(got[:, :16], cnt[:, :16])
+    assert np.array_equal(env.learner_mean.cpu().numpy(), mean)
+    gb = env.learner_best.cpu().numpy()            # best holds float64 rewards: CUDA and glibc exp differ by <= 1 ulp
+    assert np.array_equal(np.isinf(gb), np.isinf(best))
+    np.testing.assert_allclose(gb[np.isfinite(gb)], best[np.isfinite(best)], rtol=1e-14)
+    assert np.array_equal(env._obs[:, :n].t().cpu().numpy(), ob.observation())
+    np.testing.assert_allclose(env.ret_sums.cpu().numpy(), rs, rtol=1e-9)
+
+
+def test_batched_learner_training_driver(dx):
+    out = dx.training.train_learners_batched(64, 6, curriculum_config=dx.CurriculumConfig.hard(), reward_type="dense",
+                                             max_episode_steps=50, seed=5)
+    assert out["episode_rewards"].shape == (64, 6) and np.isfinite(out["episode_rewards"]).all()
+    assert (out["episode_steps"] >= 1).all() and (out["episode_steps"] <= 50).all()
+    assert not out["successes"].any()                         # run_episode semantics: success is always False
+    assert np.abs(out["mean_action"]).max() <= 0.5 and np.abs(out["mean_action"]).max() > 0.0
+    # Philox-drawn learner noise: exploration std 0.3 shows up in the actions' spread
+    sched = dx.CurriculumScheduler(dx.CurriculumConfig.easy(), dx.CurriculumConfig.hard(), success_rate_threshold=0.3,
+                                   min_episodes_before_progression=20, window_size=15, progression_steps=5)
+    out2 = dx.training.train_learners_batched(64, 4, curriculum_config=dx.CurriculumConfig.easy(), max_episode_steps=50, seed=5,
+                                              success_is_terminated=True, scheduler=sched)
+    assert out2["successes"].any() and sched.current_difficulty_level == 1.0

@@ -162,3 +162,27 @@ def test_rng_draw_ranges():
     assert a.min() >= -1 and a.max() < 1 and abs(a.mean()) < 0.03 and abs(a.std() - 1 / np.sqrt(3)) < 0.02
     h = np.asarray([oracle.policy_action(42, 3, 0, t, 2) for t in range(200)])
     assert h.min() >= -0.6001 and h.max() <= -0.3999
+
+
+def test_simple_learner_rollout(golden_dir):
+    """dexo_rollout_learner against run_episode + SimpleLearner of the unmodified reference (reused env:
+    episodes after the first keep the object position; learner mean carries over, best resets)."""
+    g = _load(golden_dir, "learner.npz")
+    K = int(g["loop_max_steps"])
+    for c in range(g["dense"].shape[0]):
+        ob = oracle.OracleBatch(1, dense=bool(g["dense"][c]), max_episode_steps=200)
+        grp = oracle.make_group(object_size=float(g["size"][c]), object_mass=float(g["mass"][c]),
+                                friction_coefficient=float(g["friction"][c]))
+        mean = np.zeros((1, 15), np.float32)
+        best = np.full(1, -np.inf)
+        for ep in range(g["steps"].shape[1]):
+            n_steps = int(g["steps"][c, ep])
+            ob.reset_predrawn(g["jp0"][c, ep], g["size"][c], g["mass"][c], g["friction"][c],
+                              g["pos"][c, ep] if ep == 0 else None)
+            best[:] = -np.inf
+            cnt, rs = oracle.rollout_learner(ob, grp, n_steps, 0, mean, best, g["act_noise"][c, ep, :n_steps][:, None, :],
+                                             g["upd_noise"][c, ep, :n_steps][:, None, :], loop_max_steps=K)
+            assert cnt[0, 0] == 1 and cnt[0, 2] == n_steps and cnt[0, 3] == g["final_contacts"][c, ep]
+            assert rs[0, 0] == pytest.approx(g["reward"][c, ep], rel=1e-13)
+            # undo the auto-reset of the finished episode: replay is per episode, like run_episode
+        assert np.array_equal(mean[0], g["final_mean"][c])
