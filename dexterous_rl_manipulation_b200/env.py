@@ -510,6 +510,40 @@ class BatchedManipulationEnv:
         return (obs, self._reward[:n], self._terminated[:n].view(torch.bool), self._truncated[:n].view(torch.bool),
                 self._make_info())
 
+    def capture_step(self, action_buffer, steps=1):
+        """CUDA-graph the hot path for small batches, where one step is bound by the ~8 us host launch path
+        rather than by the GPU: returns ``replay()`` which re-runs ``steps`` env-steps reading the actions
+        from ``action_buffer`` (CUDA float32 [num_envs, 15], or [steps, num_envs, 15]; refill it in place
+        between replays) and returns the same persistent output tensors as ``step()``.
+        Kernel parameters (seed, reward weights, group count ...) are frozen at capture time; curriculum
+        updates still apply because the group table is read from device memory at replay."""
+        if self.single or self._noisy_env:
+            raise RuntimeError("capture_step() is for batched, noise-free stepping")
+        a = action_buffer.reshape(steps, self.num_envs, 15)
+        if self._groups_dirty:
+            self._sync_groups()
+        side = torch.cuda.Stream(device=self.device)
+        side.wait_stream(torch.cuda.current_stream(self.device))
+        with torch.cuda.stream(side):                  # warm-up outside capture (lazy module load, attribute calls)
+            state = self.state_dict()
+            self.step(a[0])
+            self.load_state_dict(state)
+        torch.cuda.current_stream(self.device).wait_stream(side)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            for k in range(steps):
+                self.step(a[k])
+        out = self._step_out
+
+        def replay():
+            if self._groups_dirty:
+                self._sync_groups()
+            graph.replay()
+            return out
+
+        replay.graph = graph
+        return replay
+
     def _step_soa(self, action_soa):
         """Step with actions already in the device layout [15, ld] (tests / internal callers)."""
         io = self._io
@@ -735,7 +769,7 @@ class BatchedManipulationEnv:
     def state_dict(self):
         """All device state (checkpoint / resume is a torch.save away)."""
         keys = ("_obs", "_op64", "_thr", "_damp", "_step_count", "_cmask", "_size", "_mass", "_friction",
-                "_episode", "_ep_return", "_ep_stats")
+                "_episode", "_ep_return", "_ep_stats", "counters", "ret_sums")
         return {k: getattr(self, k).clone() for k in keys if getattr(self, k) is not None}
 
     def load_state_dict(self, sd):

@@ -628,3 +628,59 @@ def test_batched_learner_training_driver(dx):
     out2 = dx.training.train_learners_batched(64, 4, curriculum_config=dx.CurriculumConfig.easy(), max_episode_steps=50, seed=5,
                                               success_is_terminated=True, scheduler=sched)
     assert out2["successes"].any() and sched.current_difficulty_level == 1.0
+
+
+def test_capture_step_graph_replay_equals_eager(dx):
+    CC = dx.CurriculumConfig
+    n, steps = 16384, 4
+    kw = dict(max_episode_steps=30, reward_type="dense", curriculum_config=CC.easy(), auto_reset=True, respawn=True,
+              loop_max_steps=30, track_episodes=True, seed=7)
+    a, b = dx.BatchedManipulationEnv(n, "cuda", **kw), dx.BatchedManipulationEnv(n, "cuda", **kw)
+    a.reset(seed=7); b.reset(seed=7)
+    buf = torch.rand(steps, n, 15, device="cuda") * 2 - 1
+    replay = b.capture_step(buf, steps=steps)
+    for it in range(12):
+        buf.copy_(torch.rand(steps, n, 15, device="cuda") * 2 - 1)
+        for k in range(steps):
+            oa = a.step(buf[k])
+        ob = replay()
+        assert torch.equal(oa[0], ob[0]) and torch.equal(oa[1], ob[1]) and torch.equal(oa[2], ob[2])
+    assert torch.equal(a._obs, b._obs) and torch.equal(a.counters, b.counters) and int(a.counters[:, 0].sum()) > n
+
+
+def test_heldout_noise_sweep_full_size_properties(dx):
+    """BASELINE.json configs[2] at full size: 20 held-out objects x 65,536 envs, fused heuristic policy, one group
+    per (object, dynamics-noise level) cell.  Size-independent properties: counter bookkeeping closes, the
+    two-shard sum equals the single-shard table, larger objects are grasped at least as often."""
+    from dexterous_rl_manipulation_b200.config import CurriculumConfig as CC
+    rng = np.random.default_rng(123)
+    sizes = np.sort(rng.uniform(0.03, 0.12, 20))
+    objs = [CC(object_size=float(s), object_mass=float(rng.uniform(0.16, 0.26)), friction_coefficient=float(rng.uniform(0.0, 0.29)))
+            for s in sizes]
+    N, K, seed = 20 * 65536, 200, 42
+    sig = [0.0, 0.05]
+    cfgs = [o for o in objs for _ in sig]
+    sd = [s for _ in objs for s in sig]
+    kw = dict(max_episode_steps=200, reward_type="dense", track_episodes=True, groups=cfgs, group_sigma_dyn=sd, seed=seed)
+    full = dx.BatchedManipulationEnv(N, "cuda", **kw)
+    full.reset(seed=seed)
+    full.rollout(K, policy="heuristic")
+    c = full.counters.cpu().numpy()
+    assert c[:, 0].min() >= N // 40                      # every env of every cell finished at least one episode
+    assert np.array_equal(c[:, 1] + c[:, 4:10].sum(1), c[:, 0])      # success + labelled failures == episodes
+    assert np.array_equal(c[:, 4:10].sum(1), c[:, 10:16].sum(1))     # both classifiers label the same episodes
+    assert c[:, 16].sum() == 0
+    assert (c[:, 2] <= 200 * c[:, 0]).all() and (c[:, 2] >= c[:, 0]).all()
+    rate = (c[:, 1] / c[:, 0]).reshape(20, 2)
+    assert rate[-1, 0] > rate[0, 0] + 0.3                # the largest object is far easier than the smallest
+    assert np.all(np.diff(rate[:, 0]) > -0.02)           # success is (statistically) monotone in object size
+    assert np.abs(rate[:, 0] - rate[:, 1]).max() < 0.05  # sigma_dyn = 0.05 barely moves a closing grasp
+    del full
+    tot = np.zeros_like(c)
+    for r in range(2):
+        lo, hi = dx.distributed.shard_range(N, r, 2)
+        sh = dx.BatchedManipulationEnv(hi - lo, "cuda", env_gid0=lo, **kw)
+        sh.reset(seed=seed); sh.rollout(K, policy="heuristic")
+        tot += sh.counters.cpu().numpy()
+        del sh
+    assert np.array_equal(tot, c)
