@@ -260,6 +260,12 @@ def run_b200(args):
     if rank == 0 and n_gpus == 1 and not args.no_cpu_baseline:
         cpu_base = measure_cpu_baseline(args)      # before CUDA is initialised (workers fork)
 
+    # The contract is ONE JSON line on stdout.  NCCL (and anything else writing to the C-level stdout)
+    # is sent to stderr for the whole run; the JSON line goes to the saved descriptor at the end.
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
+
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
@@ -366,8 +372,8 @@ def run_b200(args):
         tt = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         e2e_s = float(tt.item())
-    e2e = {"value": E * n_gpus * args.e2e_steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": E * 15 * 4,
-           "d2h_bytes_per_step": env.ld * 41 * 4 + E * (4 + 3), "steps": args.e2e_steps,
+    e2e = {"value": E * n_gpus * args.e2e_steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": E * 15 * 4 * n_gpus,
+           "d2h_bytes_per_step": (env.ld * 41 * 4 + E * (4 + 3)) * n_gpus, "steps": args.e2e_steps,
            "note": "obs rows 33-36 (constant quaternion) are not re-copied; 8 chunks, H2D / kernel / D2H overlapped",
            "api": "BatchedManipulationEnv.step_host -> dexsim_step_host"}
     launches += args.e2e_steps
@@ -439,10 +445,11 @@ def run_b200(args):
             "fused_rollout": fused, "sweep": sweep, "clocks": clocks,
             "episodes": int(env.counters[:, 0].sum().item()),
         }
-        print(json.dumps(line))
+        os.write(json_fd, (json.dumps(line) + "\n").encode())
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+    os.close(json_fd)
     return 0
 
 
