@@ -122,6 +122,10 @@ def evaluate_heldout_set_batched(heldout_set, policy: str = "heuristic", num_epi
             rec, counts = recs[o * n_eps + e]
             d = _episode_dict(rec, counts, size[o], mass[o], fric[o])
             d["object_idx"], d["episode"] = o, e
+            # everything needed to re-run exactly this episode with full capture (replay_episode)
+            d["replay"] = {"object_idx": o, "reset_seed": env_seeds[o * n_eps + e], "env_gid": int(rec["env_gid"]),
+                           "philox_episode": int(rec["episode"]), "policy": policy, "policy_seed": int(policy_seed),
+                           "reward_type": reward_type, "max_episode_steps": int(max_episode_steps)}
             obj_results.append(d)
             all_results.append(d)
         object_results[o] = {
@@ -223,3 +227,69 @@ def evaluate_seeds_batched(heldout_set, seeds: Sequence[int], policy="heuristic"
     return {int(s): evaluate_heldout_set_batched(heldout_set, policy, num_episodes_per_object, int(s), reward_type,
                                                  max_episode_steps, device, policy_seed=int(s))
             for s in seeds}
+
+
+def replay_episode(eval_config, reset_seed: int, env_gid: int, philox_episode: int = 0, policy: str = "heuristic",
+                   policy_seed: int = 0, reward_type: str = "dense", max_episode_steps: int = 200, device="cuda",
+                   dynamics_noise_std: float = 0.0) -> Dict:
+    """Re-run ONE episode of a fused rollout step by step with full capture.  Trajectories are a pure
+    function of (reset draws, Philox key, global env id, episode index), so any episode a rollout logged can
+    be reproduced bit for bit later -- this is how failed episodes get the ``states`` / ``actions`` /
+    ``contact_history`` that FailureLogger.log_episode stores (evaluation/failure_logger.py:48-119), without
+    the rollout kernel having to write trajectories for a million envs.
+    Returns {"states": [T+1 x obs[45]], "actions": [T x a[15]], "contacts": [T+1 count-encoded rows],
+    "episode": per-episode dict} in the layout evaluation/evaluator.py:118-173 records."""
+    import ctypes as C
+    kind = {"random": _lib.POLICY_RANDOM, "heuristic": _lib.POLICY_HEURISTIC}[policy]
+    env = BatchedManipulationEnv(2, device, max_episode_steps=max_episode_steps, reward_type=reward_type, rng="numpy",
+                                 groups=[eval_config], seed=policy_seed, env_gid0=int(env_gid),
+                                 dynamics_noise_std=dynamics_noise_std, reward_components=False)
+    obs, info = env.reset(seed=[int(reset_seed), int(reset_seed)])
+    env._episode.fill_(int(philox_episode))
+    act = torch.zeros(15, env.ld, device=env.device)
+    states = [obs[0].cpu().numpy().copy()]
+    n0 = int(info["num_contacts"][0])
+    contacts = [[1.0 if i < n0 else 0.0 for i in range(5)]]
+    actions, total, steps, success = [], 0.0, 0, False
+    for _ in range(int(max_episode_steps)):
+        _lib.check(env._lib.dexsim_fill_policy_actions(C.byref(env._state), C.byref(env._params), kind, act.data_ptr(),
+                                                       env._stream()), "dexsim_fill_policy_actions")
+        a = act[:, :2].t().contiguous()
+        obs, rew, te, tr, info = env.step(a)
+        actions.append(a[0].cpu().numpy().copy())
+        states.append(obs[0].cpu().numpy().copy())
+        nc = int(info["num_contacts"][0])
+        contacts.append([1.0 if i < nc else 0.0 for i in range(5)])
+        total += float(rew[0])
+        steps += 1
+        if bool(te[0]) or bool(tr[0]):
+            success = bool(te[0])
+            break
+    episode = {"episode_reward": total, "episode_steps": steps, "success": success, "num_contacts": nc,
+               "final_contacts": nc, "contact_history": contacts[1:], "object_size": float(eval_config.object_size),
+               "object_mass": float(eval_config.object_mass), "friction_coefficient": float(eval_config.friction_coefficient)}
+    return {"states": states, "actions": actions, "contacts": contacts, "episode": episode}
+
+
+def log_failures_batched(result: Dict, heldout_set, failure_logger, device="cuda") -> int:
+    """Feed every failed episode of an ``evaluate_heldout_set_batched`` result to an (unchanged)
+    FailureLogger, re-creating its full trajectory by deterministic replay; returns the number logged.
+    Mirrors the logging branch of Evaluator.evaluate_episode (evaluation/evaluator.py:97-185)."""
+    logged = 0
+    for ep in result["all_episodes"]:
+        if ep["success"] or "replay" not in ep or ep["replay"]["policy"] not in ("random", "heuristic"):
+            continue
+        rp = ep["replay"]
+        cfg = heldout_set.get_eval_config(rp["object_idx"])
+        tr = replay_episode(cfg, rp["reset_seed"], rp["env_gid"], rp["philox_episode"], rp["policy"], rp["policy_seed"],
+                            rp["reward_type"], rp["max_episode_steps"], device)
+        if tr["episode"]["episode_steps"] != ep["episode_steps"] or tr["episode"]["final_contacts"] != ep["final_contacts"]:
+            raise RuntimeError("replay diverged from the logged episode")
+        metadata = {"seed": rp["reset_seed"], "object_size": ep["object_size"], "object_mass": ep["object_mass"],
+                    "friction_coefficient": ep["friction_coefficient"], "env_gid": rp["env_gid"],
+                    "philox_seed": rp["policy_seed"], "eval_config": cfg.to_dict() if hasattr(cfg, "to_dict") else {}}
+        data = {k: v for k, v in ep.items() if k != "replay"}
+        failure_logger.log_episode(episode_data=data, states=tr["states"], actions=tr["actions"], contacts=tr["contacts"],
+                                   metadata=metadata, max_steps=rp["max_episode_steps"])
+        logged += 1
+    return logged

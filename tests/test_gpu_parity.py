@@ -684,3 +684,54 @@ def test_heldout_noise_sweep_full_size_properties(dx):
         tot += sh.counters.cpu().numpy()
         del sh
     assert np.array_equal(tot, c)
+
+
+def test_failed_episodes_replay_and_feed_failure_logger(dx, tmp_path):
+    """Failure-trajectory capture by deterministic replay: an episode logged by the fused rollout is reproduced
+    step by step (same Philox policy stream), and the reference's FailureLogger stores it unchanged."""
+    CC = dx.CurriculumConfig
+
+    class _Obj:
+        def __init__(self, s, m, f): self.size, self.mass, self.friction = s, m, f
+
+    class _Held:                                   # duck type of evaluation/heldout_objects.py:39-143
+        heldout_objects = [_Obj(0.03, 0.2, 0.1), _Obj(0.05, 0.2, 0.2), _Obj(0.09, 0.2, 0.25)]
+
+        def get_eval_config(self, k):
+            o = self.heldout_objects[k]
+            return CC(object_size=o.size, object_mass=o.mass, friction_coefficient=o.friction)
+
+    held = _Held()
+    res = dx.evaluation.evaluate_heldout_set_batched(held, policy="heuristic", num_episodes_per_object=4, seed=42,
+                                                     reward_type="dense", max_episode_steps=60, policy_seed=9)
+    failed = [e for e in res["all_episodes"] if not e["success"]]
+    ok = [e for e in res["all_episodes"] if e["success"]]
+    assert failed and ok
+    for ep in (failed[0], failed[-1], ok[0]):
+        rp = ep["replay"]
+        tr = dx.evaluation.replay_episode(held.get_eval_config(rp["object_idx"]), rp["reset_seed"], rp["env_gid"],
+                                          rp["philox_episode"], rp["policy"], rp["policy_seed"], rp["reward_type"],
+                                          rp["max_episode_steps"])
+        assert tr["episode"]["episode_steps"] == ep["episode_steps"] and tr["episode"]["success"] == ep["success"]
+        assert tr["episode"]["contact_history"] == ep["contact_history"]
+        assert tr["episode"]["episode_reward"] == pytest.approx(ep["episode_reward"], rel=1e-5)
+        assert len(tr["states"]) == ep["episode_steps"] + 1 and len(tr["actions"]) == ep["episode_steps"]
+        assert all(-0.6001 <= a.min() and a.max() <= -0.3999 for a in tr["actions"])       # heuristic policy range
+    from oracle import ref_harness
+    if not ref_harness.available():
+        return
+    R = ref_harness.load()
+    flog = importlib_failure_logger(R)(log_dir=str(tmp_path), save_full_trajectories=True)
+    n = dx.evaluation.log_failures_batched(res, held, flog)
+    assert n == len(failed) == len(flog.logged_episodes)
+    for entry, ep in zip(flog.logged_episodes, failed):
+        assert entry["failure_mode"] == ep["failure_mode"]              # reference classifier == device label
+        assert entry["episode_steps"] == ep["episode_steps"] and len(entry["states"]) == ep["episode_steps"] + 1
+        assert entry["metadata"]["seed"] == ep["replay"]["reset_seed"]
+    path = flog.save()
+    assert os.path.exists(path)
+
+
+def importlib_failure_logger(R):
+    import importlib
+    return importlib.import_module("evaluation.failure_logger").FailureLogger
