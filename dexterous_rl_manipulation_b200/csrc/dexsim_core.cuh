@@ -34,6 +34,10 @@ constexpr int NOBS = DEXSIM_OBS;
 #if defined(__CUDACC__)
 // n_c / num_fingers for n_c = 0..5, rounded once like the reference's int / int true division
 __constant__ double kContactReward[6] = {0.0 / 5.0, 1.0 / 5.0, 2.0 / 5.0, 3.0 / 5.0, 4.0 / 5.0, 5.0 / 5.0};
+// clip(float32(1 - float32(k / 5)), 0, 1) for k = 0..5 flipped contact bits, the float32 arithmetic of
+// rewards/reward_shaping.py:178-183 folded at compile time (IEEE single-precision division and subtraction)
+__constant__ float kStabilityReward[6] = {1.0f - 0.0f / 5.0f, 1.0f - 1.0f / 5.0f, 1.0f - 2.0f / 5.0f,
+                                          1.0f - 3.0f / 5.0f, 1.0f - 4.0f / 5.0f, 1.0f - 5.0f / 5.0f};
 #endif
 
 struct EnvRegs {
@@ -178,8 +182,7 @@ DEXSIM_D void env_step(EnvRegs& e, const float* a, const DexsimParams& p, StepRe
         if (first) {                                                          // :172-175
             r.stability = 0.0;
         } else {                                                              // :178-183
-            const float changes = (float)__popc(prev ^ e.cmask);
-            r.stability = (double)clip_f32(__fsub_rn(1.0f, __fdiv_rn(changes, 5.0f)), 0.0f, 1.0f);
+            r.stability = (double)kStabilityReward[__popc((prev ^ e.cmask) & 31u)];
         }
         r.total = __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(p.w_distance, r.distance),
                                                 __dmul_rn(p.w_contact, r.contact)),
@@ -227,38 +230,53 @@ DEXSIM_D double lerp_rn(double lo, double hi, double u) {   // low + (high - low
 }
 
 // Philox stand-in for the PCG64 draws of envs/manipulation_env.py:143-161 + experiments/config.py:44-113
+// (DESIGN.md "RNG"): blocks 0-3 -> 15 joints (24-bit uniforms); block 4 -> spawn x, y, z (32-bit uniforms: the
+// position is cast to float32 anyway); blocks 5-6 -> size, mass, friction (53-bit uniforms), generated only
+// when the group actually randomises one of them -- fixed curricula (easy / medium / hard, held-out
+// objects) reset with five Philox blocks instead of seven.
 DEXSIM_D void reset_draws(uint64_t seed, uint32_t gid, uint32_t episode, const DexsimGroup& g, float* jp0,
                           double& size, double& mass, double& friction, float* pos) {
-    uint32_t w[28];
 #pragma unroll
-    for (uint32_t b = 0; b < 7; ++b) {
+    for (uint32_t b = 0; b < 4; ++b) {
         const U4 o = rng_block(seed, gid, episode, 0u, STREAM_RESET, b);
-        w[4 * b] = o.x; w[4 * b + 1] = o.y; w[4 * b + 2] = o.z; w[4 * b + 3] = o.w;
+        const uint32_t w[4] = {o.x, o.y, o.z, o.w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+            if (4 * (int)b + k < NJ) jp0[4 * b + k] = (float)__dadd_rn(-0.1, __dmul_rn(0.2, (double)u24(w[k])));
     }
+    {
+        const U4 o = rng_block(seed, gid, episode, 0u, STREAM_RESET, 4u);
+        const uint32_t w[3] = {o.x, o.y, o.z};
 #pragma unroll
-    for (int j = 0; j < NJ; ++j) jp0[j] = (float)__dadd_rn(-0.1, __dmul_rn(0.2, (double)u24(w[j])));
-    const double d0 = u53(w[16], w[17]), d1 = u53(w[18], w[19]), d2 = u53(w[20], w[21]);
-    size = g.size_ranged ? lerp_rn(g.size_lo, g.size_hi, d0) : g.size;
-    mass = g.mass_ranged ? lerp_rn(g.mass_lo, g.mass_hi, d1) : g.mass;
-    friction = g.fric_ranged ? lerp_rn(g.fric_lo, g.fric_hi, d2) : g.friction;
-#pragma unroll
-    for (int i = 0; i < 3; ++i)
-        pos[i] = (float)lerp_rn(g.spawn_lo[i], g.spawn_hi[i], u53(w[22 + 2 * i], w[23 + 2 * i]));
+        for (int i = 0; i < 3; ++i)
+            pos[i] = (float)lerp_rn(g.spawn_lo[i], g.spawn_hi[i], __dmul_rn((double)w[i], 0x1p-32));
+    }
+    size = g.size; mass = g.mass; friction = g.friction;
+    if (g.size_ranged | g.mass_ranged | g.fric_ranged) {
+        const U4 a = rng_block(seed, gid, episode, 0u, STREAM_RESET, 5u);
+        const U4 b = rng_block(seed, gid, episode, 0u, STREAM_RESET, 6u);
+        if (g.size_ranged) size = lerp_rn(g.size_lo, g.size_hi, u53(a.x, a.y));
+        if (g.mass_ranged) mass = lerp_rn(g.mass_lo, g.mass_hi, u53(a.z, a.w));
+        if (g.fric_ranged) friction = lerp_rn(g.fric_lo, g.fric_hi, u53(b.x, b.y));
+    }
 }
 
 // policies/random_policy.py:40 and policies/heuristic_policy.py:55-62 on Philox bits
 DEXSIM_D void policy_action(uint64_t seed, uint32_t gid, uint32_t episode, uint32_t step, int kind, float* a) {
-    uint32_t w[16];
 #pragma unroll
     for (uint32_t b = 0; b < 4; ++b) {
         const U4 o = rng_block(seed, gid, episode, step, STREAM_POLICY, b);
-        w[4 * b] = o.x; w[4 * b + 1] = o.y; w[4 * b + 2] = o.z; w[4 * b + 3] = o.w;
-    }
+        const uint32_t w[4] = {o.x, o.y, o.z, o.w};
 #pragma unroll
-    for (int j = 0; j < NJ; ++j) {
-        const float u = __fsub_rn(__fmul_rn(2.0f, u24(w[j])), 1.0f);
-        a[j] = (kind == DEXSIM_POLICY_HEURISTIC)
-                   ? clip_f32(__fadd_rn(-0.5f, __fmul_rn(u, 0.1f)), -1.0f, 1.0f) : u;
+        for (int k = 0; k < 4; ++k) {
+            // 2 * u24 - 1 == (x >> 8) * 2^-23 - 1: every intermediate is exact in float32, so the fused form
+            // returns the same bits as the separately rounded one
+            if (4 * (int)b + k < NJ) a[4 * b + k] = __fmaf_rn((float)(w[k] >> 8), 0x1p-23f, -1.0f);
+        }
+    }
+    if (kind == DEXSIM_POLICY_HEURISTIC) {              // warp-uniform: only the selected policy's arithmetic runs
+#pragma unroll
+        for (int j = 0; j < NJ; ++j) a[j] = clip_f32(__fadd_rn(-0.5f, __fmul_rn(a[j], 0.1f)), -1.0f, 1.0f);
     }
 }
 

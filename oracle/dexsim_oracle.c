@@ -393,18 +393,19 @@ static inline double u53(uint32_t a, uint32_t b) {
  * experiments/config.py:44-113: same draw ORDER and distributions, Philox bits. */
 void dexo_reset_draws(uint64_t seed, uint32_t env_gid, uint32_t episode, const dexo_group* g,
                       float* jp0, double* size, double* mass, double* friction, float* pos) {
+    /* blocks 0-3: joints; block 4: spawn x, y, z from 32-bit uniforms; blocks 5-6: size / mass / friction
+     * from 53-bit uniforms, only for groups that randomise them (DESIGN.md "RNG") */
     uint32_t w[28];
     for (uint32_t b = 0; b < 7; ++b) philox_block(seed, env_gid, episode, 0u, 0u, b, w + 4 * b);
     for (int j = 0; j < DEXO_NJ; ++j)
         jp0[j] = (float)(-0.1 + 0.2 * (double)u24(w[j]));     /* U(-0.1, 0.1) -> float32, :143-145 */
-    const double d0 = u53(w[16], w[17]), d1 = u53(w[18], w[19]), d2 = u53(w[20], w[21]);
-    *size     = g->size_ranged ? g->size_lo + (g->size_hi - g->size_lo) * d0 : g->size;
-    *mass     = g->mass_ranged ? g->mass_lo + (g->mass_hi - g->mass_lo) * d1 : g->mass;
-    *friction = g->fric_ranged ? g->fric_lo + (g->fric_hi - g->fric_lo) * d2 : g->friction;
     for (int i = 0; i < 3; ++i) {
-        const double d = u53(w[22 + 2 * i], w[23 + 2 * i]);
+        const double d = (double)w[16 + i] * 0x1p-32;
         pos[i] = (float)(g->spawn_lo[i] + (g->spawn_hi[i] - g->spawn_lo[i]) * d);
     }
+    *size     = g->size_ranged ? g->size_lo + (g->size_hi - g->size_lo) * u53(w[20], w[21]) : g->size;
+    *mass     = g->mass_ranged ? g->mass_lo + (g->mass_hi - g->mass_lo) * u53(w[22], w[23]) : g->mass;
+    *friction = g->fric_ranged ? g->fric_lo + (g->fric_hi - g->fric_lo) * u53(w[24], w[25]) : g->friction;
 }
 
 /* policies/random_policy.py:40 (U(-1,1) float32) and policies/heuristic_policy.py:55-62
