@@ -127,12 +127,14 @@ DEXSIM_D void env_reset(EnvRegs& e, const float* jp0, double size, double fricti
 }
 
 // envs/manipulation_env.py:184-252 + rewards/reward_shaping.py (compute)
-template <bool DENSE>
+// CLIP_ACTION = false only when the caller has already produced actions inside [-1, 1] (in-kernel random /
+// heuristic policy, or an action it clipped itself): np.clip is then the identity and is skipped.
+template <bool DENSE, bool CLIP_ACTION = true>
 DEXSIM_D void env_step(EnvRegs& e, const float* a, const DexsimParams& p, StepResult& r) {
     // :199-207
 #pragma unroll
     for (int j = 0; j < NJ; ++j) {
-        const float aj = clip_f32(a[j], -1.0f, 1.0f);
+        const float aj = CLIP_ACTION ? clip_f32(a[j], -1.0f, 1.0f) : a[j];
         e.jv[j] = __fadd_rn(__fmul_rn(0.9f, e.jv[j]), __fmul_rn(0.1f, aj));
         e.jp[j] = clip_f32(__fadd_rn(e.jp[j], __fmul_rn(e.jv[j], 0.01f)), -1.0f, 1.0f);
     }
@@ -172,8 +174,9 @@ DEXSIM_D void env_step(EnvRegs& e, const float* a, const DexsimParams& p, StepRe
             float s = -0.0f;
 #pragma unroll
             for (int j = 0; j < 3; ++j) {
-                const float v = e.jp[3 * f + j];
-                s = (v < 0.0f) ? __fadd_rn(s, v) : s;
+                // adding fminf(v, 0) == adding v only when v < 0 (NaN joints add 0, like the reference's mask);
+                // the result can differ only in the sign of an all-zero sum, which nothing downstream sees
+                s = __fadd_rn(s, fminf(e.jp[3 * f + j], 0.0f));
             }
             msum = __fadd_rn(msum, -s);
         }

@@ -460,7 +460,13 @@ rollout_kernel(const DexsimState st, const DexsimParams p, const DexsimGroup* __
             }
             StepResult r;
             const uint32_t step_idx = (uint32_t)e.sc;
-            env_step<DENSE>(e, a, p, r);
+            // every action reaching this point is already inside [-1, 1] unless it came from an external tensor:
+            // Philox policies are in range by construction, the noise and learner paths clip after adding
+            if (policy_kind == DEXSIM_POLICY_EXTERNAL && !dyn_noise && !(sigma_dyn > 0.0f)) {
+#pragma unroll
+                for (int j = 0; j < NJ; ++j) a[j] = clip_f32(a[j], -1.0f, 1.0f);
+            }
+            env_step<DENSE, false>(e, a, p, r);
             if (LEARNER && r.total > lbest) {              // SimpleLearner.update, policies/simple_learner.py:82-95
                 if (rio.learner_upd_noise) {
 #pragma unroll
