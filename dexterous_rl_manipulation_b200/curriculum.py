@@ -10,8 +10,9 @@ progressions ever.  A batched env finishes thousands of episodes per step, so th
     progress (difficulty < 1.0), spreading successes evenly through the batch of updates,
   * pushes ``scheduler.get_current_config()`` into ``env.curriculum_config`` when a
     progression happened (component_ablation.py:163-166) -- effective at the next resets,
-  * once the target difficulty is reached, folds further episodes into the scheduler's totals
-    in bulk (no decision is left to make) keeping only a bounded tail of the per-episode lists.
+  * folds the rest of a poll's episodes into the scheduler's totals in bulk (bounded tail of the
+    per-episode lists) and then lets the scheduler's own progression test run on the new totals, which
+    also drives ``StepBasedScheduler`` (step-count milestones).
 
 The scheduler is duck-typed: ``update``, ``get_current_config`` and the public attributes
 ``current_difficulty_level``, ``episode_successes``, ``episode_steps``, ``total_steps``,
@@ -36,7 +37,7 @@ def spread_successes(episodes: int, successes: int):
 
 
 class BatchedCurriculumDriver:
-    def __init__(self, env, scheduler, max_sequential_updates: int = 100_000):
+    def __init__(self, env, scheduler, max_sequential_updates: int = 4096):
         self.env = env
         self.scheduler = scheduler
         self.max_sequential_updates = int(max_sequential_updates)
@@ -69,6 +70,16 @@ class BatchedCurriculumDriver:
             sch.episode_steps.extend([base] * keep)
             sch.total_steps += rest_steps
             sch.total_episodes += rest
+            # let the scheduler act on the new totals / window exactly as further update() calls would
+            # (CurriculumScheduler: one level per call while the window rate holds; StepBasedScheduler,
+            # experiments/curriculum_scheduler.py:276-335: one milestone per call)
+            should, prog = getattr(sch, "_should_progress", None), getattr(sch, "_progress", None)
+            guard = 0
+            while should is not None and prog is not None and guard < 1024 and should():
+                guard += 1
+                if not prog():
+                    break
+                progressed += 1
         if progressed:
             self.progressions += progressed
             self.env.curriculum_config = sch.get_current_config()

@@ -207,3 +207,32 @@ def test_curriculum_driver_feeds_scheduler_and_pushes_config():
     drv2 = dx.BatchedCurriculumDriver(_FakeEnv(), dx.CurriculumScheduler(CC.easy(), CC.hard()))
     drv2.poll(c); drv2.poll(c)
     assert drv2.scheduler.total_episodes == 100 and drv2.scheduler.total_steps == 15000
+
+
+def test_driver_with_reference_schedulers_when_available():
+    """The driver feeds the reference's UNCHANGED CurriculumScheduler and StepBasedScheduler."""
+    from oracle import ref_harness
+    if not ref_harness.available():
+        pytest.skip("reference not present")
+    R = ref_harness.load()
+    RC = R.CurriculumConfig
+    env = _FakeEnv()
+    sch = R.CurriculumScheduler(RC.easy(), RC.hard(), success_rate_threshold=0.3, min_episodes_before_progression=20,
+                                window_size=15, progression_steps=5)
+    drv = dx.BatchedCurriculumDriver(env, sch)
+    assert drv.feed(3_000_000, 2_900_000, 40_000_000) == 5 and sch.current_difficulty_level == 1.0
+    assert sch.total_episodes == 3_000_000 and sch.total_steps == 40_000_000
+    assert abs(env.curriculum_config.object_size - 0.03) < 1e-12
+    # a failing population never progresses, however many episodes arrive
+    sch2 = R.CurriculumScheduler(RC.easy(), RC.hard(), success_rate_threshold=0.7)
+    drv2 = dx.BatchedCurriculumDriver(_FakeEnv(), sch2)
+    assert drv2.feed(1_000_000, 100_000, 150_000_000) == 0 and sch2.current_difficulty_level == 0.0
+    import importlib
+    SB = importlib.import_module("experiments.curriculum_scheduler").StepBasedScheduler
+    env3 = _FakeEnv()
+    sb = SB(RC.easy(), RC.hard(), step_milestones=[1000, 50_000, 2_000_000, 10_000_000])
+    drv3 = dx.BatchedCurriculumDriver(env3, sb)
+    assert drv3.feed(10, 5, 500) == 0
+    assert drv3.feed(100_000, 50_000, 3_000_000) == 3 and sb.current_difficulty_level == 0.75   # three milestones crossed
+    assert drv3.feed(1_000_000, 1, 20_000_000) == 1 and sb.current_difficulty_level == 1.0
+    assert abs(env3.curriculum_config.friction_coefficient - 0.3) < 1e-12
