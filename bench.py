@@ -375,8 +375,7 @@ def run_b200(args):
     e2e = {"value": E * n_gpus * args.e2e_steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": E * 15 * 4 * n_gpus,
            "d2h_bytes_per_step": (env.ld * 41 * 4 + E * (4 + 3)) * n_gpus, "steps": args.e2e_steps,
            "note": "obs rows 33-36 (constant quaternion) are not re-copied; 8 chunks, H2D / kernel / D2H overlapped",
-           "api": "BatchedManipulationEnv.step_host -> dexsim_step_host"}
-    launches += args.e2e_steps
+           "api": "BatchedManipulationEnv.step_host -> dexsim_step_host", "gpu_launches": args.e2e_steps * 8}
 
     # ---- fused rollout (policy in-kernel, K steps per launch) ---------------------------------------
     fused = None
@@ -441,7 +440,8 @@ def run_b200(args):
                                "poll_every": args.poll_every},
                 "parallelism": f"env-sharded dp{n_gpus}, no data-path collective",
             },
-            "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu_base,
+            "e2e": e2e, "gpu_launches": launches, "gpu_launches_note": "step_tma_kernel launches inside the main timed region (one per step)",
+            "roofline": roofline, "cpu_baseline": cpu_base,
             "fused_rollout": fused, "sweep": sweep, "clocks": clocks,
             "episodes": int(env.counters[:, 0].sum().item()),
         }
