@@ -25,6 +25,7 @@ EPISODE_RECORD_DTYPE = _np.dtype([("env_gid", "u4"), ("episode", "u4"), ("steps"
                                   ("final_contacts", "u1"), ("label_metrics", "u1"), ("label_taxonomy", "u1"),
                                   ("episode_reward", "f8"), ("t_end", "u4"), ("var_tie", "u4")])
 HOST_SKIP_QUAT = 1
+ROLLOUT_NO_DYN_NOISE = 1
 
 # value strings of FailureType (evaluation/metrics.py:15-22) / FailureMode
 # (evaluation/failure_taxonomy.py:14-26) in enum declaration order = device label codes
@@ -76,7 +77,7 @@ class DexsimRolloutIO(C.Structure):
     _fields_ = [("actions", C.c_void_p), ("dyn_noise", C.c_void_p), ("counters", C.c_void_p), ("ret_sums", C.c_void_p),
                 ("ep_log", C.c_void_p), ("ep_log_count", C.c_void_p), ("ep_log_capacity", C.c_int64),
                 ("hist", C.c_void_p), ("hist_steps", C.c_int64), ("step_base", C.c_int64),
-                ("one_episode", C.c_int32), ("pad_", C.c_int32),
+                ("one_episode", C.c_int32), ("flags", C.c_int32),
                 ("learner_mean", C.c_void_p), ("learner_best", C.c_void_p), ("learner_act_noise", C.c_void_p),
                 ("learner_upd_noise", C.c_void_p), ("learner_exploration", C.c_float), ("learner_lr", C.c_float),
                 ("learner_clip", C.c_float), ("pad2_", C.c_int32)]
@@ -92,7 +93,7 @@ class DexsimEpisodeSummary(C.Structure):
 EXPORTS = (
     "dexsim_version", "dexsim_error_string", "dexsim_sizeof_state", "dexsim_sizeof_params",
     "dexsim_sizeof_group", "dexsim_sizeof_step_io", "dexsim_sizeof_rollout_io", "dexsim_sizeof_episode_record",
-    "dexsim_device_info", "dexsim_set_step_impl", "dexsim_reset_predrawn",
+    "dexsim_device_info", "dexsim_set_step_impl", "dexsim_set_rollout_impl", "dexsim_reset_predrawn",
     "dexsim_reset_philox", "dexsim_step", "dexsim_rollout", "dexsim_fill_policy_actions",
     "dexsim_fill_normal", "dexsim_classify_summary", "dexsim_step_host",
 )
@@ -126,6 +127,7 @@ def lib():
         getattr(L, name).restype = C.c_int
     L.dexsim_device_info.argtypes = [C.POINTER(C.c_int)] * 3
     L.dexsim_set_step_impl.argtypes = [C.c_int]
+    L.dexsim_set_rollout_impl.argtypes = [C.c_int]
     L.dexsim_reset_predrawn.argtypes = [C.POINTER(DexsimState), C.POINTER(DexsimParams), vp, vp, vp, vp, vp, vp, vp]
     L.dexsim_reset_philox.argtypes = [C.POINTER(DexsimState), C.POINTER(DexsimParams), vp, vp, vp, i32, vp]
     L.dexsim_step.argtypes = [C.POINTER(DexsimState), C.POINTER(DexsimParams), vp, vp, C.POINTER(DexsimStepIO), vp]
@@ -158,6 +160,11 @@ def set_step_impl(impl):
     """'auto' | 'register' | 'tma' -- which step kernel dexsim_step launches (tests / profiling)."""
     code = {"auto": 0, "register": 1, "tma": 2}[impl]
     check(lib().dexsim_set_step_impl(code), "dexsim_set_step_impl")
+
+
+def set_rollout_impl(impl):
+    """'auto' | 'thread' | 'split' -- which fused-rollout kernel dexsim_rollout launches (tests / profiling)."""
+    check(lib().dexsim_set_rollout_impl({"auto": 0, "thread": 1, "split": 2}[impl]), "dexsim_set_rollout_impl")
 
 
 def check(code, where):

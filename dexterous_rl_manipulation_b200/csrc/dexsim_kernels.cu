@@ -172,6 +172,7 @@ __device__ __forceinline__ void finish_and_reset(EnvRegs& e, const DexsimParams&
 }  // namespace dexsim
 
 #include "dexsim_step_tma.cuh"
+#include "dexsim_rollout_split.cuh"
 
 namespace dexsim {
 
@@ -641,6 +642,7 @@ static int launch_tma_variant(int sm_count, cudaStream_t s, const DexsimState& s
 
 // 0 = auto (TMA pipeline when eligible), 1 = register-resident kernel only, 2 = TMA pipeline required.
 // Initialised from DEXSIM_STEP_IMPL (v1 | v2), changeable at run time with dexsim_set_step_impl().
+static int g_rollout_impl = 0;
 static int g_step_impl = -1;
 static int step_impl_choice() {
     if (g_step_impl < 0) {
@@ -754,6 +756,12 @@ int dexsim_set_step_impl(int impl) {
     return 0;
 }
 
+int dexsim_set_rollout_impl(int impl) {
+    if (impl < 0 || impl > 2) return DEXSIM_E_PARAM;
+    g_rollout_impl = impl;
+    return 0;
+}
+
 int dexsim_sizeof_state(void) { return (int)sizeof(DexsimState); }
 int dexsim_sizeof_params(void) { return (int)sizeof(DexsimParams); }
 int dexsim_sizeof_group(void) { return (int)sizeof(DexsimGroup); }
@@ -840,6 +848,18 @@ int dexsim_rollout(const DexsimState* st, const DexsimParams* p, const DexsimGro
         ? (size_t)G * (sizeof(DexsimGroup) + DEXSIM_NCOUNTERS * sizeof(unsigned long long) + 2 * sizeof(double)) : 0;
     cudaStream_t s = (cudaStream_t)stream;
     const bool dense = p->reward_type == 1, learner = policy_kind == DEXSIM_POLICY_LEARNER;
+    // small batches with an in-kernel policy: 5 lanes per env (dexsim_rollout_split.cuh); the crossover with the
+    // one-thread-per-env kernel was measured between 4k and 16k envs on B200
+    const bool split_ok = (rio->flags & DEXSIM_ROLLOUT_NO_DYN_NOISE) && !rio->dyn_noise && st->ep_return != nullptr &&
+                          (policy_kind == DEXSIM_POLICY_RANDOM || policy_kind == DEXSIM_POLICY_HEURISTIC);
+    if (split_ok && g_rollout_impl != 1 && (g_rollout_impl == 2 || st->n <= 8192)) {
+        const int64_t warps_needed = (st->n + SPLIT_ENVS_PER_WARP - 1) / SPLIT_ENVS_PER_WARP;
+        const int64_t sblocks = (warps_needed * 32 + SPLIT_THREADS - 1) / SPLIT_THREADS;
+        if (sblocks > 0x7FFFFFFFll) return DEXSIM_E_SIZE;
+        if (dense) rollout_split_kernel<true><<<(int)sblocks, SPLIT_THREADS, 0, s>>>(*st, *p, groups, group_of_env, k_steps, policy_kind, *rio);
+        else rollout_split_kernel<false><<<(int)sblocks, SPLIT_THREADS, 0, s>>>(*st, *p, groups, group_of_env, k_steps, policy_kind, *rio);
+        return cuda_rc(cudaGetLastError());
+    }
     if (dense && learner) rollout_kernel<true, true><<<(int)blocks, threads, smem, s>>>(*st, *p, groups, group_of_env, k_steps, policy_kind, *rio);
     else if (dense) rollout_kernel<true, false><<<(int)blocks, threads, smem, s>>>(*st, *p, groups, group_of_env, k_steps, policy_kind, *rio);
     else if (learner) rollout_kernel<false, true><<<(int)blocks, threads, smem, s>>>(*st, *p, groups, group_of_env, k_steps, policy_kind, *rio);

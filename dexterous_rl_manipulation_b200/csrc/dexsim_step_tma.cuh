@@ -91,6 +91,16 @@ __device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.
 __device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
+// Columns a 1-D bulk copy of a tile may touch: the tile's envs rounded up to 32 (copy sizes must be multiples
+// of 16 bytes, also for the 1-byte arrays).  This never leaves the allocation: every array has ld = round_up(n, 32)
+// columns, and sub-states made by dexsim_step_host start at multiples of 1,024 envs of the parent, so
+// round_up(offset + n, 32) <= parent ld.  (Bounding by `ld - base` instead is wrong for sub-states, whose `ld`
+// is the PARENT's row pitch.)
+__device__ __forceinline__ uint32_t tile_cols(int64_t n, int64_t base) {
+    const int64_t left = n - base;
+    return left >= TILE ? (uint32_t)TILE : (uint32_t)((left + 31) & ~(int64_t)31);
+}
+
 // DENSE: reward type.  AOS: action layout [n,15].  TRACK: episode tracking / auto-reset / counters.
 template <bool DENSE, bool AOS, bool TRACK, int STAGES>
 __global__ void __launch_bounds__(TMA_THREADS)
@@ -130,8 +140,7 @@ step_tma_kernel(const DexsimState st, const DexsimParams p, const DexsimGroup* _
                 const int s = k % STAGES;
                 const int64_t base = ((int64_t)blockIdx.x + (int64_t)k * gridDim.x) * TILE;
                 const uint32_t sb = smem_u32(stage_base + (size_t)s * STAGE_BYTES);
-                const int64_t cols64 = (ld - base) < TILE ? (ld - base) : TILE;
-                const uint32_t cols = (uint32_t)cols64;
+                const uint32_t cols = tile_cols(n, base);
                 tma_store_2d(&maps.obs_jpjv, (int)base, DEXSIM_ROW_JP, sb + OFF_JPJV);
                 bulk_store(st.step_count + base, sb + OFF_SC, cols * 4);
                 bulk_store(io.reward + base, sb + OFF_REWARD, cols * 4);
@@ -158,8 +167,7 @@ step_tma_kernel(const DexsimState st, const DexsimParams p, const DexsimGroup* _
                     bulk_wait_read0();
                 }
                 const int64_t base = ((int64_t)blockIdx.x + (int64_t)k * gridDim.x) * TILE;
-                const int64_t cols64 = (ld - base) < TILE ? (ld - base) : TILE;
-                const uint32_t cols = (uint32_t)cols64;
+                const uint32_t cols = tile_cols(n, base);
                 const bool full_tile = (n - base) >= TILE;
                 uint32_t tx = (30 + 3) * TILE * 4 + 3 * TILE * 8 + cols * (8 + 4 + 4 + 1);
                 if (AOS) tx += full_tile ? NJ * TILE * 4 : 0;

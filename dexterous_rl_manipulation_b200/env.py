@@ -746,6 +746,9 @@ class BatchedManipulationEnv:
                 rio.hist, rio.hist_steps = self._hist.data_ptr(), self._hist_steps
             rio.step_base = self._rollout_steps
             rio.one_episode = int(bool(one_episode))
+            so, sd = self._group_sigma if self._group_cfgs is not None else (0.0, self.dynamics_noise_std)
+            no_noise = not np.any(np.asarray(sd, dtype=np.float64) > 0.0)
+            rio.flags = _L.ROLLOUT_NO_DYN_NOISE if no_noise else 0
             _lib.check(self._lib.dexsim_rollout(
                 C.byref(self._state), C.byref(p), self._ptr(self._groups_dev), self._ptr(self._goe), int(k_steps), kind,
                 C.byref(rio), self._stream()), "dexsim_rollout")

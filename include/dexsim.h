@@ -166,6 +166,10 @@ int         dexsim_device_info(int* sm_count, int* step_ctas_per_sm, int* rollou
  * returns DEXSIM_E_PARAM when a call is not eligible).  Both produce identical results; the switch
  * exists for tests and profiling.  Process-wide. */
 int         dexsim_set_step_impl(int impl);
+/* Which fused-rollout kernel dexsim_rollout uses: 0 = auto (the 5-lanes-per-env kernel for small batches with an
+ * in-kernel policy and no dynamics noise, else one thread per env), 1 = one thread per env, 2 = 5 lanes per env
+ * whenever eligible.  Identical results; for tests and profiling.  Process-wide. */
+int         dexsim_set_rollout_impl(int impl);
 
 /* ---- reset: replaces DexterousManipulationEnv.reset, envs/manipulation_env.py:124-182 ------ */
 /* Host-sampled draws (exactly the reference's PCG64 draws when the Python face samples them):
@@ -190,6 +194,8 @@ int dexsim_step(const DexsimState* st, const DexsimParams* p, const DexsimGroup*
  *      evaluation/evaluator.py:135-158, evaluation/robustness_tests.py:292-304 with the policy
  *      (policies/random_policy.py:40 / policies/heuristic_policy.py:55-62) generated in-kernel.
  *      k_steps env-steps per env in ONE launch, state in registers, episodes auto-reset. ------ */
+
+#define DEXSIM_ROLLOUT_NO_DYN_NOISE 1   /* caller asserts that no group has sigma_dyn > 0 (enables the small-batch kernel) */
 
 /* One finished episode = the per-episode dict of evaluation/evaluator.py:163-173 (32 bytes). */
 typedef struct DexsimEpisodeRecord {
@@ -218,7 +224,7 @@ typedef struct DexsimRolloutIO {
     int64_t      step_base;    /* index of this launch's first step (for t_end and hist rows) */
     int32_t      one_episode;  /* 1: an env stops at the end of its first episode of this launch and is NOT reset
                                 * (run_episode / evaluate_episode semantics: the caller resets it) */
-    int32_t      pad_;
+    int32_t      flags;        /* DEXSIM_ROLLOUT_* */
     /* DEXSIM_POLICY_LEARNER: one independent SimpleLearner per env (policies/simple_learner.py).
      * action = clip(mean + float32 N(0, exploration)) (:60-69); after every step, if reward > best:
      * mean = clip(float32(mean + float64 N(0, lr)), +-clip), best = reward (:82-95); best = -inf at

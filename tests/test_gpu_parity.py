@@ -735,3 +735,105 @@ def test_failed_episodes_replay_and_feed_failure_logger(dx, tmp_path):
 def importlib_failure_logger(R):
     import importlib
     return importlib.import_module("evaluation.failure_logger").FailureLogger
+
+
+@pytest.mark.parametrize("n,policy,dense,respawn,one_ep", [(7, "random", True, True, False), (100, "heuristic", False, False, False),
+                                                           (4096, "random", True, True, False), (5003, "heuristic", True, False, False),
+                                                           (1000, "heuristic", True, True, True)])
+def test_split_rollout_kernel_equals_thread_rollout_kernel(dx, n, policy, dense, respawn, one_ep):
+    """The 5-lanes-per-env small-batch rollout kernel and the one-thread-per-env kernel (itself checked against the
+    oracle) must agree on every array, counter, log record and history byte."""
+    from dexterous_rl_manipulation_b200 import _lib
+    CC = dx.CurriculumConfig
+    cfgs = [CC.easy(), CC.hard(), CC(object_size_range=(0.03, 0.09), object_mass_range=(0.05, 0.15), friction_range=(0.3, 0.7))]
+    K, max_steps = 90, 30
+    envs = {}
+    try:
+        for impl in ("thread", "split"):
+            _lib.set_rollout_impl(impl)
+            env = dx.BatchedManipulationEnv(n, "cuda", max_episode_steps=max_steps, reward_type="dense" if dense else "sparse",
+                                            track_episodes=True, groups=cfgs, seed=31, env_gid0=11)
+            env.reset(seed=31)
+            env.enable_episode_log(n * K)                  # worst case: one episode per env per step
+            env.enable_history(K)
+            for chunk in (K // 3, K - K // 3):
+                env.rollout(chunk, policy=policy, respawn=respawn, one_episode=one_ep)
+            envs[impl] = env
+    finally:
+        _lib.set_rollout_impl("auto")
+    a, b = envs["thread"], envs["split"]
+    for name in ("_obs", "_op64", "_thr", "_damp", "_step_count", "_cmask", "_size", "_mass", "_friction", "_episode",
+                 "_ep_stats", "_ep_return", "counters", "_hist"):
+        assert torch.equal(getattr(a, name), getattr(b, name)), name
+    torch.testing.assert_close(a.ret_sums, b.ret_sums, rtol=1e-9, atol=0)
+    la, lb = a.read_episode_log(), b.read_episode_log()
+    order = lambda r: r[np.lexsort((r["episode"], r["env_gid"]))]
+    assert a.episode_log_overflow == 0 and b.episode_log_overflow == 0
+    assert len(la) == len(lb) and len(la) >= (n if not one_ep else 1)
+    assert np.array_equal(order(la), order(lb))
+    if not one_ep:
+        assert int(a.counters[:, 0].sum()) > n
+
+
+def _with_guard_bands(env, guard=4096):
+    """Re-home every device array of the env in the middle of a larger buffer whose margins hold a byte
+    pattern; returns a checker that fails if any kernel wrote outside its array (compute-sanitizer is not
+    available on this pool, so this is the memcheck)."""
+    names = ["_obs", "_op64", "_thr", "_damp", "_step_count", "_cmask", "_size", "_mass", "_friction", "_episode",
+             "_ep_return", "_ep_stats", "_reward", "_terminated", "_truncated", "_num_contacts", "_finished", "_action_dev"]
+    bands = []
+    for name in names:
+        t = getattr(env, name, None)
+        if t is None:
+            continue
+        nbytes = t.numel() * t.element_size()
+        big = torch.full((nbytes + 2 * guard,), 0xA5, dtype=torch.uint8, device=t.device)
+        mid = big[guard:guard + nbytes].view(t.dtype).view(t.shape)
+        mid.copy_(t)
+        setattr(env, name, mid)
+        bands.append((name, big, guard, nbytes))
+    n = env.num_envs
+    env._refresh_structs()
+    env._sync_groups()
+    env._obs_view = env._obs[:, :n].t()
+    env._info = None
+    env._step_out = (env._obs_view, env._reward[:n], env._terminated[:n].view(torch.bool),
+                     env._truncated[:n].view(torch.bool), env._make_info())
+    env._io.counters, env._io.ret_sums = env.counters.data_ptr(), env.ret_sums.data_ptr()
+
+    def check():
+        torch.cuda.synchronize()
+        for name, big, g, nb in bands:
+            assert bool((big[:g] == 0xA5).all()) and bool((big[g + nb:] == 0xA5).all()), f"out-of-bounds write around {name}"
+    return check
+
+
+@pytest.mark.parametrize("n", [130, 5000, 70_001])
+def test_no_out_of_bounds_writes(dx, n):
+    from dexterous_rl_manipulation_b200 import _lib
+    CC = dx.CurriculumConfig
+    env = dx.BatchedManipulationEnv(n, "cuda", max_episode_steps=15, reward_type="dense", auto_reset=True, respawn=True,
+                                    loop_max_steps=15, track_episodes=True, groups=[CC.easy(), CC.hard()], seed=2)
+    check = _with_guard_bands(env)
+    env.reset(seed=2)
+    check()
+    gen = torch.Generator(device="cuda").manual_seed(1)
+    try:
+        for impl in ("tma", "register"):
+            _lib.set_step_impl(impl)
+            for t in range(20):
+                env.step(torch.rand(n, 15, device="cuda", generator=gen) * 2 - 1)
+            check()
+        _lib.set_step_impl("auto")
+        for chunks in (1, 3, 8):
+            for t in range(4):
+                env.step_host(torch.rand(n, 15).mul_(2).sub_(1).pin_memory(), chunks=chunks)
+            check()
+        for impl in ("thread", "split"):
+            _lib.set_rollout_impl(impl)
+            env.rollout(40, policy="heuristic")
+            check()
+    finally:
+        _lib.set_step_impl("auto"); _lib.set_rollout_impl("auto")
+    env.reset()
+    check()
