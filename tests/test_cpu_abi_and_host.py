@@ -236,3 +236,28 @@ def test_driver_with_reference_schedulers_when_available():
     assert drv3.feed(100_000, 50_000, 3_000_000) == 3 and sb.current_difficulty_level == 0.75   # three milestones crossed
     assert drv3.feed(1_000_000, 1, 20_000_000) == 1 and sb.current_difficulty_level == 1.0
     assert abs(env3.curriculum_config.friction_coefficient - 0.3) < 1e-12
+
+
+def test_empty_batch_is_a_no_op_without_cuda():
+    """n == 0 (empty input) returns 0 before any CUDA call; argument checks still apply."""
+    L = _lib.lib()
+    buf = (C.c_char * 256)()
+    ptr = (C.addressof(buf) + 15) & ~15                     # any non-NULL, 16-byte aligned address: never dereferenced
+    st = _lib.DexsimState()
+    st.n, st.ld = 0, 0
+    for name, _ in _lib.DexsimState._fields_[2:12]:
+        setattr(st, name, ptr)
+    p = _lib.DexsimParams()
+    p.reward_type, p.num_groups = 1, 1
+    io = _lib.DexsimStepIO()
+    io.action = io.reward = io.terminated = io.truncated = io.num_contacts = ptr
+    assert L.dexsim_step(C.byref(st), C.byref(p), None, None, C.byref(io), None) == 0
+    assert L.dexsim_reset_predrawn(C.byref(st), C.byref(p), None, ptr, ptr, ptr, ptr, None, None) == 0
+    rio = _lib.DexsimRolloutIO()
+    assert L.dexsim_rollout(C.byref(st), C.byref(p), ptr, None, 5, 1, C.byref(rio), None) == 0
+    rio.counters = ptr                                        # counters without the per-env history summary
+    assert L.dexsim_rollout(C.byref(st), C.byref(p), ptr, None, 5, 1, C.byref(rio), None) == -1001
+    assert L.dexsim_rollout(C.byref(st), C.byref(p), ptr, None, 5, 7, C.byref(_lib.DexsimRolloutIO()), None) == -1004
+    p.reward_type = 5
+    assert L.dexsim_step(C.byref(st), C.byref(p), None, None, C.byref(io), None) == -1004
+    assert L.dexsim_set_step_impl(9) == -1004 and L.dexsim_set_step_impl(0) == 0
