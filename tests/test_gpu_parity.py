@@ -837,3 +837,32 @@ def test_no_out_of_bounds_writes(dx, n):
         _lib.set_step_impl("auto"); _lib.set_rollout_impl("auto")
     env.reset()
     check()
+
+
+def test_masked_reset_touches_only_masked_envs(dx):
+    """options={"mask": ...}: the manual-reset pattern of RL loops that do not use in-kernel auto-reset."""
+    CC = dx.CurriculumConfig
+    n = 3000
+    for rng_mode in ("philox", "numpy"):
+        env = dx.BatchedManipulationEnv(n, "cuda", max_episode_steps=20, reward_type="dense", curriculum_config=CC.easy(),
+                                        rng=rng_mode, seed=4, respawn=True)
+        env.reset(seed=4 if rng_mode == "philox" else list(range(n)))
+        gen = torch.Generator(device="cuda").manual_seed(0)
+        for t in range(12):
+            obs, rew, te, tr, info = env.step(torch.rand(n, 15, device="cuda", generator=gen) - 0.8)
+        done = te | tr
+        assert 0 < int(done.sum()) < n
+        before = {k: getattr(env, k).clone() for k in ("_obs", "_op64", "_step_count", "_cmask", "_episode", "_thr")}
+        obs2, _ = env.reset(options={"mask": done})
+        keep = ~done
+        for k, v in before.items():
+            cur = getattr(env, k)
+            if cur.dim() == 2:
+                assert torch.equal(cur[:, :n][:, keep], v[:, :n][:, keep]), k
+            else:
+                assert torch.equal(cur[:n][keep], v[:n][keep]), k
+        assert int(env._step_count[:n][done].max()) == 0
+        assert torch.equal(env._obs[15:30, :n][:, done], torch.zeros_like(env._obs[15:30, :n][:, done]))   # jv = 0
+        assert float(env._obs[0:15, :n][:, done].abs().max()) <= 0.1                                        # fresh joints
+        if rng_mode == "philox":
+            assert torch.equal(env._episode[:n][done], before["_episode"][:n][done] + 1)
