@@ -14,6 +14,15 @@ from . import _lib
 
 Range = Optional[Tuple[float, float]]
 
+# (size, mass, friction, spawn_distance) of the named presets, experiments/config.py:174-217
+_PRESETS = {"easy": (0.08, 0.05, 0.8, 0.10), "medium": (0.05, 0.1, 0.5, 0.15), "hard": (0.03, 0.2, 0.3, 0.20)}
+
+
+def _maybe_uniform(rng, interval: Range, fixed: float) -> float:
+    """One uniform draw when the field is randomised, the fixed value (and NO draw) otherwise --
+    the draw-count behaviour the reset sequence of envs/manipulation_env.py:151-153 depends on."""
+    return fixed if interval is None else float(rng.uniform(interval[0], interval[1]))
+
 
 @dataclass
 class CurriculumConfig:
@@ -29,29 +38,29 @@ class CurriculumConfig:
     spawn_y_range: Tuple[float, float] = (-0.1, 0.1)
     spawn_z_range: Tuple[float, float] = (0.05, 0.2)
 
-    # samplers with the reference's draw semantics (one uniform per ranged field, none otherwise)
+    # -- samplers (names and draw order are part of the env contract)
     def get_object_size(self, rng) -> float:
-        r = self.object_size_range
-        return float(rng.uniform(r[0], r[1])) if r is not None else self.object_size
+        return _maybe_uniform(rng, self.object_size_range, self.object_size)
 
     def get_object_mass(self, rng) -> float:
-        r = self.object_mass_range
-        return float(rng.uniform(r[0], r[1])) if r is not None else self.object_mass
+        return _maybe_uniform(rng, self.object_mass_range, self.object_mass)
 
     def get_friction_coefficient(self, rng) -> float:
-        r = self.friction_range
-        return float(rng.uniform(r[0], r[1])) if r is not None else self.friction_coefficient
+        return _maybe_uniform(rng, self.friction_range, self.friction_coefficient)
+
+    def get_spawn_distance(self, rng) -> float:
+        return _maybe_uniform(rng, self.spawn_distance_range, self.spawn_distance)
 
     def get_spawn_position(self, rng):
-        return tuple(float(rng.uniform(lo, hi)) for lo, hi in
-                     (self.spawn_x_range, self.spawn_y_range, self.spawn_z_range))
+        return tuple(float(rng.uniform(*axis)) for axis in (self.spawn_x_range, self.spawn_y_range, self.spawn_z_range))
 
+    # -- (de)serialisation compatible with the reference's JSON files (experiments/config_*.json)
     def to_dict(self):
         return asdict(self)
 
     @classmethod
     def from_dict(cls, d):
-        return cls(**d)
+        return cls(**{k: (tuple(v) if isinstance(v, list) else v) for k, v in d.items()})
 
     @classmethod
     def from_json(cls, path):
@@ -63,16 +72,13 @@ class CurriculumConfig:
             json.dump(self.to_dict(), fh, indent=2)
 
     @classmethod
-    def easy(cls):
-        return cls(object_size=0.08, object_mass=0.05, friction_coefficient=0.8, spawn_distance=0.10)
+    def preset(cls, name: str):
+        size, mass, friction, distance = _PRESETS[name]
+        return cls(object_size=size, object_mass=mass, friction_coefficient=friction, spawn_distance=distance)
 
-    @classmethod
-    def medium(cls):
-        return cls(object_size=0.05, object_mass=0.1, friction_coefficient=0.5, spawn_distance=0.15)
 
-    @classmethod
-    def hard(cls):
-        return cls(object_size=0.03, object_mass=0.2, friction_coefficient=0.3, spawn_distance=0.20)
+for _name in _PRESETS:          # CurriculumConfig.easy() / .medium() / .hard()
+    setattr(CurriculumConfig, _name, classmethod(lambda cls, _n=_name: cls.preset(_n)))
 
 
 def _pair(r):
