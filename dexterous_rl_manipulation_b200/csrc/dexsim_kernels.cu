@@ -526,6 +526,27 @@ rollout_kernel(const DexsimState st, const DexsimParams p, const DexsimGroup* __
     }
 }
 
+// ---- single-env read-back ------------------------------------------------------------------------------
+__global__ void pack_env_kernel(const DexsimState st, const DexsimStepIO io, const int64_t i, const int after_reset,
+                                double* __restrict__ out) {
+    const int t = threadIdx.x;
+    const int64_t ld = st.ld;
+    const float* obs = (io.noisy_obs && io.obs_noise) ? io.noisy_obs : st.obs;
+    if (t < NOBS) out[t] = (double)obs[t * ld + i];
+    if (t == 45) out[45] = after_reset ? 0.0 : (double)io.reward[i];
+    if (t == 46) out[46] = after_reset ? 0.0 : (double)io.terminated[i];
+    if (t == 47) out[47] = after_reset ? 0.0 : (double)io.truncated[i];
+    if (t == 48) out[48] = (double)__popc((unsigned)st.cmask[i]);
+    if (t == 49) out[49] = (double)st.step_count[i];
+    if (t >= 50 && t < 53) out[t] = st.op64[(t - 50) * ld + i];
+    if (t == 53) out[53] = st.size[i];
+    if (t == 54) out[54] = st.mass[i];
+    if (t == 55) out[55] = st.friction[i];
+    if (t >= 56 && t < 60) out[t] = (io.reward_comps && !after_reset) ? (double)io.reward_comps[(t - 56) * ld + i] : 0.0;
+    if (t == 60) out[60] = (io.finished && !after_reset) ? (double)io.finished[i] : 0.0;
+    if (t > 60 && t < 64) out[t] = 0.0;
+}
+
 // ---- RNG exposure ------------------------------------------------------------------------------------
 __global__ void fill_policy_kernel(const DexsimState st, const DexsimParams p, int policy_kind, float* __restrict__ out) {
     const int64_t n = st.n, ld = st.ld;
@@ -864,6 +885,16 @@ int dexsim_rollout(const DexsimState* st, const DexsimParams* p, const DexsimGro
     else if (dense) rollout_kernel<true, false><<<(int)blocks, threads, smem, s>>>(*st, *p, groups, group_of_env, k_steps, policy_kind, *rio);
     else if (learner) rollout_kernel<false, true><<<(int)blocks, threads, smem, s>>>(*st, *p, groups, group_of_env, k_steps, policy_kind, *rio);
     else rollout_kernel<false, false><<<(int)blocks, threads, smem, s>>>(*st, *p, groups, group_of_env, k_steps, policy_kind, *rio);
+    return cuda_rc(cudaGetLastError());
+}
+
+int dexsim_pack_env(const DexsimState* st, const DexsimStepIO* io, int64_t index, int32_t after_reset, double* out64,
+                    void* stream) {
+    int rc = check_state(st);
+    if (rc) return rc;
+    if (!io || !out64 || !io->reward || !io->terminated || !io->truncated) return DEXSIM_E_NULL;
+    if (index < 0 || index >= st->n) return DEXSIM_E_SIZE;
+    pack_env_kernel<<<1, 64, 0, (cudaStream_t)stream>>>(*st, *io, index, after_reset ? 1 : 0, out64);
     return cuda_rc(cudaGetLastError());
 }
 

@@ -371,8 +371,7 @@ class BatchedManipulationEnv:
                     self._ep_log_count.zero_()
                 if self.rng_mode == "numpy":
                     self._episode.zero_()
-            obs = self._emit_obs(reset=True)
-            return obs, self._make_info(after_reset=True)
+            return self._reset_outputs()
 
     def reset_from_draws(self, jp0, size, mass, friction, pos=None, mask=None):
         """Reset with caller-supplied draws (batch first): jp0 [n,15] float32, size/mass/friction [n]
@@ -405,7 +404,7 @@ class BatchedManipulationEnv:
             torch.cuda.current_stream(dev).synchronize()
             self._spawned = True
             self._did_reset = True
-            return self._emit_obs(reset=True), self._make_info(after_reset=True)
+            return self._reset_outputs()
 
     # ------------------------------------------------------------------ step
     def _ingest_action(self, action):
@@ -501,12 +500,10 @@ class BatchedManipulationEnv:
                 self._state_ref, self._params_ref, _L.RNG_STREAM_OBS, 45,
                 C.c_float(self.observation_noise_std), self._obs_noise.data_ptr(), self._stream()), "dexsim_fill_normal")
             torch.add(self._obs, self._obs_noise, out=self._noisy_obs)
+        if self.single:
+            return self._single_readback(after_reset=False, noisy=want_obs)
         obs = self._emit_obs(noisy=want_obs)
         n = self.num_envs
-        if self.single:
-            vals = torch.stack([self._reward[0].to(torch.float64), self._terminated[0].to(torch.float64),
-                                self._truncated[0].to(torch.float64)]).cpu().numpy()
-            return obs, float(vals[0]), bool(vals[1]), bool(vals[2]), self._make_info()
         return (obs, self._reward[:n], self._terminated[:n].view(torch.bool), self._truncated[:n].view(torch.bool),
                 self._make_info())
 
@@ -553,6 +550,43 @@ class BatchedManipulationEnv:
                                          self._io_ref, self._stream()), "dexsim_step")
         return self._step_out
 
+    def _reset_outputs(self):
+        obs = self._emit_obs(reset=True)          # also draws the reset observation's noise when enabled
+        if self.single:
+            o, _, _, _, info = self._single_readback(after_reset=True, noisy=self.observation_noise_std > 0.0)
+            return o, info
+        return obs, self._make_info(after_reset=True)
+
+    def _single_readback(self, after_reset, noisy):
+        """num_envs == 1: one pack kernel + one 512-byte D2H copy -> the reference's return values
+        (obs float32[45], reward float, terminated, truncated, info dict of envs/manipulation_env.py:266-283)."""
+        if getattr(self, "_pack_dev", None) is None:
+            self._pack_dev = torch.zeros(64, dtype=torch.float64, device=self.device)
+            self._pack_host = torch.zeros(64, dtype=torch.float64).pin_memory()
+        io = _lib.DexsimStepIO.from_buffer_copy(self._io)
+        if noisy:
+            io.noisy_obs, io.obs_noise = self._noisy_obs.data_ptr(), self._noisy_obs.data_ptr()
+        else:
+            io.noisy_obs = io.obs_noise = None
+        _lib.check(self._lib.dexsim_pack_env(self._state_ref, C.byref(io), 0, int(after_reset), self._pack_dev.data_ptr(),
+                                             self._stream()), "dexsim_pack_env")
+        self._pack_host.copy_(self._pack_dev, non_blocking=True)
+        torch.cuda.current_stream(self.device).synchronize()
+        h = self._pack_host.numpy()
+        obs = h[:45].astype(np.float32)
+        info = {
+            "step_count": int(h[49]),
+            "object_position": h[50:53].copy(),
+            "num_contacts": int(h[48]),
+            "curriculum": {"object_size": float(h[53]), "object_mass": float(h[54]), "friction_coefficient": float(h[55])},
+        }
+        if not after_reset and self._comps is not None:
+            info["reward_components"] = {"total": float(h[45]), "distance": float(h[56]), "contact": float(h[57]),
+                                         "closure": float(h[58]), "stability": float(h[59])}
+        if self.info_success and not after_reset:
+            info["success"] = bool(h[46])
+        return obs, float(h[45]), bool(h[46]), bool(h[47]), info
+
     def _emit_obs(self, reset=False, noisy=False):
         n = self.num_envs
         if reset and self.observation_noise_std > 0.0:
@@ -565,30 +599,11 @@ class BatchedManipulationEnv:
             noisy = True
         src = self._noisy_obs if noisy else self._obs
         if self.single:
-            return src[:, 0].cpu().numpy().copy()
+            return None                           # read back by _single_readback
         return src[:, :n].t()
 
     def _make_info(self, after_reset=False):
         n = self.num_envs
-        if self.single:
-            host = torch.cat([self._op64[:, 0], self._size[:1], self._mass[:1], self._friction[:1],
-                              self._step_count[:1].to(torch.float64), self._num_contacts[:1].to(torch.float64)
-                              if not after_reset else self._cmask[:1].to(torch.float64)]).cpu().numpy()
-            nc = int(host[7]) if not after_reset else bin(int(host[7])).count("1")
-            info = {
-                "step_count": int(host[6]),
-                "object_position": host[0:3].copy(),
-                "num_contacts": nc,
-                "curriculum": {"object_size": float(host[3]), "object_mass": float(host[4]),
-                               "friction_coefficient": float(host[5])},
-            }
-            if not after_reset and self._comps is not None:
-                c = self._comps[:, 0].to(torch.float64).cpu().numpy()
-                info["reward_components"] = {"total": float(self._reward[0]), "distance": float(c[0]),
-                                             "contact": float(c[1]), "closure": float(c[2]), "stability": float(c[3])}
-            if self.info_success and not after_reset:
-                info["success"] = bool(self._terminated[0])
-            return info
         if self._info is None:
             self._info = {
                 "step_count": self._step_count[:n],

@@ -241,6 +241,14 @@ int dexsim_rollout(const DexsimState* st, const DexsimParams* p, const DexsimGro
                    const uint16_t* group_of_env, int32_t k_steps, int32_t policy_kind,
                    const DexsimRolloutIO* rio, void* stream);
 
+/* ---- single-env read-back: everything the reference's step()/reset() return for env `index`, packed into
+ *      64 float64 on the device (one launch + one small D2H instead of a dozen scalar reads):
+ *      [0..44] obs (noisy_obs if given), 45 reward, 46 terminated, 47 truncated, 48 num_contacts, 49 step_count,
+ *      50..52 object_position (float64), 53 size, 54 mass, 55 friction, 56..59 reward components, 60 finished.
+ *      Serves the num_envs == 1 drop-in path (info dict of envs/manipulation_env.py:266-283). ------------------- */
+int dexsim_pack_env(const DexsimState* st, const DexsimStepIO* io, int64_t index, int32_t after_reset,
+                    double* out64 /* device [64] */, void* stream);
+
 /* ---- RNG exposure (so tests can pre-draw exactly what the fused kernels draw) ---------------- */
 int dexsim_fill_policy_actions(const DexsimState* st, const DexsimParams* p, int32_t policy_kind,
                                float* actions /* [15, ld] for each env's CURRENT (episode, step) */,
