@@ -64,7 +64,7 @@ class DexsimStepIO(C.Structure):
                 ("dyn_noise", C.c_void_p), ("obs_noise", C.c_void_p), ("noisy_obs", C.c_void_p),
                 ("reward", C.c_void_p), ("reward_comps", C.c_void_p), ("terminated", C.c_void_p),
                 ("truncated", C.c_void_p), ("num_contacts", C.c_void_p), ("finished", C.c_void_p),
-                ("counters", C.c_void_p), ("ret_sums", C.c_void_p)]
+                ("counters", C.c_void_p), ("ret_sums", C.c_void_p), ("reward64", C.c_void_p)]
 
 
 class DexsimEpisodeRecord(C.Structure):

@@ -249,6 +249,7 @@ step_kernel(const DexsimState st, const DexsimParams p, const DexsimGroup* __res
             continue;
         }
 
+        if (io.reward64) io.reward64[i] = r.total;
         if (io.reward_comps) {
             io.reward_comps[0 * ld + i] = (float)r.distance;
             io.reward_comps[1 * ld + i] = (float)r.contact;
@@ -533,7 +534,7 @@ __global__ void pack_env_kernel(const DexsimState st, const DexsimStepIO io, con
     const int64_t ld = st.ld;
     const float* obs = (io.noisy_obs && io.obs_noise) ? io.noisy_obs : st.obs;
     if (t < NOBS) out[t] = (double)obs[t * ld + i];
-    if (t == 45) out[45] = after_reset ? 0.0 : (double)io.reward[i];
+    if (t == 45) out[45] = after_reset ? 0.0 : (io.reward64 ? io.reward64[i] : (double)io.reward[i]);
     if (t == 46) out[46] = after_reset ? 0.0 : (double)io.terminated[i];
     if (t == 47) out[47] = after_reset ? 0.0 : (double)io.truncated[i];
     if (t == 48) out[48] = (double)__popc((unsigned)st.cmask[i]);
@@ -714,8 +715,8 @@ static int launch_step(const DexsimState* st, const DexsimParams* p, const Dexsi
     if (!io || !io->action || !io->reward || !io->terminated || !io->truncated || !io->num_contacts) return DEXSIM_E_NULL;
     if (io->action_layout != 0 && io->action_layout != 1) return DEXSIM_E_PARAM;
     if ((io->obs_noise != nullptr) != (io->noisy_obs != nullptr)) return DEXSIM_E_NULL;
-    const bool extras = io->dyn_noise || io->obs_noise || io->reward_comps || io->finished || p->auto_reset ||
-                        st->ep_return != nullptr;
+    const bool extras = io->dyn_noise || io->obs_noise || io->reward_comps || io->reward64 || io->finished ||
+                        p->auto_reset || st->ep_return != nullptr;
     rc = check_params(p, p && p->auto_reset, groups);
     if (rc) return rc;
     if (st->n == 0) return 0;
@@ -725,7 +726,7 @@ static int launch_step(const DexsimState* st, const DexsimParams* p, const Dexsi
     // TMA pipeline: everything except the noise / reward-component outputs; needs 16-byte aligned bases
     const int impl = step_impl_choice();
     const bool track = extras;
-    const bool tma_ok = !io->dyn_noise && !io->obs_noise && !io->reward_comps && (!track || st->ep_return != nullptr) &&
+    const bool tma_ok = !io->dyn_noise && !io->obs_noise && !io->reward_comps && !io->reward64 && (!track || st->ep_return != nullptr) &&
                         st->n >= TILE && st->n < (int64_t)0x7FFFFF00 &&
                         !(reinterpret_cast<uintptr_t>(io->action) & 15u) && !(reinterpret_cast<uintptr_t>(io->reward) & 15u) &&
                         !(reinterpret_cast<uintptr_t>(st->thr) & 15u) && !(reinterpret_cast<uintptr_t>(st->damp) & 15u) &&
@@ -1011,6 +1012,7 @@ int dexsim_step_host(const DexsimState* st, const DexsimParams* p, const DexsimG
         sio.action = d_action;
         sio.reward += lo; sio.terminated += lo; sio.truncated += lo; sio.num_contacts += lo;
         if (sio.reward_comps) sio.reward_comps += lo;
+        if (sio.reward64) sio.reward64 += lo;
         if (sio.finished) sio.finished += lo;
         cudaError_t err;
         if (aos) err = cudaMemcpyAsync(d_action, h_action + lo * NJ, (size_t)m * NJ * sizeof(float), cudaMemcpyHostToDevice, s);

@@ -166,6 +166,7 @@ class BatchedManipulationEnv:
         self._ep_return = z(ld, dtype=torch.float64) if self.track_episodes else None
         self._ep_stats = z(2, ld, dtype=torch.int32) if self.track_episodes else None
         self._reward = z(ld, dtype=torch.float32)
+        self._reward64 = z(ld, dtype=torch.float64) if self.single else None   # exact Python-float reward for drop-in use
         self._comps = z(4, ld, dtype=torch.float32) if self.reward_components else None
         self._terminated = z(ld, dtype=torch.uint8)
         self._truncated = z(ld, dtype=torch.uint8)
@@ -229,6 +230,7 @@ class BatchedManipulationEnv:
         io.terminated, io.truncated = self._ptr(self._terminated), self._ptr(self._truncated)
         io.num_contacts, io.finished = self._ptr(self._num_contacts), self._ptr(self._finished)
         io.counters, io.ret_sums = self._ptr(self.counters), self._ptr(self.ret_sums)
+        io.reward64 = self._ptr(self._reward64)
 
     @property
     def curriculum_config(self):

@@ -148,6 +148,9 @@ typedef struct DexsimStepIO {
     uint8_t*     finished;      /* [ld] out 0/1: episode ended this step and the env was auto-reset; or NULL */
     int64_t*     counters;      /* [num_groups, DEXSIM_NCOUNTERS] accumulated; or NULL */
     double*      ret_sums;      /* [num_groups, 2] sum and sum of squares of episode returns; or NULL */
+    double*      reward64;      /* [ld] out: the float64 total exactly as the reference returns it (Python float); or NULL.
+                                 * Needed by callers that compare rewards (SimpleLearner.update); served by the
+                                 * register-resident kernel. */
 } DexsimStepIO;
 
 /* ---- library ---------------------------------------------------------------------------- */

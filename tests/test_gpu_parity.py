@@ -866,3 +866,81 @@ def test_masked_reset_touches_only_masked_envs(dx):
         assert float(env._obs[0:15, :n][:, done].abs().max()) <= 0.1                                        # fresh joints
         if rng_mode == "philox":
             assert torch.equal(env._episode[:n][done], before["_episode"][:n][done] + 1)
+
+
+def test_more_unmodified_reference_callers(dx):
+    """RobustnessTester (noise wrappers around the env), SeedVarianceAnalyzer and the component-ablation
+    training loop of the reference, each run UNMODIFIED once with its own env and once with the drop-in."""
+    from oracle import ref_harness
+    if not ref_harness.available():
+        pytest.skip("reference (source or byte-compiled) not present")
+    import importlib
+    R = ref_harness.load()
+    make = lambda **kw: dx.BatchedManipulationEnv(1, "cuda", **kw)
+
+    def both(module, fn, factories=None):
+        out = []
+        orig = module.DexterousManipulationEnv
+        for factory in (factories or (orig, make)):
+            module.DexterousManipulationEnv = factory
+            try:
+                out.append(fn())
+            finally:
+                module.DexterousManipulationEnv = orig
+        return out
+
+    # 1. RobustnessTester.evaluate_with_noise: CombinedNoiseWrapper(seeded default_rng) wraps the env
+    cfg = R.CurriculumConfig(object_size=0.05, object_mass=0.1, friction_coefficient=0.4)
+
+    def robust():
+        np.random.seed(11)
+        probe = R.DexterousManipulationEnv()
+        tester = R.robustness_tests.RobustnessTester(R.policies.HeuristicPolicy(probe.action_space), cfg,
+                                                     reward_type="dense", max_episode_steps=40)
+        return tester.evaluate_with_noise(0.05, 0.1, num_episodes=4, seed=5)
+
+    ref, got = both(R.robustness_tests, robust)
+    assert ref["metrics"]["grasp_success_rate"] == got["metrics"]["grasp_success_rate"]
+    assert ref["metrics"]["failure_type_frequency"] == got["metrics"]["failure_type_frequency"]
+    for e0, e1 in zip(ref["episodes"], got["episodes"]):
+        assert (e0["success"], e0["episode_steps"], e0["contact_history"]) == (e1["success"], e1["episode_steps"], e1["contact_history"])
+        assert e1["episode_reward"] == pytest.approx(e0["episode_reward"], rel=1e-5)
+
+    # 2. SeedVarianceAnalyzer.evaluate_multiple_seeds (Evaluator underneath)
+    train = R.CurriculumConfig(object_size_range=(0.03, 0.07), object_mass_range=(0.05, 0.15), friction_range=(0.3, 0.7))
+    held = R.heldout_objects.HeldOutObjectSet(train_config=train, eval_size_range=(0.03, 0.08), num_heldout_objects=3, seed=2)
+
+    def seeds():
+        np.random.seed(3)
+        probe = R.DexterousManipulationEnv()
+        an = R.seed_variance.SeedVarianceAnalyzer(R.policies.HeuristicPolicy(probe.action_space), held, "dense", 40)
+        res = an.evaluate_multiple_seeds([1, 2, 3], num_episodes_per_object=2)
+        return an.compute_variance_statistics(res)
+
+    ref, got = both(R.evaluator, seeds)
+    assert ref["variance_stats"]["grasp_success_rate"] == got["variance_stats"]["grasp_success_rate"]
+    assert ref["variance_stats"]["mean_episode_length"] == got["variance_stats"]["mean_episode_length"]
+
+    # 3. component ablation training loop: run_episode + SimpleLearner + CurriculumScheduler on a reused env
+    ca = importlib.import_module("evaluation.component_ablation")
+
+    def train():
+        res = ca.train_with_config(ca.AblationConfig(use_curriculum=True, use_dense_reward=True, name="x"),
+                                   num_episodes=12, max_episode_steps=40, seed=7)
+        return res.episode_rewards, res.episode_steps
+
+    # train_with_config never seeds env.reset(): gymnasium would seed the env's generator from OS entropy.
+    # Give both env objects the same generator state so that the two runs are comparable.
+    def ref_seeded(**kw):
+        e = R.DexterousManipulationEnv(**kw)
+        e._np_random = np.random.Generator(np.random.PCG64(np.random.SeedSequence(2024)))
+        return e
+
+    def drop_in_seeded(**kw):
+        e = make(**kw)
+        e._host_rngs(2024)
+        return e
+
+    (r0, l0), (r1, l1) = both(ca, train, (ref_seeded, drop_in_seeded))
+    assert list(l0) == list(l1)
+    np.testing.assert_allclose(r1, r0, rtol=1e-5)
