@@ -254,7 +254,10 @@ def run_b200(args):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
-    n_gpus = max(args.gpus, world)
+    n_gpus = world                      # one rank per GPU; --gpus N without torchrun cannot use more than one
+    if args.gpus != world and rank == 0:
+        print(f"bench.py: --gpus {args.gpus} but WORLD_SIZE={world}; launch with torch.distributed.run for multi-GPU "
+              f"(measuring {world} GPU)", file=sys.stderr)
 
     cpu_base = None
     if rank == 0 and n_gpus == 1 and not args.no_cpu_baseline:
