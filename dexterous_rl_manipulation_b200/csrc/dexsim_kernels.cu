@@ -12,6 +12,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 
 #include "dexsim_core.cuh"
 
@@ -947,6 +948,7 @@ struct HostPipe {
     cudaEvent_t join_ev[HOST_STREAMS];
 };
 HostPipe g_pipes[64];
+std::mutex g_pipes_mutex;      // first use from several host threads at once
 
 int get_pipe(HostPipe** out) {
     int dev = 0;
@@ -954,6 +956,7 @@ int get_pipe(HostPipe** out) {
     if (err != cudaSuccess) return -(int)err;
     if (dev < 0 || dev >= 64) return DEXSIM_E_PARAM;
     HostPipe& hp = g_pipes[dev];
+    std::lock_guard<std::mutex> lock(g_pipes_mutex);
     if (!hp.ready) {
         for (int k = 0; k < HOST_STREAMS; ++k) {
             err = cudaStreamCreateWithFlags(&hp.streams[k], cudaStreamNonBlocking);

@@ -113,7 +113,7 @@ def evaluate_heldout_set_batched(heldout_set, policy: str = "heuristic", num_epi
             a = torch.cat([a, a[:, :env.num_envs - n]], 1)
         kw["actions"] = a
     # exactly the caller loop bound: at most max_episode_steps steps per episode (evaluator.py:135)
-    recs = _first_episode_records_kw(env, max_episode_steps, policy, True, max_episode_steps, contact_history, kw)
+    recs = _run_one_episode_each(env, max_episode_steps, policy, True, max_episode_steps, contact_history, kw)
     size, mass, fric = ([o.size for o in objs], [o.mass for o in objs], [o.friction for o in objs])
     all_results, object_results = [], {}
     for o in range(n_obj):
@@ -149,7 +149,7 @@ def evaluate_heldout_set_batched(heldout_set, policy: str = "heuristic", num_epi
             "metrics": metrics, "per_object_metrics": per_object_metrics}
 
 
-def _first_episode_records_kw(env, k_steps, policy, respawn, loop_max_steps, with_history, kw):
+def _run_one_episode_each(env, k_steps, policy, respawn, loop_max_steps, with_history, kw):
     """One fused launch in one-episode mode; {env index: (record, per-step contact counts)}."""
     n = env.num_envs
     env.enable_episode_log(capacity=n)
@@ -192,7 +192,7 @@ def evaluate_with_noise_batched(eval_config, policy: str = "heuristic", observat
         # reset samples the spawn, later ones keep the position the previous episode ended at
         env.reset(seed=[base + 1000 * r + ep for r in range(n)])
         env._episode.fill_(ep)                       # distinct Philox policy / noise streams per episode
-        recs = _first_episode_records_kw(env, max_episode_steps, policy, False, max_episode_steps, True, {})
+        recs = _run_one_episode_each(env, max_episode_steps, policy, False, max_episode_steps, True, {})
         for r in range(int(num_replicas)):
             rec, counts = recs[r]
             d = _episode_dict(rec, counts, eval_config.object_size, eval_config.object_mass, eval_config.friction_coefficient)

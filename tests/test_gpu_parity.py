@@ -515,15 +515,15 @@ def test_batched_robustness_front_end_matches_reference(dx):
         pass
 
     import dexterous_rl_manipulation_b200.evaluation as ev
-    orig = ev._first_episode_records_kw
+    orig = ev._run_one_episode_each
     table = torch.from_numpy(np.broadcast_to(pol.table[:, None, :], (T, 2, 15)).copy())
-    ev._first_episode_records_kw = lambda env, k, policy, respawn, lm, hist, kw: orig(env, k, "external", respawn, lm, hist,
+    ev._run_one_episode_each = lambda env, k, policy, respawn, lm, hist, kw: orig(env, k, "external", respawn, lm, hist,
                                                                                    {"actions": table})
     try:
         got = dx.evaluation.evaluate_with_noise_batched(cfg, "heuristic", 0.0, 0.0, num_episodes=n_ep, seed=7,
                                                         reward_type="dense", max_episode_steps=T)
     finally:
-        ev._first_episode_records_kw = orig
+        ev._run_one_episode_each = orig
     assert len(got["episodes"]) == len(ref["episodes"]) == n_ep
     for e0, e1 in zip(ref["episodes"], got["episodes"]):
         for k in ("success", "episode_steps", "num_contacts", "final_contacts", "contact_history"):
