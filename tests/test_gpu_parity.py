@@ -944,3 +944,46 @@ def test_more_unmodified_reference_callers(dx):
     (r0, l0), (r1, l1) = both(ca, train, (ref_seeded, drop_in_seeded))
     assert list(l0) == list(l1)
     np.testing.assert_allclose(r1, r0, rtol=1e-5)
+
+
+def test_fuzz_extreme_inputs_match_oracle(dx):
+    """Adversarial inputs: infinities, NaNs, denormals, huge magnitudes, objects outside the workspace, zero /
+    negative / infinite sizes and frictions.  Observations (NaN patterns included), flags and contact counts must
+    still equal the oracle bit for bit; rewards where finite."""
+    from oracle import oracle
+    rng = np.random.default_rng(2718)
+    n = 4096
+    specials = np.array([0.0, -0.0, 1.0, -1.0, np.inf, -np.inf, np.nan, 1e-45, -1e-45, 1e30, -1e30, 3.4e38, 0.999999, -0.999999,
+                         1.0000001, 1e-8], np.float32)
+    jp0 = rng.uniform(-1.0, 1.0, (n, 15)).astype(np.float32)
+    jp0[::7] = rng.choice(np.array([1.0, -1.0, 0.0, -0.0, 0.99999994, -0.99999994], np.float32), (len(jp0[::7]), 15))
+    size = rng.choice([0.0, -0.05, 1e-300, 0.03, 0.05, 0.08, 0.2, 1e300, np.inf, np.nan], n)
+    mass = rng.uniform(0.01, 1.0, n)
+    fric = rng.choice([0.0, -3.0, 0.3, 0.8, 1e3, 1e6, 1e40, np.inf, np.nan], n)
+    pos = rng.uniform(-0.5, 0.5, (n, 3)).astype(np.float32)
+    pos[::11] = rng.choice(np.array([0.2, -0.2, 0.3, 0.0, -0.0, 1e30, -1e30, np.inf, np.nan, 0.20000001], np.float32), (len(pos[::11]), 3))
+    for dense in (True, False):
+        ob = oracle.OracleBatch(n, dense=dense, max_episode_steps=12)
+        o0 = ob.reset_predrawn(jp0, size, mass, fric, pos)
+        for impl_comps in (True, False):                      # register kernel (comps) and TMA pipeline (no comps)
+            env = dx.BatchedManipulationEnv(n, "cuda", max_episode_steps=12, reward_type="dense" if dense else "sparse",
+                                            reward_components=impl_comps)
+            g0, _ = env.reset_from_draws(jp0, size, mass, fric, pos)
+            assert np.array_equal(g0.cpu().numpy(), o0, equal_nan=True)
+            ob2 = oracle.OracleBatch(n, dense=dense, max_episode_steps=12)
+            ob2.reset_predrawn(jp0, size, mass, fric, pos)
+            arng = np.random.default_rng(5)
+            for t in range(25):
+                a = arng.uniform(-2.0, 2.0, (n, 15)).astype(np.float32)
+                mask = arng.random((n, 15)) < 0.02
+                a[mask] = arng.choice(specials, int(mask.sum()))
+                oo, orr, _, ote, otr, onc = ob2.step(a)
+                obs, rew, te, tr, info = env.step(torch.from_numpy(a).cuda())
+                assert np.array_equal(obs.cpu().numpy(), oo, equal_nan=True), (dense, impl_comps, t)
+                assert np.array_equal(te.cpu().numpy(), ote) and np.array_equal(tr.cpu().numpy(), otr)
+                assert np.array_equal(info["num_contacts"].cpu().numpy(), onc)
+                assert np.array_equal(info["object_position"].cpu().numpy(), ob2.env["op"], equal_nan=True)
+                r = rew.cpu().numpy()
+                fin = np.isfinite(orr)
+                assert np.array_equal(np.isnan(r), np.isnan(orr))
+                np.testing.assert_allclose(r[fin], orr[fin], rtol=REWARD_RTOL, atol=REWARD_ATOL)

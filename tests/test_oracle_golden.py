@@ -186,3 +186,41 @@ def test_simple_learner_rollout(golden_dir):
             assert rs[0, 0] == pytest.approx(g["reward"][c, ep], rel=1e-13)
             # undo the auto-reset of the finished episode: replay is per episode, like run_episode
         assert np.array_equal(mean[0], g["final_mean"][c])
+
+
+def test_oracle_vs_live_reference_on_extreme_inputs():
+    """When the reference is importable: NaN / inf / denormal / out-of-workspace inputs through the UNMODIFIED env and
+    the oracle side by side (the committed goldens only cover ordinary ranges)."""
+    import warnings
+    from oracle import ref_harness
+    if not ref_harness.available():
+        pytest.skip("reference not present")
+    R = ref_harness.load()
+    rng = np.random.default_rng(99)
+    specials = np.array([0.0, -0.0, 1.0, -1.0, np.inf, -np.inf, np.nan, 1e-45, -1e-45, 1e30, -1e30, 3.4e38, 1.0000001], np.float32)
+    sizes = [0.0, -0.05, 1e-300, 0.05, 0.2, 1e300, float("inf"), float("nan")]
+    frics = [0.0, -3.0, 0.5, 1e6, 1e40, float("inf"), float("nan")]
+    with warnings.catch_warnings(), np.errstate(all="ignore"):
+        warnings.simplefilter("ignore")
+        for case in range(60):
+            dense = bool(case % 2)
+            size, fric = sizes[case % len(sizes)], frics[case % len(frics)]
+            cfg = R.CurriculumConfig(object_size=size, object_mass=0.1, friction_coefficient=fric)
+            pos = rng.uniform(-0.5, 0.5, 3).astype(np.float32)
+            if case % 5 == 0:
+                pos[rng.integers(0, 3)] = rng.choice(np.array([0.2, -0.2, 0.3, 1e30, np.inf, np.nan, -0.0], np.float32))
+            env = R.DexterousManipulationEnv(reward_type="dense" if dense else "sparse", curriculum_config=cfg,
+                                             max_episode_steps=8, object_position=pos)
+            obs0, _ = env.reset(seed=case)
+            ob = oracle.OracleBatch(1, dense=dense, max_episode_steps=8)
+            o0 = ob.reset_predrawn(env.joint_positions.copy(), size, 0.1, fric, pos)
+            assert np.array_equal(o0[0], obs0, equal_nan=True)
+            for t in range(15):
+                a = rng.uniform(-2, 2, 15).astype(np.float32)
+                m = rng.random(15) < 0.1
+                a[m] = rng.choice(specials, int(m.sum()))
+                obs, r, te, tr, info = env.step(a)
+                oo, orr, _, ote, otr, onc = ob.step(a)
+                assert np.array_equal(oo[0], obs, equal_nan=True), (case, t)
+                assert ote[0] == te and otr[0] == tr and onc[0] == info["num_contacts"], (case, t)
+                assert (np.isnan(r) and np.isnan(orr[0])) or orr[0] == pytest.approx(r, rel=1e-14, abs=1e-15), (case, t, r, orr[0])
