@@ -261,3 +261,24 @@ def test_empty_batch_is_a_no_op_without_cuda():
     p.reward_type = 5
     assert L.dexsim_step(C.byref(st), C.byref(p), None, None, C.byref(io), None) == -1004
     assert L.dexsim_set_step_impl(9) == -1004 and L.dexsim_set_step_impl(0) == 0
+
+
+def test_public_header_is_plain_c(tmp_path):
+    """include/dexsim.h is the boundary a maintainer binds against: it must compile as C99 and link against the
+    shared library from a C program (no C++ / torch types in the signatures)."""
+    import shutil
+    import subprocess
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("gcc not available")
+    src = tmp_path / "abi.c"
+    src.write_text('#include "dexsim.h"\n#include <stdio.h>\n'
+                   'int main(void) { DexsimState st = {0}; DexsimParams p = {0}; DexsimStepIO io = {0};\n'
+                   '  int rc = dexsim_step(&st, &p, 0, 0, &io, 0);\n'
+                   '  printf("%d %d %s\\n", dexsim_version(), rc, dexsim_error_string(rc)); return 0; }\n')
+    exe = tmp_path / "abi"
+    libdir = os.path.dirname(_lib.LIB_PATH)
+    subprocess.run([gcc, "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", os.path.join(ROOT, "include"), str(src),
+                    "-o", str(exe), "-L", libdir, "-ldexsim_b200", "-Wl,-rpath," + libdir], check=True)
+    out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split(None, 2)
+    assert int(out[0]) == _lib.ABI_VERSION and int(out[1]) == -1001 and "NULL" in out[2]
