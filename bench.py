@@ -469,7 +469,14 @@ def measure_cpu_baseline(args):
         steps = max(2, min(200, int(args.cpu_seconds / max(per_step, 1e-3))))
         full = subprocess.run(cmd + ["--steps", str(steps), "--warmup", "1"], capture_output=True, text=True, timeout=600)
         line = json.loads(full.stdout.strip().splitlines()[-1])
-        return line["cpu_baseline"]
+        base = line["cpu_baseline"]
+        # also the single-core figure (one process, same loop), a few seconds
+        one = subprocess.run(cmd + ["--steps", "8", "--warmup", "1", "--ref-procs", "1"], capture_output=True, text=True, timeout=300)
+        try:
+            base["one_core_value"] = json.loads(one.stdout.strip().splitlines()[-1])["value"]
+        except (ValueError, IndexError, KeyError):
+            base["one_core_value"] = None
+        return base
     except Exception as exc:       # report, never fake a number
         return {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "reference", "sample": f"failed: {exc!r}"}
 
