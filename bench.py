@@ -269,6 +269,7 @@ def run_b200(args):
     json_fd = os.dup(1)
     os.dup2(2, 1)
 
+    numa_bound = dx.distributed.bind_to_gpu_numa(local) if world > 1 else False   # before any pinned allocation
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
@@ -378,7 +379,8 @@ def run_b200(args):
     e2e = {"value": E * n_gpus * args.e2e_steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": E * 15 * 4 * n_gpus,
            "d2h_bytes_per_step": (env.ld * 41 * 4 + E * (4 + 3)) * n_gpus, "steps": args.e2e_steps,
            "note": "obs rows 33-36 (constant quaternion) are not re-copied; 8 chunks, H2D / kernel / D2H overlapped",
-           "api": "BatchedManipulationEnv.step_host -> dexsim_step_host", "gpu_launches": args.e2e_steps * 8}
+           "api": "BatchedManipulationEnv.step_host -> dexsim_step_host", "gpu_launches": args.e2e_steps * 8,
+           "numa_bound": bool(numa_bound)}
 
     # ---- fused rollout (policy in-kernel, K steps per launch) ---------------------------------------
     fused = None
