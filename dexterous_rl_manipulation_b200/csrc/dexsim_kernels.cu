@@ -642,12 +642,13 @@ static void launch_step_variant(bool extras, int grid, cudaStream_t s, const Dex
     else        step_kernel<DENSE, AOS, false><<<grid, STEP_THREADS, 0, s>>>(st, p, groups, goe, io);
 }
 
-template <bool DENSE, bool AOS, bool TRACK, int STAGES>
+template <bool DENSE, bool AOS, bool TRACK, int STAGES, int GROUPS>
 static int launch_tma_variant(int sm_count, cudaStream_t s, const DexsimState& st, const DexsimParams& p,
                               const DexsimGroup* groups, const uint16_t* goe, const DexsimStepIO& io,
                               const StepMaps& maps, int num_tiles) {
-    auto kern = step_tma_kernel<DENSE, AOS, TRACK, STAGES>;
-    const size_t smem = (size_t)STAGES * STAGE_BYTES + 2 * STAGES * sizeof(uint64_t) +
+    auto kern = step_tma_kernel<DENSE, AOS, TRACK, STAGES, GROUPS>;
+    constexpr int TMA_THREADS = tma_threads(GROUPS);
+    const size_t smem = (size_t)STAGES * STAGE_BYTES + (STAGES * GROUPS + STAGES) * sizeof(uint64_t) +
                         (TRACK ? TMA_GROUPS_MAX * (DEXSIM_NCOUNTERS * sizeof(unsigned long long) + 2 * sizeof(double)) : 0);
     static thread_local int ctas_per_sm = 0;        // per template instantiation
     if (ctas_per_sm == 0) {
@@ -674,13 +675,20 @@ static int step_impl_choice() {
     }
     return g_step_impl;
 }
-static int tma_stage_choice() {
-    static int stages = -1;
-    if (stages < 0) {
-        const char* e = getenv("DEXSIM_TMA_STAGES");
-        stages = (e && atoi(e) == 3) ? 3 : 2;
+// Pipeline shape "<stages>x<compute groups>".  2x1 (3 CTAs per SM) is the product; 3x1 and 3x2 measured within
+// 1 % of it on B200 and are only built with -DDEXSIM_TMA_EXTRA_SHAPES, selected by
+// DEXSIM_TMA_SHAPE=3x1|3x2 for experiments.
+static int tma_shape_choice() {
+#ifdef DEXSIM_TMA_EXTRA_SHAPES
+    static int shape = -1;
+    if (shape < 0) {
+        const char* e = getenv("DEXSIM_TMA_SHAPE");
+        shape = (e && !strcmp(e, "3x1")) ? 31 : (e && !strcmp(e, "3x2")) ? 32 : 21;
     }
-    return stages;
+    return shape;
+#else
+    return 21;
+#endif
 }
 
 static int launch_step_tma(const DexsimState* st, const DexsimParams* p, const DexsimGroup* groups, const uint16_t* goe,
@@ -696,11 +704,19 @@ static int launch_step_tma(const DexsimState* st, const DexsimParams* p, const D
     if (!ok) return 1;                               // caller falls back to the register-resident kernel
     const int num_tiles = (int)((st->n + TILE - 1) / TILE);
     const bool dense = p->reward_type == 1;
-    const int stages = tma_stage_choice();
-#define DEXSIM_TMA_CASE(D, A, T)                                                                              \
-    if (dense == D && aos == A && track == T)                                                                 \
-        return stages == 3 ? launch_tma_variant<D, A, T, 3>(sm_count, s, *st, *p, groups, goe, *io, maps, num_tiles) \
-                           : launch_tma_variant<D, A, T, 2>(sm_count, s, *st, *p, groups, goe, *io, maps, num_tiles);
+    const int shape = tma_shape_choice();
+    (void)shape;
+#ifdef DEXSIM_TMA_EXTRA_SHAPES
+#define DEXSIM_TMA_CASE(D, A, T)                                                                                 \
+    if (dense == D && aos == A && track == T)                                                                    \
+        return shape == 32 ? launch_tma_variant<D, A, T, 3, 2>(sm_count, s, *st, *p, groups, goe, *io, maps, num_tiles) \
+             : shape == 31 ? launch_tma_variant<D, A, T, 3, 1>(sm_count, s, *st, *p, groups, goe, *io, maps, num_tiles) \
+                           : launch_tma_variant<D, A, T, 2, 1>(sm_count, s, *st, *p, groups, goe, *io, maps, num_tiles);
+#else
+#define DEXSIM_TMA_CASE(D, A, T)                                                                                 \
+    if (dense == D && aos == A && track == T)                                                                    \
+        return launch_tma_variant<D, A, T, 2, 1>(sm_count, s, *st, *p, groups, goe, *io, maps, num_tiles);
+#endif
     DEXSIM_TMA_CASE(true, true, true) DEXSIM_TMA_CASE(true, true, false)
     DEXSIM_TMA_CASE(true, false, true) DEXSIM_TMA_CASE(true, false, false)
     DEXSIM_TMA_CASE(false, true, true) DEXSIM_TMA_CASE(false, true, false)

@@ -22,8 +22,8 @@
 namespace dexsim {
 
 constexpr int TILE = 128;
-constexpr int TMA_COMPUTE_THREADS = 128;
-constexpr int TMA_THREADS = TMA_COMPUTE_THREADS + 32;
+constexpr int TMA_COMPUTE_THREADS = 128;           // one compute group = 4 warps = one tile at a time
+__host__ __device__ constexpr int tma_threads(int groups) { return groups * TMA_COMPUTE_THREADS + 32; }
 constexpr int TMA_GROUPS_MAX = 16;     // per-CTA counter staging (keeps 3 CTAs per SM with 2 stages)
 
 // byte offsets inside one stage (all multiples of 128: TMA box destinations need 128-byte alignment)
@@ -101,28 +101,42 @@ __device__ __forceinline__ uint32_t tile_cols(int64_t n, int64_t base) {
     return left >= TILE ? (uint32_t)TILE : (uint32_t)((left + 31) & ~(int64_t)31);
 }
 
+// "Stage filled" barriers.  A parity wait can only tell the last two phases of a barrier apart, so every barrier
+// must be watched phase by phase by ONE waiter.  With two compute groups a stage alternates between them
+// (3 stages, tile k -> stage k % 3, group k % 2), hence one barrier per (stage, group): tile k uses barrier
+// k % (S * G) and it is that barrier's (k / (S * G))-th fill.  (S and G are coprime or G == 1.)
+template <int STAGES, int GROUPS>
+__device__ __forceinline__ int full_index(int k) { return GROUPS == 1 ? k % STAGES : k % (STAGES * GROUPS); }
+template <int STAGES, int GROUPS>
+__device__ __forceinline__ uint32_t full_parity(int k) {
+    return (uint32_t)((GROUPS == 1 ? k / STAGES : k / (STAGES * GROUPS)) & 1);
+}
+
 // DENSE: reward type.  AOS: action layout [n,15].  TRACK: episode tracking / auto-reset / counters.
-template <bool DENSE, bool AOS, bool TRACK, int STAGES>
-__global__ void __launch_bounds__(TMA_THREADS)
+// GROUPS: compute groups per CTA.  With 2 groups (8 compute warps, 3 stages, 2 CTAs per SM) group g works on the
+// CTA's tiles k = g, g + 2, ... so that two tiles are in their compute phase while a third one loads.
+template <bool DENSE, bool AOS, bool TRACK, int STAGES, int GROUPS>
+__global__ void __launch_bounds__(tma_threads(GROUPS), (GROUPS == 2) ? 2 : ((STAGES == 2) ? 3 : 2))
 step_tma_kernel(const DexsimState st, const DexsimParams p, const DexsimGroup* __restrict__ groups,
                 const uint16_t* __restrict__ group_of_env, const DexsimStepIO io,
                 const __grid_constant__ StepMaps maps, const int num_tiles) {
     extern __shared__ __align__(1024) unsigned char smem[];
     unsigned char* stage_base = smem;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);      // full[S], out_ready[S]
-    unsigned long long* sh_cnt = reinterpret_cast<unsigned long long*>(bars + 2 * STAGES);
+    constexpr int NFULL = STAGES * GROUPS;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);      // full[S * G], out_ready[S]
+    unsigned long long* sh_cnt = reinterpret_cast<unsigned long long*>(bars + NFULL + STAGES);
     double* sh_rs = reinterpret_cast<double*>(sh_cnt + (TRACK ? TMA_GROUPS_MAX * DEXSIM_NCOUNTERS : 0));
 
+    constexpr int TMA_THREADS = tma_threads(GROUPS);
+    constexpr int PRODUCER_TID = GROUPS * TMA_COMPUTE_THREADS;
     const int tid = threadIdx.x;
     const int64_t n = st.n, ld = st.ld;
     const bool count_episodes = TRACK && p.auto_reset && io.counters != nullptr;
     const bool staged_cnt = count_episodes && p.num_groups <= TMA_GROUPS_MAX;
 
     if (tid == 0) {
-        for (int s = 0; s < STAGES; ++s) {
-            mbar_init(smem_u32(&bars[s]), 1);
-            mbar_init(smem_u32(&bars[STAGES + s]), TMA_COMPUTE_THREADS);
-        }
+        for (int b = 0; b < NFULL; ++b) mbar_init(smem_u32(&bars[b]), 1);
+        for (int s = 0; s < STAGES; ++s) mbar_init(smem_u32(&bars[NFULL + s]), TMA_COMPUTE_THREADS);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (TRACK && staged_cnt) {
@@ -133,9 +147,9 @@ step_tma_kernel(const DexsimState st, const DexsimParams p, const DexsimGroup* _
 
     const int my_tiles = (num_tiles > (int)blockIdx.x) ? (num_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
 
-    if (tid >= TMA_COMPUTE_THREADS) {
+    if (tid >= PRODUCER_TID) {
         // ===== producer warp: one lane issues every bulk copy of this CTA =====
-        if (tid == TMA_COMPUTE_THREADS) {
+        if (tid == PRODUCER_TID) {
             auto issue_stores = [&](int k) {
                 const int s = k % STAGES;
                 const int64_t base = ((int64_t)blockIdx.x + (int64_t)k * gridDim.x) * TILE;
@@ -158,11 +172,11 @@ step_tma_kernel(const DexsimState st, const DexsimParams p, const DexsimGroup* _
             for (int k = 0; k < my_tiles; ++k) {
                 const int s = k % STAGES, use = k / STAGES;
                 const uint32_t sb = smem_u32(stage_base + (size_t)s * STAGE_BYTES);
-                const uint32_t full = smem_u32(&bars[s]);
+                const uint32_t full = smem_u32(&bars[full_index<STAGES, GROUPS>(k)]);
                 if (use > 0) {
                     // the tile that used this stage last: wait for its outputs, send them, and let
                     // the copy engine finish READING the stage before new data lands in it
-                    mbar_wait(smem_u32(&bars[STAGES + s]), (uint32_t)((use - 1) & 1));
+                    mbar_wait(smem_u32(&bars[NFULL + s]), (uint32_t)((use - 1) & 1));
                     issue_stores(k - STAGES);
                     bulk_wait_read0();
                 }
@@ -192,45 +206,46 @@ step_tma_kernel(const DexsimState st, const DexsimParams p, const DexsimGroup* _
             // drain: outputs of the last min(STAGES, my_tiles) tiles
             const int first = my_tiles > STAGES ? my_tiles - STAGES : 0;
             for (int k = first; k < my_tiles; ++k) {
-                mbar_wait(smem_u32(&bars[STAGES + k % STAGES]), (uint32_t)((k / STAGES) & 1));
+                mbar_wait(smem_u32(&bars[NFULL + k % STAGES]), (uint32_t)((k / STAGES) & 1));
                 issue_stores(k);
             }
             bulk_wait0();       // shared memory must outlive every outstanding bulk store
         }
     } else {
         // ===== compute warps: lane == column of the tile =====
-        for (int k = 0; k < my_tiles; ++k) {
+        const int col = tid & (TMA_COMPUTE_THREADS - 1);
+        for (int k = tid / TMA_COMPUTE_THREADS; k < my_tiles; k += GROUPS) {
             const int s = k % STAGES, use = k / STAGES;
             unsigned char* sp = stage_base + (size_t)s * STAGE_BYTES;
             const int64_t base = ((int64_t)blockIdx.x + (int64_t)k * gridDim.x) * TILE;
-            const int64_t i = base + tid;
-            mbar_wait(smem_u32(&bars[s]), (uint32_t)(use & 1));
+            const int64_t i = base + col;
+            mbar_wait(smem_u32(&bars[full_index<STAGES, GROUPS>(k)]), full_parity<STAGES, GROUPS>(k));
             if (i < n) {
                 float* s_jpjv = reinterpret_cast<float*>(sp + OFF_JPJV);
                 const float* s_ov = reinterpret_cast<const float*>(sp + OFF_OV);
                 const double* s_op = reinterpret_cast<const double*>(sp + OFF_OP64);
                 EnvRegs e;
 #pragma unroll
-                for (int j = 0; j < NJ; ++j) { e.jp[j] = s_jpjv[j * TILE + tid]; e.jv[j] = s_jpjv[(NJ + j) * TILE + tid]; }
+                for (int j = 0; j < NJ; ++j) { e.jp[j] = s_jpjv[j * TILE + col]; e.jv[j] = s_jpjv[(NJ + j) * TILE + col]; }
 #pragma unroll
-                for (int c = 0; c < 3; ++c) { e.ov[c] = s_ov[c * TILE + tid]; e.op[c] = s_op[c * TILE + tid]; }
-                e.thr = reinterpret_cast<const double*>(sp + OFF_THR)[tid];
-                e.damp = reinterpret_cast<const float*>(sp + OFF_DAMP)[tid];
-                e.sc = reinterpret_cast<const int*>(sp + OFF_SC)[tid];
-                e.cmask = reinterpret_cast<const uint8_t*>(sp + OFF_CMASK)[tid];
+                for (int c = 0; c < 3; ++c) { e.ov[c] = s_ov[c * TILE + col]; e.op[c] = s_op[c * TILE + col]; }
+                e.thr = reinterpret_cast<const double*>(sp + OFF_THR)[col];
+                e.damp = reinterpret_cast<const float*>(sp + OFF_DAMP)[col];
+                e.sc = reinterpret_cast<const int*>(sp + OFF_SC)[col];
+                e.cmask = reinterpret_cast<const uint8_t*>(sp + OFF_CMASK)[col];
                 float a[NJ];
                 const float* s_act = reinterpret_cast<const float*>(sp + OFF_ACT);
                 if (AOS) {
                     if ((n - base) >= TILE) {
 #pragma unroll
-                        for (int j = 0; j < NJ; ++j) a[j] = s_act[tid * NJ + j];
+                        for (int j = 0; j < NJ; ++j) a[j] = s_act[col * NJ + j];
                     } else {        // ragged last tile: its byte count need not be a multiple of 16
 #pragma unroll
                         for (int j = 0; j < NJ; ++j) a[j] = __ldg(io.action + i * NJ + j);
                     }
                 } else {
 #pragma unroll
-                    for (int j = 0; j < NJ; ++j) a[j] = s_act[j * TILE + tid];
+                    for (int j = 0; j < NJ; ++j) a[j] = s_act[j * TILE + col];
                 }
                 double op_old[3]; float ov_old[3];
 #pragma unroll
@@ -240,15 +255,15 @@ step_tma_kernel(const DexsimState st, const DexsimParams p, const DexsimGroup* _
                 StepResult r;
                 env_step<DENSE>(e, a, p, r);
 
-                reinterpret_cast<float*>(sp + OFF_REWARD)[tid] = (float)r.total;
-                (sp + OFF_TERM)[tid] = r.terminated ? 1 : 0;
-                (sp + OFF_TRUNC)[tid] = r.truncated ? 1 : 0;
-                (sp + OFF_NC)[tid] = (unsigned char)r.n_c;
+                reinterpret_cast<float*>(sp + OFF_REWARD)[col] = (float)r.total;
+                (sp + OFF_TERM)[col] = r.terminated ? 1 : 0;
+                (sp + OFF_TRUNC)[col] = r.truncated ? 1 : 0;
+                (sp + OFF_NC)[col] = (unsigned char)r.n_c;
 
                 bool did_reset = false;
                 if (TRACK) {
-                    double ep_return = __dadd_rn(reinterpret_cast<double*>(sp + OFF_EPRET)[tid], r.total);
-                    EpStats es{reinterpret_cast<uint32_t*>(sp + OFF_EPST0)[tid], reinterpret_cast<uint32_t*>(sp + OFF_EPST1)[tid]};
+                    double ep_return = __dadd_rn(reinterpret_cast<double*>(sp + OFF_EPRET)[col], r.total);
+                    EpStats es{reinterpret_cast<uint32_t*>(sp + OFF_EPST0)[col], reinterpret_cast<uint32_t*>(sp + OFF_EPST1)[col]};
                     epstats_push(es, e.sc - 1, r.n_c);
                     const bool done = r.terminated || r.truncated || (p.loop_max_steps > 0 && e.sc >= p.loop_max_steps);
                     if (p.auto_reset && done) {
@@ -269,15 +284,15 @@ step_tma_kernel(const DexsimState st, const DexsimParams p, const DexsimGroup* _
                         st.size[i] = size; st.mass[i] = mass; st.friction[i] = friction;
                         st.thr[i] = e.thr; st.damp[i] = e.damp;
                     }
-                    reinterpret_cast<double*>(sp + OFF_EPRET)[tid] = ep_return;
-                    reinterpret_cast<uint32_t*>(sp + OFF_EPST0)[tid] = es.w0;
-                    reinterpret_cast<uint32_t*>(sp + OFF_EPST1)[tid] = es.w1;
-                    (sp + OFF_FIN)[tid] = did_reset ? 1 : 0;
+                    reinterpret_cast<double*>(sp + OFF_EPRET)[col] = ep_return;
+                    reinterpret_cast<uint32_t*>(sp + OFF_EPST0)[col] = es.w0;
+                    reinterpret_cast<uint32_t*>(sp + OFF_EPST1)[col] = es.w1;
+                    (sp + OFF_FIN)[col] = did_reset ? 1 : 0;
                 }
                 // always-changing state goes back through the stage (one bulk store per tile)
 #pragma unroll
-                for (int j = 0; j < NJ; ++j) { s_jpjv[j * TILE + tid] = e.jp[j]; s_jpjv[(NJ + j) * TILE + tid] = e.jv[j]; }
-                reinterpret_cast<int*>(sp + OFF_SC)[tid] = e.sc;
+                for (int j = 0; j < NJ; ++j) { s_jpjv[j * TILE + col] = e.jp[j]; s_jpjv[(NJ + j) * TILE + col] = e.jv[j]; }
+                reinterpret_cast<int*>(sp + OFF_SC)[col] = e.sc;
                 // rarely-changing rows: straight from registers, only when they changed
                 float* __restrict__ obs = st.obs;
 #pragma unroll
@@ -297,7 +312,7 @@ step_tma_kernel(const DexsimState st, const DexsimParams p, const DexsimGroup* _
                 }
             }
             fence_async_smem();                       // generic-proxy writes -> visible to the copy engine
-            mbar_arrive(smem_u32(&bars[STAGES + s]));
+            mbar_arrive(smem_u32(&bars[NFULL + s]));
         }
     }
     if (TRACK && staged_cnt) {
