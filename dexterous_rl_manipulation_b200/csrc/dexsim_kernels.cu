@@ -650,9 +650,15 @@ static int launch_tma_variant(int sm_count, cudaStream_t s, const DexsimState& s
     constexpr int TMA_THREADS = tma_threads(GROUPS);
     const size_t smem = (size_t)STAGES * STAGE_BYTES + (STAGES * GROUPS + STAGES) * sizeof(uint64_t) +
                         (TRACK ? TMA_GROUPS_MAX * (DEXSIM_NCOUNTERS * sizeof(unsigned long long) + 2 * sizeof(double)) : 0);
-    static thread_local int ctas_per_sm = 0;        // per template instantiation
+    // per template instantiation and per device: the shared-memory opt-in is a per-device function attribute
+    static thread_local int occupancy[64] = {0};
+    int dev = 0;
+    cudaError_t err = cudaGetDevice(&dev);
+    if (err != cudaSuccess) return -(int)err;
+    int uncached = 0;
+    int& ctas_per_sm = (dev >= 0 && dev < 64) ? occupancy[dev] : uncached;
     if (ctas_per_sm == 0) {
-        cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (err != cudaSuccess) return -(int)err;
         err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, kern, TMA_THREADS, smem);
         if (err != cudaSuccess) return -(int)err;
