@@ -971,6 +971,7 @@ struct HostPipe {
 };
 HostPipe g_pipes[64];
 std::mutex g_pipes_mutex;      // first use from several host threads at once
+std::mutex g_enqueue_mutex;    // the fork / join events of a device's pipe are reused by every call
 
 int get_pipe(HostPipe** out) {
     int dev = 0;
@@ -1011,9 +1012,12 @@ int dexsim_step_host(const DexsimState* st, const DexsimParams* p, const DexsimG
     int64_t per = ((n + (chunks > 0 ? chunks : 1) - 1) / (chunks > 0 ? chunks : 1) + 1023) / 1024 * 1024;
     const int nchunks = (int)((n + per - 1) / per);
     HostPipe* hp = nullptr;
+    // The device's internal streams and events are shared by every caller: enqueue one step at a time.
+    std::unique_lock<std::mutex> enqueue_lock(g_enqueue_mutex, std::defer_lock);
     if (nchunks > 1) {
         rc = get_pipe(&hp);
         if (rc) return rc;
+        enqueue_lock.lock();
         cudaError_t err = cudaEventRecord(hp->fork_ev, user);
         if (err != cudaSuccess) return -(int)err;
         for (int k = 0; k < HOST_STREAMS && k < nchunks; ++k) {
@@ -1021,6 +1025,9 @@ int dexsim_step_host(const DexsimState* st, const DexsimParams* p, const DexsimG
             if (err != cudaSuccess) return -(int)err;
         }
     }
+    // Whatever happens while enqueueing, the caller's stream is joined with the internal ones before returning,
+    // so that no copy is still in flight on a stream the caller cannot see.
+    auto enqueue_chunks = [&]() -> int {
     for (int c = 0; c < nchunks; ++c) {
         const int64_t lo = (int64_t)c * per, hi = (lo + per < n) ? lo + per : n, m = hi - lo;
         cudaStream_t s = nchunks > 1 ? hp->streams[c % HOST_STREAMS] : user;
@@ -1070,15 +1077,19 @@ int dexsim_step_host(const DexsimState* st, const DexsimParams* p, const DexsimG
             if (err != cudaSuccess) return -(int)err;
         }
     }
+    return 0;
+    };
+    rc = enqueue_chunks();
     if (nchunks > 1) {
         for (int k = 0; k < HOST_STREAMS && k < nchunks; ++k) {
             cudaError_t err = cudaEventRecord(hp->join_ev[k], hp->streams[k]);
-            if (err != cudaSuccess) return -(int)err;
-            err = cudaStreamWaitEvent(user, hp->join_ev[k], 0);
-            if (err != cudaSuccess) return -(int)err;
+            if (err == cudaSuccess) err = cudaStreamWaitEvent(user, hp->join_ev[k], 0);
+            if (err != cudaSuccess && rc == 0) rc = -(int)err;
         }
+        enqueue_lock.unlock();
     }
-    return cuda_rc(cudaStreamSynchronize(user));
+    const int sync_rc = cuda_rc(cudaStreamSynchronize(user));
+    return rc ? rc : sync_rc;
 }
 
 }  // extern "C"
