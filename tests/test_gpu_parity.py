@@ -417,6 +417,49 @@ def test_tma_pipeline_equals_register_kernel(dx, n, track, dense):
         _lib.set_step_impl("auto")
 
 
+def test_maximum_size_batch(dx):
+    """33.5 M envs in one batch (~11 GB of state, 7.7e9 bytes of observations, a ragged last tile): both step kernels
+    agree on every array, and the LAST 1,000 envs equal a 1,000-env batch created with env_gid0 = n - 1000 --
+    every index above 2^31 bytes / 2^25 columns goes through the same 64-bit arithmetic as the small ones."""
+    from dexterous_rl_manipulation_b200 import _lib
+    free, _ = torch.cuda.mem_get_info()
+    if free < 40 * 2 ** 30:
+        pytest.skip("needs 40 GB of free device memory")
+    CC = dx.CurriculumConfig
+    n, tail = (1 << 25) + 128 + 77, 1000
+    kw = dict(max_episode_steps=3, reward_type="dense", seed=11, groups=[CC.easy(), CC.hard()],
+              auto_reset=True, respawn=True, loop_max_steps=3, track_episodes=True)
+    try:
+        a = torch.rand(n, 15, device="cuda", generator=torch.Generator(device="cuda").manual_seed(1)) * 2.4 - 1.2
+        small = dx.BatchedManipulationEnv(tail, "cuda", env_gid0=n - tail, **kw)
+        small.reset(seed=11)
+        for _ in range(5):
+            small.step(a[n - tail:])
+        ref = None
+        for impl in ("register", "tma"):
+            _lib.set_step_impl(impl)
+            env = dx.BatchedManipulationEnv(n, "cuda", **kw)
+            env.reset(seed=11)
+            for _ in range(5):                      # episodes are 3 steps long: every env resets at least once
+                out = env.step(a)
+            assert torch.equal(env._obs[:, n - tail:n], small._obs[:, :tail]), impl
+            assert torch.equal(env._step_count[n - tail:n], small._step_count[:tail])
+            assert torch.equal(env._episode[n - tail:n], small._episode[:tail])
+            assert torch.equal(env._ep_return[n - tail:n], small._ep_return[:tail])
+            assert torch.equal(out[1][n - tail:], small._step_out[1])
+            assert int(env.counters[:, 0].sum()) >= n
+            state = (env._obs, env._op64, env._step_count, env._cmask, env._episode, env._ep_return, env._ep_stats,
+                     env._thr, env._size, env.counters.clone(), out[1], out[2], out[3])
+            if ref is None:
+                ref = state
+            else:
+                for k, (x, y) in enumerate(zip(ref, state)):
+                    assert torch.equal(x, y), k
+            del env
+    finally:
+        _lib.set_step_impl("auto")
+
+
 @pytest.mark.parametrize("n,chunks,track", [(5000, 3, True), (4096, 1, False), (70_000, 8, True)])
 def test_step_host_matches_device_step(dx, n, chunks, track):
     """The end-to-end entry (host buffers, chunked copy/compute overlap) equals the device-tensor API."""
