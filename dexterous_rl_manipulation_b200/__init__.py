@@ -12,7 +12,13 @@ from ._lib import (CNT_EPISODES, CNT_LABEL_METRICS, CNT_LABEL_TAXONOMY, CNT_SUCC
                    NCOUNTERS, DexsimError, classify_summary)
 from .config import CurriculumConfig, group_from_config, group_table
 
-_lib.lib()          # fail loudly at import time when the CUDA extension is absent
+import sys as _sys
+
+# Fail loudly at import time when the CUDA extension is absent or stale -- except for the one command whose job is
+# to produce it (`python -m dexterous_rl_manipulation_b200.build` imports this package before running build.py).
+_argv = list(getattr(_sys, "orig_argv", []))
+if not ("-m" in _argv and __name__ + ".build" in _argv):
+    _lib.lib()
 
 from .env import BatchedManipulationEnv, Box  # noqa: E402
 from . import distributed  # noqa: E402

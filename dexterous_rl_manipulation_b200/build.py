@@ -12,7 +12,8 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 SRC = os.path.join(HERE, "csrc", "dexsim_kernels.cu")
-DEPS = [SRC, os.path.join(HERE, "csrc", "dexsim_core.cuh"), os.path.join(HERE, "..", "include", "dexsim.h")]
+DEPS = [SRC] + [os.path.join(HERE, "csrc", h) for h in ("dexsim_core.cuh", "dexsim_step_tma.cuh", "dexsim_rollout_split.cuh")] \
+    + [os.path.join(HERE, "..", "include", "dexsim.h")]
 OUT = os.path.join(HERE, "libdexsim_b200.so")
 
 NVCC_FLAGS = [

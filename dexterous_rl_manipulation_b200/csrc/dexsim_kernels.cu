@@ -529,8 +529,10 @@ rollout_kernel(const DexsimState st, const DexsimParams p, const DexsimGroup* __
 }
 
 // ---- single-env read-back ------------------------------------------------------------------------------
+// TAGGED: slot 63 = tag, written after every other slot is visible system-wide (host polling on mapped memory).
+template <bool TAGGED>
 __global__ void pack_env_kernel(const DexsimState st, const DexsimStepIO io, const int64_t i, const int after_reset,
-                                double* __restrict__ out) {
+                                double* __restrict__ out, const double tag) {
     const int t = threadIdx.x;
     const int64_t ld = st.ld;
     const float* obs = (io.noisy_obs && io.obs_noise) ? io.noisy_obs : st.obs;
@@ -546,7 +548,14 @@ __global__ void pack_env_kernel(const DexsimState st, const DexsimStepIO io, con
     if (t == 55) out[55] = st.friction[i];
     if (t >= 56 && t < 60) out[t] = (io.reward_comps && !after_reset) ? (double)io.reward_comps[(t - 56) * ld + i] : 0.0;
     if (t == 60) out[60] = (io.finished && !after_reset) ? (double)io.finished[i] : 0.0;
-    if (t > 60 && t < 64) out[t] = 0.0;
+    if (t > 60 && t < 63) out[t] = 0.0;
+    if (!TAGGED) {
+        if (t == 63) out[63] = 0.0;
+    } else {
+        __threadfence_system();
+        __syncthreads();
+        if (t == 0) *reinterpret_cast<volatile double*>(out + 63) = tag;
+    }
 }
 
 // ---- RNG exposure ------------------------------------------------------------------------------------
@@ -918,7 +927,17 @@ int dexsim_pack_env(const DexsimState* st, const DexsimStepIO* io, int64_t index
     if (rc) return rc;
     if (!io || !out64 || !io->reward || !io->terminated || !io->truncated) return DEXSIM_E_NULL;
     if (index < 0 || index >= st->n) return DEXSIM_E_SIZE;
-    pack_env_kernel<<<1, 64, 0, (cudaStream_t)stream>>>(*st, *io, index, after_reset ? 1 : 0, out64);
+    pack_env_kernel<false><<<1, 64, 0, (cudaStream_t)stream>>>(*st, *io, index, after_reset ? 1 : 0, out64, 0.0);
+    return cuda_rc(cudaGetLastError());
+}
+
+int dexsim_pack_env_tagged(const DexsimState* st, const DexsimStepIO* io, int64_t index, int32_t after_reset, double* out64,
+                           double tag, void* stream) {
+    int rc = check_state(st);
+    if (rc) return rc;
+    if (!io || !out64 || !io->reward || !io->terminated || !io->truncated) return DEXSIM_E_NULL;
+    if (index < 0 || index >= st->n) return DEXSIM_E_SIZE;
+    pack_env_kernel<true><<<1, 64, 0, (cudaStream_t)stream>>>(*st, *io, index, after_reset ? 1 : 0, out64, tag);
     return cuda_rc(cudaGetLastError());
 }
 

@@ -427,6 +427,14 @@ class BatchedManipulationEnv:
             # the reference silently promotes float64 actions and corrupts its own dtypes
             # (SURVEY.md 8a-1); the batched env takes float32 only
             a = a.astype(np.float32)
+        if self.single:
+            # 60 bytes: the kernel reads them from mapped page-locked host memory, no copy call.  Safe to
+            # overwrite: every single-env step ends by waiting for its result, so no kernel is still reading.
+            if getattr(self, "_action_pin", None) is None:
+                self._action_pin = torch.zeros(16, dtype=torch.float32).pin_memory()
+                self._action_pin_np = self._action_pin.numpy()
+            self._action_pin_np[:15] = a.reshape(15)
+            return self._action_pin
         self._action_dev.copy_(torch.from_numpy(np.ascontiguousarray(a.reshape(n, 15))), non_blocking=False)
         return self._action_dev
 
@@ -562,19 +570,29 @@ class BatchedManipulationEnv:
     def _single_readback(self, after_reset, noisy):
         """num_envs == 1: one pack kernel + one 512-byte D2H copy -> the reference's return values
         (obs float32[45], reward float, terminated, truncated, info dict of envs/manipulation_env.py:266-283)."""
-        if getattr(self, "_pack_dev", None) is None:
-            self._pack_dev = torch.zeros(64, dtype=torch.float64, device=self.device)
+        if getattr(self, "_pack_host", None) is None:
+            # page-locked and (unified addressing) mapped into the device: the pack kernel writes straight into it
             self._pack_host = torch.zeros(64, dtype=torch.float64).pin_memory()
+            self._pack_np = self._pack_host.numpy()
+            self._pack_tag = 0.0
         io = _lib.DexsimStepIO.from_buffer_copy(self._io)
         if noisy:
             io.noisy_obs, io.obs_noise = self._noisy_obs.data_ptr(), self._noisy_obs.data_ptr()
         else:
             io.noisy_obs = io.obs_noise = None
-        _lib.check(self._lib.dexsim_pack_env(self._state_ref, C.byref(io), 0, int(after_reset), self._pack_dev.data_ptr(),
-                                             self._stream()), "dexsim_pack_env")
-        self._pack_host.copy_(self._pack_dev, non_blocking=True)
-        torch.cuda.current_stream(self.device).synchronize()
-        h = self._pack_host.numpy()
+        self._pack_tag = tag = self._pack_tag + 1.0
+        _lib.check(self._lib.dexsim_pack_env_tagged(self._state_ref, C.byref(io), 0, int(after_reset),
+                                                    self._pack_host.data_ptr(), tag, self._stream()), "dexsim_pack_env_tagged")
+        h = self._pack_np
+        # the tag lands after the 63 data slots: poll it instead of paying a stream synchronize, but never
+        # spin forever -- a failed launch surfaces through the synchronize below
+        for _ in range(20000):
+            if h[63] == tag:
+                break
+        else:
+            torch.cuda.current_stream(self.device).synchronize()
+            if h[63] != tag:
+                raise RuntimeError("dexsim_pack_env_tagged: result did not arrive")
         obs = h[:45].astype(np.float32)
         info = {
             "step_count": int(h[49]),

@@ -252,6 +252,14 @@ int dexsim_rollout(const DexsimState* st, const DexsimParams* p, const DexsimGro
 int dexsim_pack_env(const DexsimState* st, const DexsimStepIO* io, int64_t index, int32_t after_reset,
                     double* out64 /* device [64] */, void* stream);
 
+/* Same, for a host that polls instead of synchronizing the stream: `out64` may be page-locked host memory that is
+ * mapped into the device address space (cudaHostAlloc under unified addressing -- the kernel writes straight into
+ * it, no copy); slot 63 receives `tag` AFTER slots 0..62 are visible system-wide, so a host thread that reads
+ * out64[63] == tag may read the other slots.  Use a tag that differs from the previous call's.  `io->action` of the
+ * preceding dexsim_step may likewise point to mapped page-locked host memory when n is small. */
+int dexsim_pack_env_tagged(const DexsimState* st, const DexsimStepIO* io, int64_t index, int32_t after_reset,
+                           double* out64 /* device or mapped host [64] */, double tag, void* stream);
+
 /* ---- RNG exposure (so tests can pre-draw exactly what the fused kernels draw) ---------------- */
 int dexsim_fill_policy_actions(const DexsimState* st, const DexsimParams* p, int32_t policy_kind,
                                float* actions /* [15, ld] for each env's CURRENT (episode, step) */,
