@@ -11,7 +11,7 @@ import numpy as _np
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("DEXSIM_LIB_PATH") or os.path.join(HERE, "libdexsim_b200.so")   # env override: kernel experiments only
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 NJ, NF, OBS = 15, 5, 45
 NCOUNTERS = 18
 MAX_GROUPS = 256
@@ -64,7 +64,8 @@ class DexsimStepIO(C.Structure):
                 ("dyn_noise", C.c_void_p), ("obs_noise", C.c_void_p), ("noisy_obs", C.c_void_p),
                 ("reward", C.c_void_p), ("reward_comps", C.c_void_p), ("terminated", C.c_void_p),
                 ("truncated", C.c_void_p), ("num_contacts", C.c_void_p), ("finished", C.c_void_p),
-                ("counters", C.c_void_p), ("ret_sums", C.c_void_p), ("reward64", C.c_void_p)]
+                ("counters", C.c_void_p), ("ret_sums", C.c_void_p), ("reward64", C.c_void_p),
+                ("sigma_dyn", C.c_float), ("sigma_obs", C.c_float)]
 
 
 class DexsimEpisodeRecord(C.Structure):

@@ -182,6 +182,17 @@ namespace dexsim {
 // memory with coalesced float4 reads (15 is odd, so the per-thread reads are bank-conflict free).
 // EXTRAS: noise, reward components, episode tracking, auto-reset -- the plain path carries none
 // of their registers or branches.
+// Observation entry `row` (envs/manipulation_env.py:254-264) of an env held in registers; `row` is a compile-time
+// constant wherever this is called from an unrolled loop.
+__device__ __forceinline__ float obs_entry(const EnvRegs& e, const int row) {
+    if (row < DEXSIM_ROW_JV) return e.jp[row - DEXSIM_ROW_JP];
+    if (row < DEXSIM_ROW_OP) return e.jv[row - DEXSIM_ROW_JV];
+    if (row < DEXSIM_ROW_QUAT) return (float)e.op[row - DEXSIM_ROW_OP];
+    if (row < DEXSIM_ROW_OV) return row == DEXSIM_ROW_QUAT ? 1.0f : 0.0f;
+    if (row < DEXSIM_ROW_CONTACT) return e.ov[row - DEXSIM_ROW_OV];
+    return ((e.cmask >> (row - DEXSIM_ROW_CONTACT)) & 1u) ? 1.0f : 0.0f;
+}
+
 template <bool DENSE, bool AOS, bool EXTRAS>
 __global__ void __launch_bounds__(STEP_THREADS, DEXSIM_STEP_MIN_BLOCKS)
 step_kernel(const DexsimState st, const DexsimParams p, const DexsimGroup* __restrict__ groups,
@@ -231,10 +242,28 @@ step_kernel(const DexsimState st, const DexsimParams p, const DexsimGroup* __res
         for (int k = 0; k < 3; ++k) { h.op_old[k] = e.op[k]; h.ov_old[k] = e.ov[k]; }
         h.cmask_old = e.cmask;
 
+        // in-kernel Philox noise (DexsimStepIO.sigma_*): needs the env's identity before the step
+        const bool fused_dyn = EXTRAS && !io.dyn_noise && io.sigma_dyn != 0.0f;
+        const bool fused_obs = EXTRAS && !io.obs_noise && io.noisy_obs && io.sigma_obs != 0.0f;
+        const int64_t gid = p.env_gid0 + i;
+        uint32_t episode = 0u;
+        int g = 0;
+        if (EXTRAS && (fused_dyn || fused_obs)) {
+            episode = st.episode[i];
+            if (io.sigma_dyn < 0.0f || io.sigma_obs < 0.0f) g = group_index(group_of_env, i, gid, p.num_groups);
+        }
         if (EXTRAS && io.dyn_noise) {                // evaluation/robustness_tests.py:180-187
 #pragma unroll
             for (int j = 0; j < NJ; ++j)
                 a[j] = clip_f32(__fadd_rn(a[j], __ldg(io.dyn_noise + j * ld + i)), -1.0f, 1.0f);
+        } else if (fused_dyn) {
+            const float sigma = io.sigma_dyn > 0.0f ? io.sigma_dyn : groups[g].sigma_dyn;
+            if (sigma > 0.0f) {
+                float nz[NJ];
+                normal_rows<NJ>(p.seed, (uint32_t)gid, episode, (uint32_t)e.sc, STREAM_DYN, sigma, nz);
+#pragma unroll
+                for (int j = 0; j < NJ; ++j) a[j] = clip_f32(__fadd_rn(a[j], nz[j]), -1.0f, 1.0f);
+            }
         }
 
         StepResult r;
@@ -269,9 +298,8 @@ step_kernel(const DexsimState st, const DexsimParams p, const DexsimGroup* __res
         bool finished = false;
         if (p.auto_reset && done) {
             finished = true;
-            const int64_t gid = p.env_gid0 + i;
-            const int g = group_index(group_of_env, i, gid, p.num_groups);
-            uint32_t episode = st.episode[i];
+            g = group_index(group_of_env, i, gid, p.num_groups);
+            episode = st.episode[i];
             double size, mass, friction;
             unsigned long long* cnt = nullptr;
             double* rs = nullptr;
@@ -312,6 +340,23 @@ step_kernel(const DexsimState st, const DexsimParams p, const DexsimGroup* __res
             for (int f = 0; f < NF; ++f)
                 out[(DEXSIM_ROW_CONTACT + f) * ld + i] =
                     __fadd_rn(((e.cmask >> f) & 1u) ? 1.0f : 0.0f, __ldg(nz + (DEXSIM_ROW_CONTACT + f) * ld + i));
+        } else if (fused_obs) {
+            // the same 45 normals dexsim_fill_normal(STREAM_OBS) would produce for the env's state AFTER this step
+            // (and after an auto-reset): one Philox block = four observation rows, written as they are drawn
+            const float sigma = io.sigma_obs > 0.0f ? io.sigma_obs : groups[g].sigma_obs;
+            float* __restrict__ out = io.noisy_obs;
+#pragma unroll
+            for (int b = 0; b < (NOBS + 3) / 4; ++b) {
+                const U4 o = rng_block(p.seed, (uint32_t)gid, episode, (uint32_t)e.sc, STREAM_OBS, (uint32_t)b);
+                float z[4];
+                normal_pair(o.x, o.y, z[0], z[1]);
+                normal_pair(o.z, o.w, z[2], z[3]);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const int row = 4 * b + k;
+                    if (row < NOBS) out[row * ld + i] = __fadd_rn(obs_entry(e, row), __fmul_rn(sigma, z[k]));
+                }
+            }
         }
     }
     if (EXTRAS && staged) {
@@ -746,10 +791,13 @@ static int launch_step(const DexsimState* st, const DexsimParams* p, const Dexsi
     if (rc) return rc;
     if (!io || !io->action || !io->reward || !io->terminated || !io->truncated || !io->num_contacts) return DEXSIM_E_NULL;
     if (io->action_layout != 0 && io->action_layout != 1) return DEXSIM_E_PARAM;
-    if ((io->obs_noise != nullptr) != (io->noisy_obs != nullptr)) return DEXSIM_E_NULL;
+    const bool fused_dyn = !io->dyn_noise && io->sigma_dyn != 0.0f;
+    const bool fused_obs = !io->obs_noise && io->sigma_obs != 0.0f;
+    if ((io->obs_noise != nullptr || fused_obs) != (io->noisy_obs != nullptr)) return DEXSIM_E_NULL;
     const bool extras = io->dyn_noise || io->obs_noise || io->reward_comps || io->reward64 || io->finished ||
-                        p->auto_reset || st->ep_return != nullptr;
-    rc = check_params(p, p && p->auto_reset, groups);
+                        (p && p->auto_reset) || st->ep_return != nullptr || fused_dyn || fused_obs;
+    const bool group_sigma = (fused_dyn && io->sigma_dyn < 0.0f) || (fused_obs && io->sigma_obs < 0.0f);
+    rc = check_params(p, p && (p->auto_reset || group_sigma), groups);
     if (rc) return rc;
     if (st->n == 0) return 0;
     DeviceInfo di;
@@ -758,7 +806,7 @@ static int launch_step(const DexsimState* st, const DexsimParams* p, const Dexsi
     // TMA pipeline: everything except the noise / reward-component outputs; needs 16-byte aligned bases
     const int impl = step_impl_choice();
     const bool track = extras;
-    const bool tma_ok = !io->dyn_noise && !io->obs_noise && !io->reward_comps && !io->reward64 && (!track || st->ep_return != nullptr) &&
+    const bool tma_ok = !io->dyn_noise && !io->obs_noise && !fused_dyn && !fused_obs && !io->reward_comps && !io->reward64 && (!track || st->ep_return != nullptr) &&
                         st->n >= TILE && st->n < (int64_t)0x7FFFFF00 &&
                         !(reinterpret_cast<uintptr_t>(io->action) & 15u) && !(reinterpret_cast<uintptr_t>(io->reward) & 15u) &&
                         !(reinterpret_cast<uintptr_t>(st->thr) & 15u) && !(reinterpret_cast<uintptr_t>(st->damp) & 15u) &&
@@ -1022,7 +1070,8 @@ int dexsim_step_host(const DexsimState* st, const DexsimParams* p, const DexsimG
     int rc = check_state(st);
     if (rc) return rc;
     if (!p || !io || !io->action || !h_action || !h_reward || !h_terminated || !h_truncated) return DEXSIM_E_NULL;
-    if (io->dyn_noise || io->obs_noise || io->noisy_obs) return DEXSIM_E_PARAM;   // noise: use dexsim_step
+    if (io->dyn_noise || io->obs_noise || io->noisy_obs || io->sigma_dyn != 0.0f || io->sigma_obs != 0.0f)
+        return DEXSIM_E_PARAM;   // noise: use dexsim_step
     cudaStream_t user = (cudaStream_t)stream;
     const int64_t n = st->n, ld = st->ld;
     if (n == 0) return 0;

@@ -215,7 +215,7 @@ step_tma_kernel(const DexsimState st, const DexsimParams p, const DexsimGroup* _
         // ===== compute warps: lane == column of the tile =====
         const int col = tid & (TMA_COMPUTE_THREADS - 1);
         for (int k = tid / TMA_COMPUTE_THREADS; k < my_tiles; k += GROUPS) {
-            const int s = k % STAGES, use = k / STAGES;
+            const int s = k % STAGES;
             unsigned char* sp = stage_base + (size_t)s * STAGE_BYTES;
             const int64_t base = ((int64_t)blockIdx.x + (int64_t)k * gridDim.x) * TILE;
             const int64_t i = base + col;

@@ -195,7 +195,9 @@ class BatchedManipulationEnv:
         self._did_reset = False
         self._rollout_steps = 0
         self._n15 = n * 15
-        self._noisy_env = self.observation_noise_std > 0.0 or self.dynamics_noise_std > 0.0
+        # Philox noise of noisy envs is drawn inside the step kernel; False = separate dexsim_fill_normal launches
+        # (same numbers, kept for cross-checking)
+        self.fused_noise = True
         self._io_has_noise = False
         self._state_ref, self._params_ref, self._io_ref = C.byref(self._state), C.byref(self._params), C.byref(self._io)
         self._goe_ptr = self._ptr(self._goe)
@@ -267,6 +269,10 @@ class BatchedManipulationEnv:
         if self._group_cfgs is None:
             so, sd = self.observation_noise_std, self.dynamics_noise_std
         table = group_table(cfgs, so, sd)
+        # noise cells of a multi-group batch (group_sigma_*): step() draws them in-kernel with each env's group value
+        self._group_noise = (self._group_cfgs is not None and bool(np.any(np.asarray(so, np.float64) > 0.0)),
+                             self._group_cfgs is not None and bool(np.any(np.asarray(sd, np.float64) > 0.0)))
+        self._noisy_env = (self.observation_noise_std > 0.0 or self.dynamics_noise_std > 0.0 or any(self._group_noise))
         raw = torch.frombuffer(bytearray(bytes(table)), dtype=torch.uint8)
         if self._groups_dev is None or self._groups_dev.numel() != raw.numel():
             self._groups_dev = torch.empty(raw.numel(), dtype=torch.uint8, device=self.device)
@@ -468,6 +474,7 @@ class BatchedManipulationEnv:
             io.action, io.action_layout = action.data_ptr(), 1
             if self._io_has_noise:
                 io.dyn_noise = io.obs_noise = io.noisy_obs = None
+                io.sigma_dyn = io.sigma_obs = 0.0
                 self._io_has_noise = False
             rc = self._lib.dexsim_step(self._state_ref, self._params_ref, self._groups_ptr, self._goe_ptr,
                                        self._io_ref, torch.cuda.current_stream().cuda_stream)
@@ -482,28 +489,39 @@ class BatchedManipulationEnv:
         a = self._ingest_action(action)
         io.action, io.action_layout = a.data_ptr(), 1
         keep = [a]
-        want_dyn = dyn_noise is not None or self.dynamics_noise_std > 0.0
-        want_obs = obs_noise is not None or self.observation_noise_std > 0.0
+        group_obs, group_dyn = self._group_noise
+        want_dyn = dyn_noise is not None or self.dynamics_noise_std > 0.0 or group_dyn
+        want_obs = obs_noise is not None or self.observation_noise_std > 0.0 or group_obs
         io.dyn_noise = io.obs_noise = io.noisy_obs = None
-        self._io_has_noise = want_dyn or obs_noise is not None
+        io.sigma_dyn = io.sigma_obs = 0.0
+        self._io_has_noise = want_dyn or want_obs
         if want_dyn or want_obs:
             self._noise_buffers()
+        fused = self.fused_noise
         if want_dyn:
             if dyn_noise is not None:
                 dn = self._soa(dyn_noise, 15)
+                io.dyn_noise = dn.data_ptr(); keep.append(dn)
+            elif group_dyn and not self.dynamics_noise_std > 0.0:
+                io.sigma_dyn = -1.0                         # each env's group value, drawn inside the step kernel
+            elif fused:
+                io.sigma_dyn = self.dynamics_noise_std      # Philox normals drawn inside the step kernel
             else:
                 dn = self._dyn_noise
                 _lib.check(self._lib.dexsim_fill_normal(
                     self._state_ref, self._params_ref, _L.RNG_STREAM_DYN, 15,
                     C.c_float(self.dynamics_noise_std), dn.data_ptr(), self._stream()), "dexsim_fill_normal")
-            io.dyn_noise = dn.data_ptr(); keep.append(dn)
+                io.dyn_noise = dn.data_ptr(); keep.append(dn)
         if obs_noise is not None:
             on = self._soa(obs_noise, 45)
             io.obs_noise, io.noisy_obs = on.data_ptr(), self._noisy_obs.data_ptr()
             keep.append(on)
+        elif want_obs and (fused or not self.observation_noise_std > 0.0):
+            io.sigma_obs = self.observation_noise_std if self.observation_noise_std > 0.0 else -1.0
+            io.noisy_obs = self._noisy_obs.data_ptr()
         _lib.check(self._lib.dexsim_step(self._state_ref, self._params_ref, self._groups_ptr, self._goe_ptr,
                                          self._io_ref, self._stream()), "dexsim_step")
-        if want_obs and obs_noise is None:
+        if want_obs and obs_noise is None and not fused and self.observation_noise_std > 0.0:
             # Philox observation noise is keyed by (episode, step count AFTER the step), so it is
             # drawn once the step has run (evaluation/robustness_tests.py:204-205)
             _lib.check(self._lib.dexsim_fill_normal(
@@ -556,6 +574,7 @@ class BatchedManipulationEnv:
         io = self._io
         io.action, io.action_layout = action_soa.data_ptr(), 0
         io.dyn_noise = io.obs_noise = io.noisy_obs = None
+        io.sigma_dyn = io.sigma_obs = 0.0
         _lib.check(self._lib.dexsim_step(self._state_ref, self._params_ref, self._groups_ptr, self._goe_ptr,
                                          self._io_ref, self._stream()), "dexsim_step")
         return self._step_out
@@ -674,6 +693,7 @@ class BatchedManipulationEnv:
             io = self._io
             io.action, io.action_layout = self._action_dev.data_ptr(), 1
             io.dyn_noise = io.obs_noise = io.noisy_obs = None
+            io.sigma_dyn = io.sigma_obs = 0.0
             _lib.check(self._lib.dexsim_step_host(
                 C.byref(self._state), C.byref(self._params), self._ptr(self._groups_dev), self._ptr(self._goe),
                 C.byref(io), a.data_ptr(), self._h_obs.data_ptr(), self._h_reward.data_ptr(), self._h_term.data_ptr(),

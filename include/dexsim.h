@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define DEXSIM_ABI_VERSION 1
+#define DEXSIM_ABI_VERSION 2
 #define DEXSIM_NJ 15      /* joints            envs/manipulation_env.py:52 */
 #define DEXSIM_NF 5       /* fingers           envs/manipulation_env.py:50 */
 #define DEXSIM_OBS 45     /* observation width envs/manipulation_env.py:96-106 */
@@ -151,6 +151,14 @@ typedef struct DexsimStepIO {
     double*      reward64;      /* [ld] out: the float64 total exactly as the reference returns it (Python float); or NULL.
                                  * Needed by callers that compare rewards (SimpleLearner.update); served by the
                                  * register-resident kernel. */
+    /* Noise drawn INSIDE the step kernel (Philox normals, the streams dexsim_fill_normal exposes), used when the
+     * corresponding pre-drawn pointer above is NULL:  > 0 = this standard deviation for every env,  < 0 = each env's
+     * group value (DexsimGroup.sigma_dyn / sigma_obs; needs the group table),  0 = off.
+     * sigma_dyn: a <- clip(a + N(0, sigma), -1, 1) keyed by (episode, step count BEFORE the step)
+     * (robustness_tests.py:180-187);  sigma_obs: noisy_obs <- obs + N(0, sigma) for all 45 entries, keyed by
+     * (episode, step count AFTER the step and a possible auto-reset) (:204-205); needs `noisy_obs`. */
+    float        sigma_dyn;
+    float        sigma_obs;
 } DexsimStepIO;
 
 /* ---- library ---------------------------------------------------------------------------- */

@@ -417,6 +417,56 @@ def test_tma_pipeline_equals_register_kernel(dx, n, track, dense):
         _lib.set_step_impl("auto")
 
 
+@pytest.mark.parametrize("n,track", [(1000, False), (4096 + 5, True)])
+def test_in_kernel_noise_equals_separate_noise_kernels(dx, n, track):
+    """DexsimStepIO.sigma_dyn / sigma_obs (Philox normals drawn inside the step kernel) give exactly what the
+    separate dexsim_fill_normal launches + add give: same streams, same counters, also across auto-resets."""
+    CC = dx.CurriculumConfig
+    kw = dict(max_episode_steps=20, reward_type="dense", seed=9, curriculum_config=CC.easy(),
+              observation_noise_std=0.05, dynamics_noise_std=0.1)
+    if track:
+        kw.update(auto_reset=True, respawn=True, loop_max_steps=20, track_episodes=True)
+    a, b = dx.BatchedManipulationEnv(n, "cuda", **kw), dx.BatchedManipulationEnv(n, "cuda", **kw)
+    b.fused_noise = False
+    oa, _ = a.reset(seed=9)
+    ob, _ = b.reset(seed=9)
+    assert torch.equal(oa, ob)
+    gen = torch.Generator(device="cuda").manual_seed(2)
+    for t in range(50):
+        act = torch.rand(n, 15, device="cuda", generator=gen) * 2.4 - 1.2
+        ra, rb = a.step(act), b.step(act)
+        for x, y in zip(ra[:4], rb[:4]):
+            assert torch.equal(x, y), t
+        assert torch.equal(ra[4]["num_contacts"], rb[4]["num_contacts"])
+    assert not torch.equal(ra[0], a._obs[:, :n].t())                  # the returned observation is the noisy one
+    for name in ("_obs", "_op64", "_step_count", "_cmask", "_episode", "_noisy_obs"):
+        assert torch.equal(getattr(a, name), getattr(b, name)), name
+    if track:
+        assert torch.equal(a.counters, b.counters) and int(a.counters[:, 0].sum()) > n
+
+
+def test_group_noise_cells_in_step(dx):
+    """Noise cells as groups of one batch (group_sigma_*), stepped through the API with external actions: every
+    env behaves like the same env of a batch whose env-level noise is its group's value."""
+    CC = dx.CurriculumConfig
+    n, cfg = 2048, CC.medium()
+    kw = dict(max_episode_steps=30, reward_type="dense", seed=4)
+    cells = dx.BatchedManipulationEnv(n, "cuda", groups=[cfg, cfg], group_sigma_obs=[0.02, 0.0], group_sigma_dyn=[0.0, 0.1], **kw)
+    only_obs = dx.BatchedManipulationEnv(n, "cuda", groups=[cfg, cfg], observation_noise_std=0.02, **kw)
+    only_dyn = dx.BatchedManipulationEnv(n, "cuda", groups=[cfg, cfg], dynamics_noise_std=0.1, **kw)
+    for e in (cells, only_obs, only_dyn):
+        e.reset(seed=4)
+    gen = torch.Generator(device="cuda").manual_seed(6)
+    for t in range(30):
+        act = torch.rand(n, 15, device="cuda", generator=gen) * 2 - 1
+        rc, ro, rd = cells.step(act), only_obs.step(act), only_dyn.step(act)
+        assert torch.equal(rc[0][0::2], ro[0][0::2]) and torch.equal(rc[1][0::2], ro[1][0::2]), t     # group 0: sigma_obs
+        assert torch.equal(rc[0][1::2], rd[0][1::2]) and torch.equal(rc[1][1::2], rd[1][1::2]), t     # group 1: sigma_dyn
+    assert torch.equal(cells._obs[:, 0:n:2], only_obs._obs[:, 0:n:2])
+    assert torch.equal(cells._obs[:, 1:n:2], only_dyn._obs[:, 1:n:2])
+    assert not torch.equal(cells._obs[:, 1:n:2], only_obs._obs[:, 1:n:2])       # dynamics noise did change trajectories
+
+
 def test_maximum_size_batch(dx):
     """33.5 M envs in one batch (~11 GB of state, 7.7e9 bytes of observations, a ragged last tile): both step kernels
     agree on every array, and the LAST 1,000 envs equal a 1,000-env batch created with env_gid0 = n - 1000 --
