@@ -132,8 +132,14 @@ struct EpisodeLog {
 // (loop shape of evaluation/evaluator.py:135-173 / training/episode_utils.py:42-55).
 __device__ __forceinline__ void finish_episode(const EnvRegs& e, const DexsimParams& p, uint32_t gid, uint32_t episode,
                                                double ep_return, const EpStats& es, bool terminated, int n_c,
-                                               unsigned long long* cnt, double* rs, const EpisodeLog* log) {
+                                               unsigned long long* cnt, double* rs, const EpisodeLog* log,
+                                               const bool classify = true) {
     if (!(cnt || (log && log->rec))) return;
+    if (!classify) {            // counts-only tracking: no history summary, no return -> no labels, no return sums
+        if (cnt) record_episode(cnt, nullptr, p.success_is_terminated ? (terminated ? 1 : 0) : 0, e.sc, n_c,
+                                DEXSIM_LABEL_NONE, DEXSIM_LABEL_NONE, 0, 0.0);
+        return;
+    }
     DexsimEpisodeSummary s;
     s.success = p.success_is_terminated ? (terminated ? 1 : 0) : 0;
     s.episode_steps = e.sc; s.num_contacts = n_c; s.final_contacts = n_c; s.hist_len = e.sc;
@@ -160,8 +166,8 @@ __device__ __forceinline__ void finish_and_reset(EnvRegs& e, const DexsimParams&
                                                  uint32_t gid, uint32_t& episode, double& ep_return, EpStats& es,
                                                  bool terminated, int n_c, unsigned long long* cnt, double* rs,
                                                  double& size, double& mass, double& friction,
-                                                 const EpisodeLog* log = nullptr) {
-    finish_episode(e, p, gid, episode, ep_return, es, terminated, n_c, cnt, rs, log);
+                                                 const EpisodeLog* log = nullptr, const bool classify = true) {
+    finish_episode(e, p, gid, episode, ep_return, es, terminated, n_c, cnt, rs, log, classify);
     episode += 1u;
     float jp0[NJ], pos[3];
     reset_draws(p.seed, gid, episode, grp, jp0, size, mass, friction, pos);
@@ -203,7 +209,7 @@ step_kernel(const DexsimState st, const DexsimParams p, const DexsimGroup* __res
     // on the same 18 L2 addresses.
     __shared__ unsigned long long sh_cnt[EXTRAS ? SMEM_GROUPS_MAX * DEXSIM_NCOUNTERS : 1];
     __shared__ double sh_rs[EXTRAS ? SMEM_GROUPS_MAX * 2 : 1];
-    const bool count_episodes = EXTRAS && p.auto_reset && io.counters != nullptr && st.ep_return != nullptr;
+    const bool count_episodes = EXTRAS && p.auto_reset && io.counters != nullptr;     // with or without per-env tracking arrays
     const bool staged = count_episodes && p.num_groups <= SMEM_GROUPS_MAX;
     if (EXTRAS && staged) {
         for (int w = threadIdx.x; w < p.num_groups * DEXSIM_NCOUNTERS; w += STEP_THREADS) sh_cnt[w] = 0ull;
@@ -308,7 +314,7 @@ step_kernel(const DexsimState st, const DexsimParams p, const DexsimGroup* __res
                 if (io.ret_sums) rs = (staged ? sh_rs : io.ret_sums) + 2 * g;
             }
             finish_and_reset(e, p, groups[g], (uint32_t)gid, episode, ep_return, es, r.terminated, r.n_c,
-                             cnt, rs, size, mass, friction);
+                             cnt, rs, size, mass, friction, nullptr, /*classify=*/tracking);
             st.episode[i] = episode;
             st.size[i] = size; st.mass[i] = mass; st.friction[i] = friction;
             store_env_full(st, i, e);
@@ -696,7 +702,7 @@ static void launch_step_variant(bool extras, int grid, cudaStream_t s, const Dex
     else        step_kernel<DENSE, AOS, false><<<grid, STEP_THREADS, 0, s>>>(st, p, groups, goe, io);
 }
 
-template <bool DENSE, bool AOS, bool TRACK, int STAGES, int GROUPS>
+template <bool DENSE, bool AOS, int TRACK, int STAGES, int GROUPS>
 static int launch_tma_variant(int sm_count, cudaStream_t s, const DexsimState& st, const DexsimParams& p,
                               const DexsimGroup* groups, const uint16_t* goe, const DexsimStepIO& io,
                               const StepMaps& maps, int num_tiles) {
@@ -751,8 +757,9 @@ static int tma_shape_choice() {
 #endif
 }
 
+// track: 0 = plain step, 1 = full episode tracking (returns + history summaries -> labels), 2 = counts only
 static int launch_step_tma(const DexsimState* st, const DexsimParams* p, const DexsimGroup* groups, const uint16_t* goe,
-                           const DexsimStepIO* io, cudaStream_t s, bool track, int sm_count) {
+                           const DexsimStepIO* io, cudaStream_t s, int track, int sm_count) {
     StepMaps maps;
     memset(&maps, 0, sizeof(maps));
     const bool aos = io->action_layout == 1;
@@ -777,10 +784,10 @@ static int launch_step_tma(const DexsimState* st, const DexsimParams* p, const D
     if (dense == D && aos == A && track == T)                                                                    \
         return launch_tma_variant<D, A, T, 2, 1>(sm_count, s, *st, *p, groups, goe, *io, maps, num_tiles);
 #endif
-    DEXSIM_TMA_CASE(true, true, true) DEXSIM_TMA_CASE(true, true, false)
-    DEXSIM_TMA_CASE(true, false, true) DEXSIM_TMA_CASE(true, false, false)
-    DEXSIM_TMA_CASE(false, true, true) DEXSIM_TMA_CASE(false, true, false)
-    DEXSIM_TMA_CASE(false, false, true) DEXSIM_TMA_CASE(false, false, false)
+    DEXSIM_TMA_CASE(true, true, 0) DEXSIM_TMA_CASE(true, true, 1) DEXSIM_TMA_CASE(true, true, 2)
+    DEXSIM_TMA_CASE(true, false, 0) DEXSIM_TMA_CASE(true, false, 1) DEXSIM_TMA_CASE(true, false, 2)
+    DEXSIM_TMA_CASE(false, true, 0) DEXSIM_TMA_CASE(false, true, 1) DEXSIM_TMA_CASE(false, true, 2)
+    DEXSIM_TMA_CASE(false, false, 0) DEXSIM_TMA_CASE(false, false, 1) DEXSIM_TMA_CASE(false, false, 2)
 #undef DEXSIM_TMA_CASE
     return 1;
 }
@@ -805,16 +812,16 @@ static int launch_step(const DexsimState* st, const DexsimParams* p, const Dexsi
     if (rc) return rc;
     // TMA pipeline: everything except the noise / reward-component outputs; needs 16-byte aligned bases
     const int impl = step_impl_choice();
-    const bool track = extras;
-    const bool tma_ok = !io->dyn_noise && !io->obs_noise && !fused_dyn && !fused_obs && !io->reward_comps && !io->reward64 && (!track || st->ep_return != nullptr) &&
+    const int track = !extras ? 0 : (st->ep_return != nullptr ? 1 : 2);
+    const bool tma_ok = !io->dyn_noise && !io->obs_noise && !fused_dyn && !fused_obs && !io->reward_comps && !io->reward64 &&
                         st->n >= TILE && st->n < (int64_t)0x7FFFFF00 &&
                         !(reinterpret_cast<uintptr_t>(io->action) & 15u) && !(reinterpret_cast<uintptr_t>(io->reward) & 15u) &&
                         !(reinterpret_cast<uintptr_t>(st->thr) & 15u) && !(reinterpret_cast<uintptr_t>(st->damp) & 15u) &&
                         !(reinterpret_cast<uintptr_t>(st->step_count) & 15u) && !(reinterpret_cast<uintptr_t>(st->cmask) & 15u) &&
                         !(reinterpret_cast<uintptr_t>(io->terminated) & 15u) && !(reinterpret_cast<uintptr_t>(io->truncated) & 15u) &&
                         !(reinterpret_cast<uintptr_t>(io->num_contacts) & 15u) &&
-                        (!track || (!(reinterpret_cast<uintptr_t>(st->ep_return) & 15u) && !(reinterpret_cast<uintptr_t>(st->ep_stats) & 15u) &&
-                                    !(reinterpret_cast<uintptr_t>(io->finished) & 15u)));
+                        (track != 1 || (!(reinterpret_cast<uintptr_t>(st->ep_return) & 15u) && !(reinterpret_cast<uintptr_t>(st->ep_stats) & 15u))) &&
+                        !(reinterpret_cast<uintptr_t>(io->finished) & 15u);
     if (impl != 1 && tma_ok) {
         rc = launch_step_tma(st, p, groups, goe, io, s, track, di.sm_count);
         if (rc <= 0) return rc;                      // launched (0) or CUDA error (< 0); 1 = not available

@@ -112,10 +112,12 @@ __device__ __forceinline__ uint32_t full_parity(int k) {
     return (uint32_t)((GROUPS == 1 ? k / STAGES : k / (STAGES * GROUPS)) & 1);
 }
 
-// DENSE: reward type.  AOS: action layout [n,15].  TRACK: episode tracking / auto-reset / counters.
+// DENSE: reward type.  AOS: action layout [n,15].  TRACK: 0 = plain step; 1 = episode tracking (return + history
+// summary per env -> failure labels), auto-reset, counters; 2 = auto-reset and counters only (what a curriculum
+// needs: episodes, successes, lengths) without the per-env return / history arrays.
 // GROUPS: compute groups per CTA.  With 2 groups (8 compute warps, 3 stages, 2 CTAs per SM) group g works on the
 // CTA's tiles k = g, g + 2, ... so that two tiles are in their compute phase while a third one loads.
-template <bool DENSE, bool AOS, bool TRACK, int STAGES, int GROUPS>
+template <bool DENSE, bool AOS, int TRACK, int STAGES, int GROUPS>
 __global__ void __launch_bounds__(tma_threads(GROUPS), (GROUPS == 2) ? 2 : ((STAGES == 2) ? 3 : 2))
 step_tma_kernel(const DexsimState st, const DexsimParams p, const DexsimGroup* __restrict__ groups,
                 const uint16_t* __restrict__ group_of_env, const DexsimStepIO io,
@@ -161,12 +163,12 @@ step_tma_kernel(const DexsimState st, const DexsimParams p, const DexsimGroup* _
                 bulk_store(io.terminated + base, sb + OFF_TERM, cols);
                 bulk_store(io.truncated + base, sb + OFF_TRUNC, cols);
                 bulk_store(io.num_contacts + base, sb + OFF_NC, cols);
-                if (TRACK) {
+                if (TRACK == 1) {
                     bulk_store(st.ep_return + base, sb + OFF_EPRET, cols * 8);
                     bulk_store(st.ep_stats + base, sb + OFF_EPST0, cols * 4);
                     bulk_store(st.ep_stats + ld + base, sb + OFF_EPST1, cols * 4);
-                    if (io.finished) bulk_store(io.finished + base, sb + OFF_FIN, cols);
                 }
+                if (TRACK && io.finished) bulk_store(io.finished + base, sb + OFF_FIN, cols);
                 bulk_commit();
             };
             for (int k = 0; k < my_tiles; ++k) {
@@ -186,7 +188,7 @@ step_tma_kernel(const DexsimState st, const DexsimParams p, const DexsimGroup* _
                 uint32_t tx = (30 + 3) * TILE * 4 + 3 * TILE * 8 + cols * (8 + 4 + 4 + 1);
                 if (AOS) tx += full_tile ? NJ * TILE * 4 : 0;
                 else tx += NJ * TILE * 4;
-                if (TRACK) tx += cols * (8 + 4 + 4);
+                if (TRACK == 1) tx += cols * (8 + 4 + 4);
                 mbar_expect_tx(full, tx);
                 tma_load_2d(sb + OFF_JPJV, &maps.obs_jpjv, (int)base, DEXSIM_ROW_JP, full);
                 tma_load_2d(sb + OFF_OV, &maps.obs_ov, (int)base, DEXSIM_ROW_OV, full);
@@ -197,7 +199,7 @@ step_tma_kernel(const DexsimState st, const DexsimParams p, const DexsimGroup* _
                 bulk_load(sb + OFF_DAMP, st.damp + base, cols * 4, full);
                 bulk_load(sb + OFF_SC, st.step_count + base, cols * 4, full);
                 bulk_load(sb + OFF_CMASK, st.cmask + base, cols, full);
-                if (TRACK) {
+                if (TRACK == 1) {
                     bulk_load(sb + OFF_EPRET, st.ep_return + base, cols * 8, full);
                     bulk_load(sb + OFF_EPST0, st.ep_stats + base, cols * 4, full);
                     bulk_load(sb + OFF_EPST1, st.ep_stats + ld + base, cols * 4, full);
@@ -262,9 +264,14 @@ step_tma_kernel(const DexsimState st, const DexsimParams p, const DexsimGroup* _
 
                 bool did_reset = false;
                 if (TRACK) {
-                    double ep_return = __dadd_rn(reinterpret_cast<double*>(sp + OFF_EPRET)[col], r.total);
-                    EpStats es{reinterpret_cast<uint32_t*>(sp + OFF_EPST0)[col], reinterpret_cast<uint32_t*>(sp + OFF_EPST1)[col]};
-                    epstats_push(es, e.sc - 1, r.n_c);
+                    double ep_return = 0.0;
+                    EpStats es{0u, 0u};
+                    if (TRACK == 1) {
+                        ep_return = __dadd_rn(reinterpret_cast<double*>(sp + OFF_EPRET)[col], r.total);
+                        es.w0 = reinterpret_cast<uint32_t*>(sp + OFF_EPST0)[col];
+                        es.w1 = reinterpret_cast<uint32_t*>(sp + OFF_EPST1)[col];
+                        epstats_push(es, e.sc - 1, r.n_c);
+                    }
                     const bool done = r.terminated || r.truncated || (p.loop_max_steps > 0 && e.sc >= p.loop_max_steps);
                     if (p.auto_reset && done) {
                         did_reset = true;
@@ -279,14 +286,16 @@ step_tma_kernel(const DexsimState st, const DexsimParams p, const DexsimGroup* _
                             if (io.ret_sums) rs = (staged_cnt ? sh_rs : io.ret_sums) + 2 * g;
                         }
                         finish_and_reset(e, p, groups[g], (uint32_t)gid, episode, ep_return, es, r.terminated, r.n_c,
-                                         cnt, rs, size, mass, friction);
+                                         cnt, rs, size, mass, friction, nullptr, /*classify=*/TRACK == 1);
                         st.episode[i] = episode;
                         st.size[i] = size; st.mass[i] = mass; st.friction[i] = friction;
                         st.thr[i] = e.thr; st.damp[i] = e.damp;
                     }
-                    reinterpret_cast<double*>(sp + OFF_EPRET)[col] = ep_return;
-                    reinterpret_cast<uint32_t*>(sp + OFF_EPST0)[col] = es.w0;
-                    reinterpret_cast<uint32_t*>(sp + OFF_EPST1)[col] = es.w1;
+                    if (TRACK == 1) {
+                        reinterpret_cast<double*>(sp + OFF_EPRET)[col] = ep_return;
+                        reinterpret_cast<uint32_t*>(sp + OFF_EPST0)[col] = es.w0;
+                        reinterpret_cast<uint32_t*>(sp + OFF_EPST1)[col] = es.w1;
+                    }
                     (sp + OFF_FIN)[col] = did_reset ? 1 : 0;
                 }
                 // always-changing state goes back through the stage (one bulk store per tile)

@@ -376,15 +376,16 @@ def test_unmodified_reference_callers_when_available(dx):
 
 
 @pytest.mark.parametrize("n,track,dense", [(128, False, True), (1000, False, False), (4096 + 77, True, True),
-                                            (65536, True, True), (200_000, False, True)])
+                                            (65536, True, True), (200_000, False, True), (4096 + 77, "counts", True),
+                                            (70_000, "counts", False)])
 def test_tma_pipeline_equals_register_kernel(dx, n, track, dense):
     """The TMA/mbarrier step kernel and the register-resident one must agree bit for bit on every
     array (full and ragged last tiles, AoS and SoA actions, with and without tracking/auto-reset)."""
     from dexterous_rl_manipulation_b200 import _lib
     CC = dx.CurriculumConfig
     kw = dict(max_episode_steps=25, reward_type="dense" if dense else "sparse", seed=3, groups=[CC.easy(), CC.hard()])
-    if track:
-        kw.update(auto_reset=True, respawn=True, loop_max_steps=25, track_episodes=True)
+    if track:       # "counts": auto-reset + counters without the per-env return / history arrays
+        kw.update(auto_reset=True, respawn=True, loop_max_steps=25, track_episodes=track != "counts")
     envs = {}
     try:
         for impl in ("register", "tma"):
@@ -410,8 +411,23 @@ def test_tma_pipeline_equals_register_kernel(dx, n, track, dense):
         for name in ("_obs", "_op64", "_thr", "_damp", "_step_count", "_cmask", "_size", "_mass", "_friction", "_episode"):
             assert torch.equal(getattr(a, name), getattr(b, name)), name
         if track:
-            assert torch.equal(a._ep_stats, b._ep_stats) and torch.equal(a._ep_return, b._ep_return)
             assert torch.equal(a.counters, b.counters) and int(a.counters[:, 0].sum()) > 0
+        if track == "counts":
+            # same trajectories as full tracking: episodes / successes / lengths agree, labels and returns stay empty
+            full = dx.BatchedManipulationEnv(n, "cuda", **dict(kw, track_episodes=True))
+            full.reset(seed=3)
+            gen = torch.Generator(device="cuda").manual_seed(5)
+            for t in range(60):
+                full.step(torch.rand(n, 15, device="cuda", generator=gen) * 2.6 - 1.3)
+            from dexterous_rl_manipulation_b200._lib import (CNT_EPISODES, CNT_LABEL_METRICS, CNT_SUCCESSES,
+                                                             CNT_SUM_FINAL_CONTACTS, CNT_SUM_STEPS, CNT_SUM_STEPS_SQ)
+            cols = [CNT_EPISODES, CNT_SUCCESSES, CNT_SUM_STEPS, CNT_SUM_STEPS_SQ, CNT_SUM_FINAL_CONTACTS]
+            assert torch.equal(full.counters[:, cols], b.counters[:, cols])
+            assert torch.equal(full._obs, b._obs) and torch.equal(full._episode, b._episode)
+            assert int(b.counters[:, CNT_LABEL_METRICS:CNT_LABEL_METRICS + 13].sum()) == 0 and float(b.ret_sums.abs().sum()) == 0.0
+            assert int(full.counters[:, CNT_LABEL_METRICS:CNT_LABEL_METRICS + 13].sum()) > 0
+        elif track:
+            assert torch.equal(a._ep_stats, b._ep_stats) and torch.equal(a._ep_return, b._ep_return)
             torch.testing.assert_close(a.ret_sums, b.ret_sums, rtol=1e-9, atol=0)
     finally:
         _lib.set_step_impl("auto")

@@ -2,8 +2,8 @@
 
     python tools/profile_step.py [num_envs] [variant]
 
-variant: api (step kernel, plain), api_track (step kernel with auto-reset + tracking, the bench
-path), fused (rollout kernel).  8 warm-up launches, then 6 profiled-range launches.
+variant: api (step kernel, plain), api_counts (auto-reset + counters, the bench path), api_track (auto-reset +
+full episode tracking), fused (rollout kernel).  8 warm-up launches, then 6 profiled-range launches.
 """
 import os
 import sys
@@ -20,8 +20,9 @@ CC = dx.CurriculumConfig
 kw = dict(max_episode_steps=200, reward_type="dense", curriculum_config=CC.hard(), seed=42)
 if variant == "api":
     env = dx.BatchedManipulationEnv(n, "cuda", **kw)
-elif variant == "api_track":
-    env = dx.BatchedManipulationEnv(n, "cuda", auto_reset=True, respawn=True, loop_max_steps=200, track_episodes=True, **kw)
+elif variant in ("api_track", "api_counts"):
+    env = dx.BatchedManipulationEnv(n, "cuda", auto_reset=True, respawn=True, loop_max_steps=200,
+                                    track_episodes=variant == "api_track", **kw)
 else:
     env = dx.BatchedManipulationEnv(n, "cuda", track_episodes=True, **kw)
 env.reset(seed=42)

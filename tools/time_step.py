@@ -9,10 +9,10 @@ import dexterous_rl_manipulation_b200 as dx  # noqa: E402
 
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 1 << 20
 CC = dx.CurriculumConfig
-for variant in ("api", "api_track"):
+for variant in ("api", "api_counts", "api_track"):
     kw = dict(max_episode_steps=200, reward_type="dense", curriculum_config=CC.hard(), seed=42)
-    if variant == "api_track":
-        kw.update(auto_reset=True, respawn=True, loop_max_steps=200, track_episodes=True)
+    if variant != "api":
+        kw.update(auto_reset=True, respawn=True, loop_max_steps=200, track_episodes=variant == "api_track")
     env = dx.BatchedManipulationEnv(n, "cuda", **kw)
     env.reset(seed=42)
     g = torch.Generator(device="cuda").manual_seed(0)
