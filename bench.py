@@ -51,6 +51,7 @@ def parse_args():
     ap.add_argument("--poll-every", type=int, default=100, help="curriculum driver poll period (steps)")
     ap.add_argument("--e2e-steps", type=int, default=30)
     ap.add_argument("--no-sweep", action="store_true")
+    ap.add_argument("--no-tracking-variant", action="store_true", help="skip the extra run with full per-env episode tracking")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="target CPU time of the cpu_baseline sample")
     ap.add_argument("--ref-steps-per-proc", type=int, default=0,
@@ -283,10 +284,13 @@ def run_b200(args):
     E = args.num_envs
     CC = dx.CurriculumConfig
 
-    def make_env(n, seed=SEED, gid0=0):
+    def make_env(n, seed=SEED, gid0=0, track=False):
+        # track=False: auto-reset + per-group episode counters (episodes, successes, lengths) -- everything the
+        # CurriculumScheduler consumes; track=True adds the per-env return / contact-history arrays that the
+        # evaluation outputs (failure labels, return statistics) need
         env = dx.BatchedManipulationEnv(n, dev, max_episode_steps=MAX_EPISODE_STEPS, reward_type="dense",
                                         curriculum_config=CC.easy(), auto_reset=True, respawn=True,
-                                        loop_max_steps=MAX_EPISODE_STEPS, track_episodes=True, seed=seed, env_gid0=gid0)
+                                        loop_max_steps=MAX_EPISODE_STEPS, track_episodes=track, seed=seed, env_gid0=gid0)
         sched = dx.CurriculumScheduler(CC.easy(), CC.hard(), **SCHED)
         drv = dx.BatchedCurriculumDriver(env, sched)
         env.reset(seed=seed)
@@ -356,11 +360,23 @@ def run_b200(args):
             traffic = tr["dram_bytes_per_launch"]
     except (OSError, ValueError, KeyError):
         pass
-    roofline = {"bound": "hbm", "kernel": "dexsim::step_tma_kernel<dense, AoS action, track, 2 stages>", "achieved": achieved,
+    roofline = {"bound": "hbm", "kernel": "dexsim::step_tma_kernel<dense, AoS action, auto-reset + counters, 2 stages>", "achieved": achieved,
                 "peak": peak, "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if peaks else "fallback 6650 GB/s",
                 "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                 "algorithmic_bytes_per_env_step": ALGO_BYTES_PER_ENV_STEP, "envs_per_launch": E,
                 "kernel_ms": k_ms, "how": "timed-region average per launch (includes auto-reset waves and 1 curriculum poll per 100 steps)"}
+
+    # ---- the same loop with full per-env episode tracking (returns + history summaries -> failure labels) ----
+    tracking_full = None
+    if not args.no_tracking_variant:
+        env_t, _, drv_t = make_env(E, gid0=rank * E, track=True)
+        t_steps = max(50, args.steps // 4)
+        ms_t = timed_api(env_t, drv_t, pool, t_steps, max(args.warmup, 3), args.poll_every)
+        tracking_full = {"value": E * n_gpus * t_steps / (ms_t * 1e-3), "ms_per_step": ms_t / t_steps, "steps": t_steps,
+                         "roofline_frac": ALGO_BYTES_PER_ENV_STEP * E / (ms_t / t_steps * 1e-3) / 1e9 / peak,
+                         "note": "track_episodes=True: +32 B/env-step of per-env return / history traffic that the "
+                                 "410 B algorithmic figure does not count"}
+        del env_t, drv_t
 
     # ---- end to end: pinned host actions in, obs / reward / flags out ------------------------------
     h_pool = [torch.rand(E, 15).mul_(2).sub_(1).pin_memory() for _ in range(2)]
@@ -438,7 +454,8 @@ def run_b200(args):
             "dtype": "f32+f64", "data": "synthetic",
             "config": {
                 "workload": f"config_default.json dense + curriculum_scheduler(easy->hard), random_policy actions resident in HBM, "
-                            f"{E} envs per GPU, auto-reset respawn, max_episode_steps 200",
+                            f"{E} envs per GPU, auto-reset respawn with per-group episode counters feeding the scheduler, "
+                            f"max_episode_steps 200",
                 "envs_per_gpu": E, "envs_total": E * n_gpus, "l2": "state + actions per step exceed the 126 MB L2 (no flush needed)"
                 if E * ALGO_BYTES_PER_ENV_STEP > 130e6 else "state fits in L2 at this size",
                 "curriculum": {"difficulty": sched.current_difficulty_level, "progressions": drv.progressions,
@@ -447,7 +464,7 @@ def run_b200(args):
             },
             "e2e": e2e, "gpu_launches": launches, "gpu_launches_note": "step_tma_kernel launches inside the main timed region (one per step)",
             "roofline": roofline, "cpu_baseline": cpu_base,
-            "fused_rollout": fused, "sweep": sweep, "clocks": clocks,
+            "tracking_full": tracking_full, "fused_rollout": fused, "sweep": sweep, "clocks": clocks,
             "episodes": int(env.counters[:, 0].sum().item()),
         }
         os.write(json_fd, (json.dumps(line) + "\n").encode())
