@@ -430,6 +430,20 @@ def run_b200(args):
             pool_s = action_pool(n)
             s_ms = timed_api(env_s, drv_s, pool_s, 300, 120, 100)
             v = n * 300 / (s_ms * 1e-3)
+            # the same API step replayed from a CUDA graph (8 steps per replay): removes the host launch path
+            buf = torch.stack(pool_s + pool_s)
+            replay = env_s.capture_step(buf, steps=8)
+            for _ in range(10):
+                replay()
+            torch.cuda.synchronize(dev)
+            g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            g0.record()
+            for _ in range(40):
+                replay()
+            g1.record()
+            torch.cuda.synchronize(dev)
+            gv = n * 320 / (g0.elapsed_time(g1) * 1e-3)
+            del replay, buf
             env_f = dx.BatchedManipulationEnv(n, dev, max_episode_steps=MAX_EPISODE_STEPS, reward_type="dense",
                                               curriculum_config=CC.hard(), track_episodes=True, seed=SEED)
             env_f.reset(seed=SEED)
@@ -443,7 +457,8 @@ def run_b200(args):
             torch.cuda.synchronize(dev)
             fv = n * 400 / (f0.elapsed_time(f1) * 1e-3)
             sweep.append({"envs": n, "value": v, "ms_per_step": s_ms / 300,
-                          "roofline_frac": v * ALGO_BYTES_PER_ENV_STEP / 1e9 / peak, "fused_rollout_value": fv,
+                          "roofline_frac": v * ALGO_BYTES_PER_ENV_STEP / 1e9 / peak, "graph_replay_value": gv,
+                          "fused_rollout_value": fv,
                           "note": "API mode is bound by the ~8.5 us host launch path at this size (state is L2-resident)"})
             del env_s, pool_s, env_f
 
