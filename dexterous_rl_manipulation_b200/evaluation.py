@@ -15,7 +15,7 @@ Reset draws follow the reference exactly (``rng="numpy"``: env (object o, episod
 policy randomness is Philox, because the reference's policies draw from process-global NumPy state
 that has no batched equivalent.
 """
-from typing import Dict, List, Optional, Sequence
+from typing import Tuple, Dict, List, Optional, Sequence
 
 import numpy as np
 import torch
@@ -84,36 +84,74 @@ def _episode_dict(rec, counts, size, mass, friction):
     return d
 
 
+def _heldout_shard(heldout_set, policy, n_eps, seeds, reward_type, max_episode_steps, device, policy_seed,
+                   contact_history, actions, lo, hi):
+    """Envs [lo, hi) of the (object, episode) batch -> {global env index: (record, per-step counts)}.
+    Reset seeds, groups and Philox keys depend on the GLOBAL env index only, so any partition of the batch
+    (one shard per GPU) produces the records of the unpartitioned run."""
+    objs = heldout_set.heldout_objects
+    n_obj = len(objs)
+    cfgs = [heldout_set.get_eval_config(k) for k in range(n_obj)]
+    m = hi - lo
+    pad = max(m, 2) - m
+    group_of_env = np.concatenate([np.arange(lo, hi) // n_eps, np.zeros(pad, np.int64)])
+    env = BatchedManipulationEnv(m + pad, device, max_episode_steps=max_episode_steps, reward_type=reward_type,
+                                 track_episodes=True, rng="numpy", groups=cfgs, seed=policy_seed, env_gid0=lo,
+                                 group_of_env=group_of_env)
+    env_seeds = [seeds[i % n_eps] for i in range(lo, hi)] + [0] * pad
+    env.reset(seed=env_seeds)
+    kw = {}
+    if policy == "external":
+        a = torch.as_tensor(actions, dtype=torch.float32).reshape(max_episode_steps, -1, 15)[:, lo:hi]
+        if pad:
+            a = torch.cat([a, torch.zeros(max_episode_steps, pad, 15)], 1)
+        kw["actions"] = a
+    # exactly the caller loop bound: at most max_episode_steps steps per episode (evaluator.py:135)
+    recs = _run_one_episode_each(env, max_episode_steps, policy, True, max_episode_steps, contact_history, kw)
+    return {lo + i: (recs[i][0].copy(), None if recs[i][1] is None else recs[i][1].copy()) for i in range(m)}
+
+
 def evaluate_heldout_set_batched(heldout_set, policy: str = "heuristic", num_episodes_per_object: int = 5,
                                  seed: Optional[int] = None, reward_type: str = "dense", max_episode_steps: int = 200,
                                  device="cuda", policy_seed: int = 0, contact_history: bool = True,
-                                 actions=None) -> Dict:
+                                 actions=None, shard: Optional[Tuple[int, int]] = None) -> Dict:
     """All (object, episode) pairs of Evaluator.evaluate_heldout_set as ONE batch.
 
     ``policy``: "heuristic" | "random" (fused, Philox) or "external" with ``actions`` of shape
-    [max_episode_steps, n_objects * n_episodes, 15] (env index = object * n_episodes + episode)."""
+    [max_episode_steps, n_objects * n_episodes, 15] (env index = object * n_episodes + episode).
+
+    Multi-GPU: with ``torch.distributed`` initialised (or an explicit ``shard=(rank, world_size)``) every rank
+    runs a contiguous slice of the batch on its own GPU and the per-episode records are all-gathered, so every
+    rank returns the complete result -- identical to the single-GPU one.  Pass a ``seed`` in that case (an
+    unseeded run draws different episode seeds on every rank)."""
+    import torch.distributed as dist
+    from .distributed import shard_range
     objs = heldout_set.heldout_objects
     n_obj, n_eps = len(objs), int(num_episodes_per_object)
-    cfgs = [heldout_set.get_eval_config(k) for k in range(n_obj)]
     n = n_obj * n_eps
-    group_of_env = np.repeat(np.arange(n_obj), n_eps)
-    env = BatchedManipulationEnv(max(n, 2), device, max_episode_steps=max_episode_steps, reward_type=reward_type,
-                                 track_episodes=True, rng="numpy", groups=cfgs, seed=policy_seed,
-                                 group_of_env=np.concatenate([group_of_env, np.zeros(max(n, 2) - n, np.int64)]))
     if seed is None:
         seeds = [int(s) for s in np.random.default_rng(None).integers(0, 2 ** 31, n_eps)]   # evaluator.py:222
     else:
         seeds = [int(seed) + e for e in range(n_eps)]
-    env_seeds = [seeds[i % n_eps] for i in range(n)] + [0] * (env.num_envs - n)
-    env.reset(seed=env_seeds)
-    kw = {}
-    if policy == "external":
-        a = torch.as_tensor(actions, dtype=torch.float32).reshape(max_episode_steps, n, 15)
-        if env.num_envs > n:
-            a = torch.cat([a, a[:, :env.num_envs - n]], 1)
-        kw["actions"] = a
-    # exactly the caller loop bound: at most max_episode_steps steps per episode (evaluator.py:135)
-    recs = _run_one_episode_each(env, max_episode_steps, policy, True, max_episode_steps, contact_history, kw)
+    distributed = shard is None and dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+    rank, world = shard if shard is not None else ((dist.get_rank(), dist.get_world_size()) if distributed else (0, 1))
+    lo, hi = shard_range(n, rank, world)
+    recs = _heldout_shard(heldout_set, policy, n_eps, seeds, reward_type, max_episode_steps, device, policy_seed,
+                          contact_history, actions, lo, hi)
+    if distributed:
+        parts = [None] * world
+        dist.all_gather_object(parts, recs)
+        recs = {k: v for part in parts for k, v in part.items()}
+    elif shard is not None and world > 1:
+        return {"shard_records": recs, "range": (lo, hi)}          # caller merges (tests, custom launchers)
+    return _heldout_result(heldout_set, recs, n_eps, seeds, policy, policy_seed, reward_type, max_episode_steps)
+
+
+def _heldout_result(heldout_set, recs, n_eps, seeds, policy, policy_seed, reward_type, max_episode_steps) -> Dict:
+    """Result dictionary of Evaluator.evaluate_heldout_set (evaluation/evaluator.py:191-271) from episode records."""
+    objs = heldout_set.heldout_objects
+    n_obj = len(objs)
+    env_seeds = [seeds[i % n_eps] for i in range(n_obj * n_eps)]
     size, mass, fric = ([o.size for o in objs], [o.mass for o in objs], [o.friction for o in objs])
     all_results, object_results = [], {}
     for o in range(n_obj):

@@ -154,6 +154,37 @@ def config5_learner_seeds(runs_per_cell=4096, episodes=20,
          env_steps_per_sec=total_steps / float(sec.item()), timing="wall clock incl. per-episode log read-back", **summary)
 
 
+class _HeldOut:
+    """Duck type of evaluation/heldout_objects.py::HeldOutObjectSet (the reference's class works the same way)."""
+
+    class _Obj:
+        def __init__(self, size, mass, friction):
+            self.size, self.mass, self.friction = size, mass, friction
+
+    def __init__(self, n=20, seed=123):
+        rng = np.random.default_rng(seed)
+        self.heldout_objects = [self._Obj(float(rng.uniform(0.08, 0.12)), float(rng.uniform(0.16, 0.26)),
+                                          float(rng.uniform(0.0, 0.29))) for _ in range(n)]
+
+    def get_eval_config(self, k):
+        o = self.heldout_objects[k]
+        return CC(object_size=o.size, object_mass=o.mass, friction_coefficient=o.friction)
+
+
+def frontend_heldout(episodes_per_object=500):
+    """Evaluator.evaluate_heldout_set's result dictionary from the batched front-end; with several ranks every rank
+    evaluates a slice of the (object, episode) batch and the per-episode records are all-gathered."""
+    t0 = time.perf_counter()
+    res = dx.evaluation.evaluate_heldout_set_batched(_HeldOut(), policy="heuristic", seed=42,
+                                                     num_episodes_per_object=episodes_per_object, contact_history=False)
+    sec = time.perf_counter() - t0
+    m = res["metrics"]
+    emit("front-end: evaluate_heldout_set_batched, 20 objects x %d episodes" % episodes_per_object,
+         episodes=res["overall_stats"]["total_episodes"], success_rate=m["grasp_success_rate"],
+         mean_episode_length=m["mean_episode_length"], mean_reward=res["overall_stats"]["mean_reward"],
+         failure_types={k: v["count"] for k, v in m["failure_type_frequency"].items()}, wall_seconds=round(sec, 3))
+
+
 def main():
     torch.cuda.set_device(LOCAL)
     if WORLD > 1:
@@ -167,6 +198,8 @@ def main():
         config4_variable()
     if "5" in which:
         config5_learner_seeds()
+    if "frontend" in which:
+        frontend_heldout()
     if WORLD > 1:
         torch.distributed.destroy_process_group()
 

@@ -605,6 +605,15 @@ def test_batched_evaluator_front_end_matches_reference(dx):
         assert again["failure_type_frequency"] == got["metrics"]["failure_type_frequency"]
         assert again["grasp_success_rate"] == got["metrics"]["grasp_success_rate"]
         assert isinstance(R.metrics.format_metrics_report(got["metrics"]), str)
+        # one shard per GPU: three slices of the batch merged give the same records as the single batch
+        from dexterous_rl_manipulation_b200.evaluation import _heldout_result
+        merged = {}
+        for r in range(3):
+            part = dx.evaluation.evaluate_heldout_set_batched(held, policy="external", actions=actions, num_episodes_per_object=n_eps,
+                                                              seed=42, reward_type=reward_type, max_episode_steps=T, shard=(r, 3))
+            merged.update(part["shard_records"])
+        again3 = _heldout_result(held, merged, n_eps, [42 + e for e in range(n_eps)], "external", 0, reward_type, T)
+        assert again3["all_episodes"] == got["all_episodes"] and again3["metrics"] == got["metrics"]
 
 
 def test_batched_robustness_front_end_matches_reference(dx):
