@@ -224,6 +224,31 @@ def test_step_autoreset_equals_fused_rollout(dx):
     torch.testing.assert_close(a.ret_sums, b.ret_sums, rtol=1e-9, atol=0)
 
 
+def test_noisy_step_equals_noisy_fused_rollout(dx):
+    """Dynamics-noise cells (per-group sigma): API stepping with in-kernel noise == the fused rollout kernel's noise --
+    two independent code paths drawing from the same Philox stream keyed by (env, episode, step)."""
+    from dexterous_rl_manipulation_b200 import _lib
+    import ctypes as C
+    CC = dx.CurriculumConfig
+    n, K, seed = 1536, 70, 21
+    kw = dict(max_episode_steps=30, reward_type="dense", track_episodes=True, groups=[CC.easy(), CC.medium(), CC.hard()],
+              group_sigma_dyn=[0.0, 0.05, 0.2], seed=seed)
+    a = dx.BatchedManipulationEnv(n, "cuda", auto_reset=True, respawn=True, loop_max_steps=30, **kw)
+    b = dx.BatchedManipulationEnv(n, "cuda", **kw)
+    a.reset(seed=seed); b.reset(seed=seed)
+    act = torch.zeros(15, a.ld, device="cuda")
+    for t in range(K):
+        _lib.check(a._lib.dexsim_fill_policy_actions(C.byref(a._state), C.byref(a._params), 1, act.data_ptr(), a._stream()), "fill")
+        a.step(act[:, :n].t().contiguous())
+    b.rollout(K, policy="random", respawn=True, loop_max_steps=30)
+    assert torch.equal(a.counters, b.counters) and int(a.counters[:, 0].sum()) > n
+    assert torch.equal(a._obs, b._obs) and torch.equal(a._op64, b._op64) and torch.equal(a._episode, b._episode)
+    quiet = dx.BatchedManipulationEnv(n, "cuda", **dict(kw, group_sigma_dyn=0.0))
+    quiet.reset(seed=seed); quiet.rollout(K, policy="random", respawn=True, loop_max_steps=30)
+    assert torch.equal(quiet._obs[:, 0::3], b._obs[:, 0::3])           # group 0 (sigma 0) is untouched by the others' noise
+    assert not torch.equal(quiet._obs[:, 2::3], b._obs[:, 2::3])
+
+
 def test_sharding_is_gpu_count_independent(dx):
     """Two half shards keyed by global env id reproduce one full shard."""
     CC = dx.CurriculumConfig
