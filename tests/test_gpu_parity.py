@@ -508,6 +508,44 @@ def test_group_noise_cells_in_step(dx):
     assert not torch.equal(cells._obs[:, 1:n:2], only_obs._obs[:, 1:n:2])       # dynamics noise did change trajectories
 
 
+def test_c_abi_demo_matches_python_face(dx, tmp_path):
+    """examples/c_abi_demo.c drives libdexsim_b200.so from plain C (cudaMalloc buffers, no Python, no torch);
+    its counters and observation checksum equal the Python face's on the same configuration."""
+    import json
+    import shutil
+    import subprocess
+    from dexterous_rl_manipulation_b200 import _lib
+    import ctypes as C
+    if not shutil.which("gcc"):
+        pytest.skip("gcc not available")
+    root = os.path.abspath(os.path.join(os.path.dirname(__file__), ".."))
+    cuda = os.environ.get("CUDA_HOME", "/usr/local/cuda")
+    exe = str(tmp_path / "c_abi_demo")
+    libdir = os.path.join(root, "dexterous_rl_manipulation_b200")
+    subprocess.run(["gcc", "-O2", "-std=c99", "-Wall", "-Werror", f"-I{root}/include", f"-I{cuda}/include",
+                    os.path.join(root, "examples", "c_abi_demo.c"), "-o", exe, f"-L{libdir}", "-ldexsim_b200",
+                    f"-L{cuda}/lib64", "-lcudart", f"-Wl,-rpath,{libdir}", f"-Wl,-rpath,{cuda}/lib64"], check=True)
+    n, steps, seed = 5000, 120, 7
+    out = json.loads(subprocess.run([exe, str(n), str(steps), str(seed)], check=True, capture_output=True, text=True,
+                                    timeout=120).stdout)
+    env = dx.BatchedManipulationEnv(n, "cuda", reward_type="dense", max_episode_steps=50, curriculum_config=dx.CurriculumConfig.hard(),
+                                    auto_reset=True, respawn=True, loop_max_steps=50, track_episodes=False, seed=seed)
+    env.reset(seed=seed)
+    act = torch.zeros(15, env.ld, device="cuda")
+    for _ in range(steps):
+        _lib.check(env._lib.dexsim_fill_policy_actions(C.byref(env._state), C.byref(env._params), _lib.POLICY_RANDOM,
+                                                       act.data_ptr(), env._stream()), "fill")
+        env._step_soa(act)
+    c = env.counters.cpu().numpy()[0]
+    assert (out["episodes"], out["successes"], out["sum_steps"]) == (int(c[0]), int(c[1]), int(c[2])) and out["episodes"] >= n
+    bits = env._obs[:, :n].t().contiguous().cpu().numpy().view(np.uint32).reshape(-1).copy()
+    bits[bits == 0x80000000] = 0
+    h = 1469598103934665603
+    for byte in bits.view(np.uint8).tolist():                # little-endian bytes, env-major: the demo's order
+        h = ((h ^ byte) * 1099511628211) & 0xFFFFFFFFFFFFFFFF
+    assert out["obs_fnv1a"] == f"{h:016x}"
+
+
 def test_maximum_size_batch(dx):
     """33.5 M envs in one batch (~11 GB of state, 7.7e9 bytes of observations, a ragged last tile): both step kernels
     agree on every array, and the LAST 1,000 envs equal a 1,000-env batch created with env_gid0 = n - 1000 --
