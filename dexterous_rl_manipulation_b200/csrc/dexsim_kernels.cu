@@ -428,8 +428,11 @@ reset_philox_kernel(const DexsimState st, const DexsimParams p, const DexsimGrou
 }
 
 // ---- fused rollout ------------------------------------------------------------------------------------
+#ifndef DEXSIM_ROLLOUT_MIN_BLOCKS
+#define DEXSIM_ROLLOUT_MIN_BLOCKS 2
+#endif
 template <bool DENSE, bool LEARNER>
-__global__ void __launch_bounds__(STEP_THREADS, 2)
+__global__ void __launch_bounds__(STEP_THREADS, DEXSIM_ROLLOUT_MIN_BLOCKS)
 rollout_kernel(const DexsimState st, const DexsimParams p, const DexsimGroup* __restrict__ groups,
                const uint16_t* __restrict__ group_of_env, const int k_steps, const int policy_kind,
                const DexsimRolloutIO rio) {
