@@ -21,8 +21,12 @@
 // included by dexsim_kernels.cu after finish_and_reset() is defined
 namespace dexsim {
 
-constexpr int TILE = 128;
-constexpr int TMA_COMPUTE_THREADS = 128;           // one compute group = 4 warps = one tile at a time
+#ifndef DEXSIM_TMA_TILE
+#define DEXSIM_TMA_TILE 128
+#endif
+constexpr int TILE = DEXSIM_TMA_TILE;              // envs per tile: 128, or 96 (24.7 KB stages, four CTAs per SM)
+static_assert(TILE % 32 == 0 && TILE <= 256, "a tile is a whole number of warps and one TMA box wide");
+constexpr int TMA_COMPUTE_THREADS = TILE;          // one compute group = one thread per env of a tile
 __host__ __device__ constexpr int tma_threads(int groups) { return groups * TMA_COMPUTE_THREADS + 32; }
 constexpr int TMA_GROUPS_MAX = 16;     // per-CTA counter staging (keeps 3 CTAs per SM with 2 stages)
 
@@ -43,8 +47,11 @@ constexpr int OFF_EPRET = OFF_NC + TILE;            // [128] f64, in/out (tracki
 constexpr int OFF_EPST0 = OFF_EPRET + TILE * 8;     // [128] u32, in/out (tracking)
 constexpr int OFF_EPST1 = OFF_EPST0 + TILE * 4;     // [128] u32, in/out (tracking)
 constexpr int OFF_FIN = OFF_EPST1 + TILE * 4;       // [128] u8, out (auto-reset)
-constexpr int STAGE_BYTES = OFF_FIN + TILE;
-static_assert(STAGE_BYTES % 128 == 0, "stage size must keep every stage 128-byte aligned");
+constexpr int STAGE_BYTES = (OFF_FIN + TILE + 127) / 128 * 128;      // every stage starts 128-byte aligned
+static_assert(OFF_OV % 128 == 0 && OFF_OP64 % 128 == 0 && OFF_ACT % 128 == 0, "tensor-map box destinations");
+static_assert(OFF_THR % 16 == 0 && OFF_DAMP % 16 == 0 && OFF_SC % 16 == 0 && OFF_REWARD % 16 == 0 && OFF_CMASK % 16 == 0 &&
+              OFF_TERM % 16 == 0 && OFF_TRUNC % 16 == 0 && OFF_NC % 16 == 0 && OFF_EPRET % 16 == 0 && OFF_EPST0 % 16 == 0 &&
+              OFF_EPST1 % 16 == 0 && OFF_FIN % 16 == 0, "1-D bulk copy destinations");
 
 struct StepMaps {             // tensor maps live in kernel parameter space (__grid_constant__)
     CUtensorMap obs_jpjv;     // obs [45, ld] f32, box {128, 30}
@@ -118,7 +125,7 @@ __device__ __forceinline__ uint32_t full_parity(int k) {
 // GROUPS: compute groups per CTA.  With 2 groups (8 compute warps, 3 stages, 2 CTAs per SM) group g works on the
 // CTA's tiles k = g, g + 2, ... so that two tiles are in their compute phase while a third one loads.
 template <bool DENSE, bool AOS, int TRACK, int STAGES, int GROUPS>
-__global__ void __launch_bounds__(tma_threads(GROUPS), (GROUPS == 2) ? 2 : ((STAGES == 2) ? 3 : 2))
+__global__ void __launch_bounds__(tma_threads(GROUPS), (GROUPS == 2) ? 2 : ((STAGES == 2) ? (TILE <= 96 ? 4 : 3) : 2))
 step_tma_kernel(const DexsimState st, const DexsimParams p, const DexsimGroup* __restrict__ groups,
                 const uint16_t* __restrict__ group_of_env, const DexsimStepIO io,
                 const __grid_constant__ StepMaps maps, const int num_tiles) {
@@ -215,7 +222,7 @@ step_tma_kernel(const DexsimState st, const DexsimParams p, const DexsimGroup* _
         }
     } else {
         // ===== compute warps: lane == column of the tile =====
-        const int col = tid & (TMA_COMPUTE_THREADS - 1);
+        const int col = tid % TMA_COMPUTE_THREADS;
         for (int k = tid / TMA_COMPUTE_THREADS; k < my_tiles; k += GROUPS) {
             const int s = k % STAGES;
             unsigned char* sp = stage_base + (size_t)s * STAGE_BYTES;
