@@ -1,0 +1,79 @@
+"""Randomised differential test, CUDA fused rollout vs the oracle's rollout (experiments / soak; the fixed-seed
+versions of these checks live in tests/test_gpu_parity.py).  Runs random configurations until the time budget is
+spent and stops at the first mismatch.
+
+    python tools/fuzz_parity.py [seconds] [first_seed]
+"""
+import os
+import sys
+import time
+
+import numpy as np
+import torch
+
+sys.path.insert(0, os.path.abspath(os.path.join(os.path.dirname(__file__), "..")))
+import dexterous_rl_manipulation_b200 as dx  # noqa: E402
+from oracle import oracle  # noqa: E402
+
+budget = float(sys.argv[1]) if len(sys.argv) > 1 else 60.0
+case = int(sys.argv[2]) if len(sys.argv) > 2 else 0
+CC = dx.CurriculumConfig
+t_end = time.time() + budget
+done = episodes = 0
+while time.time() < t_end:
+    rng = np.random.default_rng(case)
+    n = int(rng.choice([1, 31, 32, 129, 777, 4096, 6000, 20011]))
+    dense = bool(rng.integers(2))
+    respawn = bool(rng.integers(2))
+    policy = ["random", "heuristic"][int(rng.integers(2))]
+    max_steps = int(rng.choice([1, 2, 7, 40, 200]))
+    loop_max = int(rng.choice([2 * max_steps, max_steps, max(1, max_steps // 2)]))   # the oracle's loops always have a bound
+    K = int(rng.integers(1, 260))
+    gid0 = int(rng.choice([0, 5, 2 ** 31 - 50_000, 2 ** 32 - 30_000]))
+    seed = int(rng.integers(0, 2 ** 63))
+    n_groups = int(rng.integers(1, 5))
+    cfgs = []
+    for _ in range(n_groups):
+        kw = dict(object_size=float(rng.uniform(0.01, 0.3)), object_mass=float(rng.uniform(0.01, 2.0)),
+                  friction_coefficient=float(rng.uniform(0.0, 1.5)))
+        if rng.integers(2):
+            lo = float(rng.uniform(0.01, 0.1)); kw["object_size_range"] = (lo, lo + float(rng.uniform(0, 0.2)))
+        if rng.integers(2):
+            lo = float(rng.uniform(0.01, 0.5)); kw["object_mass_range"] = (lo, lo + float(rng.uniform(0, 1.0)))
+        if rng.integers(2):
+            lo = float(rng.uniform(0.0, 0.5)); kw["friction_range"] = (lo, lo + float(rng.uniform(0, 1.0)))
+        if rng.integers(2):
+            kw["spawn_z_range"] = (0.0, float(rng.uniform(0.0, 0.3)))
+        cfgs.append(CC(**kw))
+    n_env = max(n, 2)
+    env = dx.BatchedManipulationEnv(n_env, "cuda", max_episode_steps=max_steps, reward_type="dense" if dense else "sparse",
+                                    track_episodes=True, groups=cfgs, seed=seed, env_gid0=gid0)
+    env.reset(seed=seed)
+    ob = oracle.OracleBatch(n_env, dense=dense, max_episode_steps=max_steps)
+    groups = np.concatenate([oracle.make_group(c) for c in cfgs])
+    gidx = [((gid0 + i) & 0xFFFFFFFF) % n_groups for i in range(n_env)]
+    draws = [oracle.reset_draws(seed, (gid0 + i) & 0xFFFFFFFF, 0, groups[gidx[i]:gidx[i] + 1]) for i in range(n_env)]
+    ob.reset_predrawn(np.stack([d[0] for d in draws]), np.array([d[1] for d in draws]), np.array([d[2] for d in draws]),
+                      np.array([d[3] for d in draws]), np.stack([d[4] for d in draws]))
+    desc = dict(case=case, n=n_env, dense=dense, respawn=respawn, policy=policy, max_steps=max_steps, loop_max=loop_max, K=K,
+                gid0=gid0, groups=n_groups)
+    assert np.array_equal(env._obs[:, :n_env].t().cpu().numpy(), ob.observation()), ("reset", desc)
+    env.rollout(K, policy=policy, respawn=respawn, loop_max_steps=loop_max)
+    cnt_o, rs_o = ob.rollout(groups, K, seed, policy_kind=1 if policy == "random" else 2, respawn=respawn, env_gid0=gid0,
+                             loop_max_steps=loop_max)
+    cnt = env.counters.cpu().numpy()
+    ok = (np.array_equal(cnt[:, :16], cnt_o[:, :16]) and np.array_equal(cnt[:, 17], cnt_o[:, 17])
+          and np.array_equal(env._obs[:, :n_env].t().cpu().numpy(), ob.observation(), equal_nan=True)
+          and np.array_equal(env._op64[:, :n_env].t().cpu().numpy(), ob.env["op"])
+          and np.array_equal(env._step_count[:n_env].cpu().numpy(), ob.env["step_count"])
+          and np.array_equal(env._episode[:n_env].cpu().numpy().astype(np.uint32), ob.env["episode"])
+          and np.allclose(env._ep_return[:n_env].cpu().numpy(), ob.env["ep_return"], rtol=1e-12, atol=1e-12)
+          and np.allclose(env.ret_sums.cpu().numpy(), rs_o, rtol=1e-9))
+    if not ok:
+        print("MISMATCH", desc, flush=True)
+        sys.exit(1)
+    done += 1
+    episodes += int(cnt[:, 0].sum())
+    case += 1
+    del env
+print(f"fuzz ok: {done} random configurations, {episodes} finished episodes compared, next seed {case}")
