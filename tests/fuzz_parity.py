@@ -2,7 +2,7 @@
 versions of these checks live in tests/test_gpu_parity.py).  Runs random configurations until the time budget is
 spent and stops at the first mismatch.
 
-    python tools/fuzz_parity.py [seconds] [first_seed]
+    python tests/fuzz_parity.py [seconds] [first_seed]
 """
 import os
 import sys
