@@ -20,7 +20,54 @@ case = int(sys.argv[2]) if len(sys.argv) > 2 else 0
 CC = dx.CurriculumConfig
 t_end = time.time() + budget
 done = episodes = 0
+def fuzz_api_steps(case):
+    """dexsim_step (TMA pipeline or register kernel, AoS actions) vs the oracle's step on hostile actions."""
+    rng = np.random.default_rng(10_000_000 + case)
+    n = int(rng.choice([2, 33, 128, 129, 1000, 4096, 9999]))
+    dense = bool(rng.integers(2))
+    comps = bool(rng.integers(2))                       # False keeps n >= 128 on the TMA pipeline
+    max_steps = int(rng.choice([1, 5, 60, 200]))
+    T = int(rng.integers(1, 120))
+    w = tuple(float(x) for x in rng.uniform(0.0, 3.0, 4)) if dense and rng.integers(2) else None
+    jp0 = rng.uniform(-1.0, 1.0, (n, 15)).astype(np.float32) if rng.integers(2) else rng.uniform(-0.1, 0.1, (n, 15)).astype(np.float32)
+    size, mass, fric = rng.uniform(0.005, 0.4, n), rng.uniform(0.01, 3.0, n), rng.uniform(0.0, 2.0, n)
+    pos = np.stack([rng.uniform(-0.3, 0.3, n), rng.uniform(-0.3, 0.3, n), rng.uniform(0.0, 0.4, n)], 1).astype(np.float32)
+    kw = {}
+    if w is not None:
+        class _W:            # duck type of rewards/reward_shaping.py::RewardShaping(weights)
+            distance_weight, contact_weight, closure_weight, stability_weight = w
+        kw["reward_shaping"] = _W()
+    env = dx.BatchedManipulationEnv(n, "cuda", max_episode_steps=max_steps, reward_type="dense" if dense else "sparse",
+                                    reward_components=comps, **kw)
+    ob = oracle.OracleBatch(n, dense=dense, max_episode_steps=max_steps, **({"weights": w} if w is not None else {}))
+    g0, _ = env.reset_from_draws(jp0, size, mass, fric, pos)
+    desc = dict(case=case, mode="api", n=n, dense=dense, comps=comps, max_steps=max_steps, T=T, weights=w)
+    assert np.array_equal(g0.cpu().numpy(), ob.reset_predrawn(jp0, size, mass, fric, pos)), ("reset", desc)
+    for t in range(T):
+        kind = int(rng.integers(5))
+        a = (rng.uniform(-1.5, 1.5, (n, 15)) if kind < 2 else rng.normal(0, [0.3, 3.0, 1e3][kind - 2], (n, 15))).astype(np.float32)
+        if rng.integers(4) == 0:
+            idx = rng.integers(0, n, 3), rng.integers(0, 15, 3)
+            a[idx] = [np.nan, np.inf, -np.inf]
+        oo, orr, oc, ote, otr, onc = ob.step(a)
+        obs, rew, te, tr, info = env.step(torch.from_numpy(a).cuda())
+        ok = (np.array_equal(obs.cpu().numpy(), oo, equal_nan=True) and np.array_equal(te.cpu().numpy(), ote)
+              and np.array_equal(tr.cpu().numpy(), otr) and np.array_equal(info["num_contacts"].cpu().numpy(), onc)
+              and np.allclose(rew.cpu().numpy(), orr, rtol=1e-6, atol=1e-7, equal_nan=True)
+              and np.array_equal(info["object_position"].cpu().numpy(), ob.env["op"], equal_nan=True))
+        if not ok:
+            print("MISMATCH", desc, "step", t, flush=True)
+            sys.exit(1)
+    return T * n
+
+
+api_steps = 0
 while time.time() < t_end:
+    if case % 2:
+        api_steps += fuzz_api_steps(case)
+        done += 1
+        case += 1
+        continue
     rng = np.random.default_rng(case)
     n = int(rng.choice([1, 31, 32, 129, 777, 4096, 6000, 20011]))
     dense = bool(rng.integers(2))
@@ -76,4 +123,4 @@ while time.time() < t_end:
     episodes += int(cnt[:, 0].sum())
     case += 1
     del env
-print(f"fuzz ok: {done} random configurations, {episodes} finished episodes compared, next seed {case}")
+print(f"fuzz ok: {done} random configurations, {episodes} finished episodes and {api_steps} API env-steps compared, next seed {case}")
