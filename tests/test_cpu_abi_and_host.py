@@ -6,6 +6,7 @@ No compute kernels are launched here."""
 import ctypes as C
 import os
 import re
+import sys
 
 import numpy as np
 import pytest
@@ -282,3 +283,26 @@ def test_public_header_is_plain_c(tmp_path):
                     "-o", str(exe), "-L", libdir, "-ldexsim_b200", "-Wl,-rpath," + libdir], check=True)
     out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split(None, 2)
     assert int(out[0]) == _lib.ABI_VERSION and int(out[1]) == -1001 and "NULL" in out[2]
+
+
+def test_bench_reference_arm_prints_one_contract_line():
+    """bench.py --impl reference runs on host cores only (no GPU): one JSON line on stdout with the contract's keys."""
+    import json
+    import subprocess
+    root = os.path.abspath(os.path.join(os.path.dirname(__file__), ".."))
+    proc = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "2", "--warmup", "1",
+                           "--ref-budget-seconds", "6", "--ref-procs", "2"], capture_output=True, text=True, timeout=300)
+    assert proc.returncode == 0, proc.stderr[-2000:]
+    lines = [ln for ln in proc.stdout.splitlines() if ln.strip()]
+    assert len(lines) == 1, lines
+    d = json.loads(lines[0])
+    if "unavailable" in d:                 # neither /root/reference nor the byte-compiled copy is present
+        assert d["impl"] == "reference"
+        return
+    for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+                "vs_baseline", "dtype", "data", "config", "e2e", "cpu_baseline", "impl"):
+        assert key in d, key
+    assert d["impl"] == "reference" and d["metric"] == "env_steps_per_sec" and d["unit"] == "env-steps/s"
+    assert d["steps"] == 2 and d["warmup"] == 1 and d["value"] > 0 and d["vs_baseline"] is None
+    assert d["cpu_baseline"]["kind"] in ("reference", "port") and d["cpu_baseline"]["cores"] == 2
+    assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0 and "workload" in d["config"]
