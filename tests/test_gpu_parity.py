@@ -1168,3 +1168,31 @@ def test_fuzz_extreme_inputs_match_oracle(dx):
                 fin = np.isfinite(orr)
                 assert np.array_equal(np.isnan(r), np.isnan(orr))
                 np.testing.assert_allclose(r[fin], orr[fin], rtol=REWARD_RTOL, atol=REWARD_ATOL)
+
+
+def test_bench_b200_arm_prints_one_contract_line():
+    """bench.py (a short run at a reduced env count): exactly one JSON line on stdout carrying every key of the
+    bench contract, the roofline and the end-to-end object."""
+    import json
+    import subprocess
+    import sys
+    root = os.path.abspath(os.path.join(os.path.dirname(__file__), ".."))
+    proc = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--steps", "20", "--warmup", "3", "--num-envs", "262144",
+                           "--e2e-steps", "3", "--no-sweep", "--no-cpu-baseline", "--no-tracking-variant"],
+                          capture_output=True, text=True, timeout=300)
+    assert proc.returncode == 0, proc.stderr[-2000:]
+    lines = [ln for ln in proc.stdout.splitlines() if ln.strip()]
+    assert len(lines) == 1, lines
+    d = json.loads(lines[0])
+    for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+                "vs_baseline", "dtype", "data", "config", "e2e", "gpu_launches", "roofline", "cpu_baseline", "clocks"):
+        assert key in d, key
+    assert d["metric"] == "env_steps_per_sec" and d["n_gpus"] == 1 and d["steps"] == 20 and d["warmup"] == 3
+    assert d["gpu_launches"] == 20 and d["scaling"] == "weak" and d["vs_baseline"] is None and d["data"] == "synthetic"
+    r = d["roofline"]
+    assert r["bound"] == "hbm" and r["unit"] == "GB/s" and 0.0 < r["frac"] < 1.0
+    assert abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9
+    assert abs(d["value"] - 262144 * 20 / (d["ms_per_step"] * 20e-3)) / d["value"] < 1e-6
+    e = d["e2e"]
+    assert e["value"] > 0 and e["h2d_bytes_per_step"] == 262144 * 60 and e["d2h_bytes_per_step"] > 262144 * 164
+    assert e["value"] < d["value"]                       # host buffers cross PCIe: never faster than the device-resident loop
