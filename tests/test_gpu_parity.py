@@ -1020,6 +1020,47 @@ def test_no_out_of_bounds_writes(dx, n):
     check()
 
 
+@pytest.mark.parametrize("n", [130, 4097, 70_001])
+def test_no_out_of_bounds_writes_counts_and_noise_paths(dx, n):
+    """Guard bands around every array for the counts-only auto-reset mode (both step kernels, chunked host path) and
+    for the in-kernel noise path (noisy_obs output included)."""
+    from dexterous_rl_manipulation_b200 import _lib
+    CC = dx.CurriculumConfig
+    gen = torch.Generator(device="cuda").manual_seed(1)
+    env = dx.BatchedManipulationEnv(n, "cuda", max_episode_steps=10, reward_type="dense", auto_reset=True, respawn=True,
+                                    loop_max_steps=10, track_episodes=False, groups=[CC.easy(), CC.hard()], seed=2)
+    check = _with_guard_bands(env)
+    env.reset(seed=2)
+    try:
+        for impl in ("tma", "register"):
+            _lib.set_step_impl(impl)
+            for t in range(25):
+                env.step(torch.rand(n, 15, device="cuda", generator=gen) * 2 - 1)
+            check()
+        _lib.set_step_impl("auto")
+        for chunks in (1, 5):
+            env.step_host(torch.rand(n, 15).mul_(2).sub_(1).pin_memory(), chunks=chunks)
+            check()
+    finally:
+        _lib.set_step_impl("auto")
+    assert int(env.counters[:, 0].sum()) > n
+    noisy = dx.BatchedManipulationEnv(n, "cuda", max_episode_steps=10, reward_type="sparse", auto_reset=True, respawn=True,
+                                      loop_max_steps=10, track_episodes=True, curriculum_config=CC.medium(), seed=3,
+                                      observation_noise_std=0.1, dynamics_noise_std=0.2)
+    noisy.reset(seed=3)                       # allocates the noise buffers
+    noisy.step(torch.zeros(n, 15, device="cuda"))
+    check2 = _with_guard_bands(noisy)
+    nbytes = noisy._noisy_obs.numel() * 4
+    big = torch.full((nbytes + 8192,), 0xA5, dtype=torch.uint8, device="cuda")
+    noisy._noisy_obs = big[4096:4096 + nbytes].view(torch.float32).view(45, noisy.ld)
+    for t in range(25):
+        obs = noisy.step(torch.rand(n, 15, device="cuda", generator=gen) * 2 - 1)[0]
+    check2()
+    torch.cuda.synchronize()
+    assert bool((big[:4096] == 0xA5).all()) and bool((big[4096 + nbytes:] == 0xA5).all()), "out-of-bounds write around noisy_obs"
+    assert obs.data_ptr() == noisy._noisy_obs.data_ptr() and bool(torch.isfinite(obs).all())
+
+
 def test_masked_reset_touches_only_masked_envs(dx):
     """options={"mask": ...}: the manual-reset pattern of RL loops that do not use in-kernel auto-reset."""
     CC = dx.CurriculumConfig
