@@ -14,7 +14,10 @@
  *     pointers (pinned for full speed) and are documented as such.
  *   - `stream` is a cudaStream_t passed as void* (0 = legacy default stream).  Calls are
  *     asynchronous on that stream unless stated; no allocation and no per-call global state
- *     (the only process-wide switch is dexsim_set_step_impl) => thread-safe per (device, stream).
+ *     (the only process-wide switches are dexsim_set_step_impl / dexsim_set_rollout_impl, for tests
+ *     and profiling) => thread-safe per (device, stream).  dexsim_step_host forks onto a few internal
+ *     streams per device, joins them into `stream` and synchronizes it before returning; concurrent
+ *     callers are serialised while they enqueue.
  *   - Return value: 0 = ok; negative cudaError_t (-e) for CUDA failures; DEXSIM_E_* for
  *     argument errors.  No exceptions cross the boundary.  dexsim_error_string() explains.
  *   - Per-env arrays are structure-of-arrays with leading dimension `ld` (>= n, multiple of
