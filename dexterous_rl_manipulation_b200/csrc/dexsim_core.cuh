@@ -289,8 +289,9 @@ DEXSIM_D void normal_pair(uint32_t wa, uint32_t wb, float& z0, float& z1) {
     const float u1 = (float)((wa >> 8) + 1u) * 5.9604644775390625e-08f;   // (0, 1]
     const float u2 = u24(wb);
     const float rad = sqrtf(-2.0f * __logf(u1));
-    float s, c;
-    sincospif(2.0f * u2, &s, &c);
+    // uniform angle in [-pi, pi): the range in which the hardware sine / cosine keep ~2^-21 absolute error
+    const float theta = 6.2831855f * (u2 - 0.5f);
+    const float s = __sinf(theta), c = __cosf(theta);
     z0 = rad * c; z1 = rad * s;
 }
 template <int ROWS>
