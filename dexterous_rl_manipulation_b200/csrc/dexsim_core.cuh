@@ -95,10 +95,11 @@ DEXSIM_D unsigned update_contacts(const EnvRegs& e, int& n_c, double& dmin) {
         const double dy = __dsub_rn(tip, e.op[1]);
         const double dz = __dsub_rn(tip, e.op[2]);
         const double sq = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
-        bool c;
-        if (sq < lo2) c = true;
-        else if (sq > hi2) c = false;
-        else c = __dsqrt_rn(sq) < e.thr;                           // tie band (and NaN): exact test, :310
+        // two compares and a select for all but the tie band: lanes of a warp differ in their contact state all the
+        // time, so an if / else-if chain here diverges (ncu: 26 of 32 lanes active on these lines); the band does not
+        const bool below = sq < lo2, above = sq > hi2;
+        bool c = below;
+        if (!(below || above)) c = __dsqrt_rn(sq) < e.thr;         // tie band (and NaN): exact test, :310
         c = c && thr_pos;
         mask |= (c ? 1u : 0u) << f;
         n_c += c ? 1 : 0;

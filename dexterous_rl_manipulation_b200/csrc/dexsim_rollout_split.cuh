@@ -54,10 +54,9 @@ DEXSIM_D bool split_contact(const SplitRegs& e, double& sq) {
     const double tip = (double)__fmul_rn(s, 0.1f);
     const double dx = __dsub_rn(tip, e.op[0]), dy = __dsub_rn(tip, e.op[1]), dz = __dsub_rn(tip, e.op[2]);
     sq = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
-    bool c;
-    if (sq < lo2) c = true;
-    else if (sq > hi2) c = false;
-    else c = __dsqrt_rn(sq) < e.thr;
+    const bool below = sq < lo2, above = sq > hi2;     // branch only for the tie band (see update_contacts)
+    bool c = below;
+    if (!(below || above)) c = __dsqrt_rn(sq) < e.thr;
     return c && (e.thr > 0.0);
 }
 
