@@ -210,32 +210,50 @@ def _run_one_episode_each(env, k_steps, policy, respawn, loop_max_steps, with_hi
 def evaluate_with_noise_batched(eval_config, policy: str = "heuristic", observation_noise_std: float = 0.0,
                                 dynamics_noise_std: float = 0.0, num_episodes: int = 20, seed: Optional[int] = None,
                                 reward_type: str = "dense", max_episode_steps: int = 200, device="cuda",
-                                num_replicas: int = 1, policy_seed: int = 0) -> Dict:
+                                num_replicas: int = 1, policy_seed: int = 0,
+                                shard: Optional[Tuple[int, int]] = None) -> Dict:
     """RobustnessTester.evaluate_with_noise: ONE env object reused for ``num_episodes`` episodes -- the
     object is respawned only for the first one and stays where the previous episode left it afterwards
     (evaluation/robustness_tests.py:260,282; envs/manipulation_env.py:156-161); every episode is one
     fused launch in one-episode mode followed by the reference's own reset(seed + episode).  ``num_replicas``
     independent copies of that experiment run side by side (replica r is seeded with seed + 1000 r).
     Dynamics noise is drawn in-kernel; observation noise cannot change the trajectory of a policy that
-    ignores observations (all shipped policies do) and is only recorded in the output."""
-    n = max(int(num_replicas), 2)
+    ignores observations (all shipped policies do) and is only recorded in the output.
+    With ``torch.distributed`` initialised (or ``shard=(rank, world_size)``) the replicas are spread over the ranks
+    and the records all-gathered; every rank returns the complete, GPU-count-independent result."""
+    import torch.distributed as dist
+    from .distributed import shard_range
+    distributed = shard is None and dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+    rank, world = shard if shard is not None else ((dist.get_rank(), dist.get_world_size()) if distributed else (0, 1))
+    if world > 1 and seed is None:
+        raise ValueError("pass a seed when the replicas are spread over several ranks")
+    lo, hi = shard_range(int(num_replicas), rank, world)          # this rank's replicas; Philox keys use the global index
+    m = hi - lo
+    n = max(m, 2)
     base = int(np.random.default_rng(None).integers(0, 2 ** 31)) if seed is None else int(seed)
     env = BatchedManipulationEnv(n, device, max_episode_steps=max_episode_steps, reward_type=reward_type,
                                  track_episodes=True, rng="numpy", groups=[eval_config],
                                  group_sigma_obs=observation_noise_std, group_sigma_dyn=dynamics_noise_std,
-                                 seed=policy_seed if seed is None else base)
-    replicas = [[] for _ in range(int(num_replicas))]
+                                 seed=policy_seed if seed is None else base, env_gid0=lo)
+    local = {lo + r: [] for r in range(m)}
     for ep in range(int(num_episodes)):
         # robustness_tests.py:281-282: reset(seed = seed + episode) on the SAME env object -- the first
         # reset samples the spawn, later ones keep the position the previous episode ended at
-        env.reset(seed=[base + 1000 * r + ep for r in range(n)])
+        env.reset(seed=[base + 1000 * (lo + r) + ep for r in range(n)])
         env._episode.fill_(ep)                       # distinct Philox policy / noise streams per episode
         recs = _run_one_episode_each(env, max_episode_steps, policy, False, max_episode_steps, True, {})
-        for r in range(int(num_replicas)):
+        for r in range(m):
             rec, counts = recs[r]
             d = _episode_dict(rec, counts, eval_config.object_size, eval_config.object_mass, eval_config.friction_coefficient)
-            replicas[r].append({k: d[k] for k in ("success", "episode_steps", "num_contacts", "final_contacts",
-                                                  "contact_history", "episode_reward", "failure_type", "failure_mode")})
+            local[lo + r].append({k: d[k] for k in ("success", "episode_steps", "num_contacts", "final_contacts",
+                                                    "contact_history", "episode_reward", "failure_type", "failure_mode")})
+    if distributed:
+        parts = [None] * world
+        dist.all_gather_object(parts, local)
+        local = {k: v for part in parts for k, v in part.items()}
+    elif shard is not None and world > 1:
+        return {"shard_replicas": local, "range": (lo, hi)}          # caller merges (tests, custom launchers)
+    replicas = [local[r] for r in range(int(num_replicas))]
     episodes = [e for eps in replicas for e in eps]
     return {"episodes": episodes, "metrics": aggregate_metrics(episodes, max_episode_steps),
             "noise_levels": {"observation_noise_std": observation_noise_std, "dynamics_noise_std": dynamics_noise_std},

@@ -719,6 +719,14 @@ def test_batched_robustness_front_end_matches_reference(dx):
     assert set(sweep["combined_noise"]) == {"obs_0.000_dyn_0.100", "obs_0.050_dyn_0.000", "obs_0.050_dyn_0.100"}
     assert sweep["dynamics_noise"][0.1]["metrics"]["total_episodes"] == 32
     assert sweep["dynamics_noise"][0.1]["noise_levels"] == {"observation_noise_std": 0.0, "dynamics_noise_std": 0.1}
+    # replicas spread over ranks: three shards of 8 noisy replicas == the single batch, record for record
+    whole = dx.evaluation.evaluate_with_noise_batched(cfg, "heuristic", 0.0, 0.1, num_episodes=4, seed=3, max_episode_steps=T,
+                                                      num_replicas=8)
+    merged = {}
+    for r in range(3):
+        merged.update(dx.evaluation.evaluate_with_noise_batched(cfg, "heuristic", 0.0, 0.1, num_episodes=4, seed=3,
+                                                                max_episode_steps=T, num_replicas=8, shard=(r, 3))["shard_replicas"])
+    assert [merged[r] for r in range(8)] == whole["replicas"]
 
 
 def test_seed_variance_front_end_feeds_reference_statistics(dx):
