@@ -763,15 +763,27 @@ static int tma_shape_choice() {
 // track: 0 = plain step, 1 = full episode tracking (returns + history summaries -> labels), 2 = counts only
 static int launch_step_tma(const DexsimState* st, const DexsimParams* p, const DexsimGroup* groups, const uint16_t* goe,
                            const DexsimStepIO* io, cudaStream_t s, int track, int sm_count) {
-    StepMaps maps;
-    memset(&maps, 0, sizeof(maps));
+    // Tensor maps are pure functions of (base pointers, n, ld): a stepping loop re-encodes nothing.  One cached set
+    // per host thread; the SoA action map is keyed by the action pointer too (AoS actions use 1-D bulk copies).
+    struct MapCache { const void* obs; const void* op64; const void* act; int64_t n, ld; bool valid; StepMaps maps; };
+    static thread_local MapCache cache = {nullptr, nullptr, nullptr, 0, 0, false, {}};
     const bool aos = io->action_layout == 1;
-    bool ok = make_map_2d(&maps.obs_jpjv, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, st->obs, st->n, st->ld, DEXSIM_OBS, 30) &&
-              make_map_2d(&maps.obs_ov, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, st->obs, st->n, st->ld, DEXSIM_OBS, 3) &&
-              make_map_2d(&maps.op64, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 8, st->op64, st->n, st->ld, 3, 3);
-    if (ok && !aos)
-        ok = make_map_2d(&maps.act_soa, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(io->action), st->n, st->ld, NJ, NJ);
-    if (!ok) return 1;                               // caller falls back to the register-resident kernel
+    const void* act_key = aos ? nullptr : (const void*)io->action;
+    if (!(cache.valid && cache.obs == st->obs && cache.op64 == st->op64 && cache.act == act_key && cache.n == st->n &&
+          cache.ld == st->ld)) {
+        cache.valid = false;
+        memset(&cache.maps, 0, sizeof(cache.maps));
+        bool ok = make_map_2d(&cache.maps.obs_jpjv, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, st->obs, st->n, st->ld, DEXSIM_OBS, 30) &&
+                  make_map_2d(&cache.maps.obs_ov, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, st->obs, st->n, st->ld, DEXSIM_OBS, 3) &&
+                  make_map_2d(&cache.maps.op64, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 8, st->op64, st->n, st->ld, 3, 3);
+        if (ok && !aos)
+            ok = make_map_2d(&cache.maps.act_soa, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(io->action), st->n,
+                             st->ld, NJ, NJ);
+        if (!ok) return 1;                           // caller falls back to the register-resident kernel
+        cache.obs = st->obs; cache.op64 = st->op64; cache.act = act_key; cache.n = st->n; cache.ld = st->ld;
+        cache.valid = true;
+    }
+    const StepMaps& maps = cache.maps;
     const int num_tiles = (int)((st->n + TILE - 1) / TILE);
     const bool dense = p->reward_type == 1;
     const int shape = tma_shape_choice();
