@@ -475,7 +475,7 @@ def run_b200(args):
             sweep.append({"envs": n, "value": v, "ms_per_step": s_ms / 300,
                           "roofline_frac": v * ALGO_BYTES_PER_ENV_STEP / 1e9 / peak, "graph_replay_value": gv,
                           "fused_rollout_value": fv,
-                          "note": "API mode is bound by the ~8.5 us host launch path at this size (state is L2-resident)"})
+                          "note": "state is L2-resident at this size: one step is a launch plus one load-compute-store round trip (latency-bound, ~5 us of host issue per step)"})
             del env_s, pool_s, env_f
 
     if rank == 0:
