@@ -183,6 +183,48 @@ __device__ __forceinline__ void finish_and_reset(EnvRegs& e, const DexsimParams&
 
 namespace dexsim {
 
+// ---- single-env read-back ------------------------------------------------------------------------------
+// TAGGED: slot 63 = tag, written after every other slot is visible system-wide (host polling on mapped memory).
+// Runs in the first 64 threads of a CTA.
+template <bool TAGGED>
+__device__ __forceinline__ void pack_env_body(const DexsimState& st, const DexsimStepIO& io, const int64_t i, const int after_reset,
+                                              double* __restrict__ out) {
+    const int t = threadIdx.x;
+    const int64_t ld = st.ld;
+    const bool noisy = io.noisy_obs && (io.obs_noise || io.sigma_obs != 0.0f);
+    const float* obs = noisy ? io.noisy_obs : st.obs;
+    if (t < NOBS) out[t] = (double)obs[t * ld + i];
+    if (t == 45) out[45] = after_reset ? 0.0 : (io.reward64 ? io.reward64[i] : (double)io.reward[i]);
+    if (t == 46) out[46] = after_reset ? 0.0 : (double)io.terminated[i];
+    if (t == 47) out[47] = after_reset ? 0.0 : (double)io.truncated[i];
+    if (t == 48) out[48] = (double)__popc((unsigned)st.cmask[i]);
+    if (t == 49) out[49] = (double)st.step_count[i];
+    if (t >= 50 && t < 53) out[t] = st.op64[(t - 50) * ld + i];
+    if (t == 53) out[53] = st.size[i];
+    if (t == 54) out[54] = st.mass[i];
+    if (t == 55) out[55] = st.friction[i];
+    if (t >= 56 && t < 60) out[t] = (io.reward_comps && !after_reset) ? (double)io.reward_comps[(t - 56) * ld + i] : 0.0;
+    if (t == 60) out[60] = (io.finished && !after_reset) ? (double)io.finished[i] : 0.0;
+    if (t > 60 && t < 63) out[t] = 0.0;
+    if (!TAGGED) {
+        if (t == 63) out[63] = 0.0;
+    } else {
+        __threadfence_system();         // the caller writes the tag after a block-wide barrier (pack_env_publish)
+    }
+}
+// Every thread of the block must call this (it contains the barrier).
+__device__ __forceinline__ void pack_env_publish(double* __restrict__ out, const double tag) {
+    __syncthreads();
+    if (threadIdx.x == 0) *reinterpret_cast<volatile double*>(out + 63) = tag;
+}
+
+template <bool TAGGED>
+__global__ void pack_env_kernel(const DexsimState st, const DexsimStepIO io, const int64_t i, const int after_reset,
+                                double* __restrict__ out, const double tag) {
+    pack_env_body<TAGGED>(st, io, i, after_reset, out);
+    if (TAGGED) pack_env_publish(out, tag);
+}
+
 // ---- step kernel -----------------------------------------------------------------------------------
 // DENSE: reward type.  AOS: action is [n, 15] (reference layout) and is transposed through shared
 // memory with coalesced float4 reads (15 is odd, so the per-thread reads are bank-conflict free).
@@ -202,7 +244,8 @@ __device__ __forceinline__ float obs_entry(const EnvRegs& e, const int row) {
 template <bool DENSE, bool AOS, bool EXTRAS>
 __global__ void __launch_bounds__(STEP_THREADS, DEXSIM_STEP_MIN_BLOCKS)
 step_kernel(const DexsimState st, const DexsimParams p, const DexsimGroup* __restrict__ groups,
-            const uint16_t* __restrict__ group_of_env, const DexsimStepIO io) {
+            const uint16_t* __restrict__ group_of_env, const DexsimStepIO io,
+            double* __restrict__ pack_out = nullptr, const double pack_tag = 0.0) {
     __shared__ __align__(16) float sh_act[AOS ? STEP_THREADS * NJ : 4];
     // Finished episodes are counted per CTA in shared memory and flushed with one global atomic per
     // non-zero counter at the end: thousands of episodes end per step and would otherwise serialise
@@ -373,6 +416,13 @@ step_kernel(const DexsimState st, const DexsimParams p, const DexsimGroup* __res
         if (io.ret_sums)
             for (int w = threadIdx.x; w < p.num_groups * 2; w += STEP_THREADS)
                 if (sh_rs[w] != 0.0) atomicAdd(&io.ret_sums[w], sh_rs[w]);
+    }
+    // dexsim_step_single (one env, one CTA): pack what step() returns in the same launch; the 64 packing threads
+    // read what thread 0 just stored, hence the block-wide barrier
+    if (EXTRAS && pack_out) {
+        __syncthreads();
+        if (threadIdx.x < 64) pack_env_body<true>(st, io, 0, 0, pack_out);
+        pack_env_publish(pack_out, pack_tag);
     }
 }
 
@@ -583,35 +633,6 @@ rollout_kernel(const DexsimState st, const DexsimParams p, const DexsimGroup* __
 }
 
 // ---- single-env read-back ------------------------------------------------------------------------------
-// TAGGED: slot 63 = tag, written after every other slot is visible system-wide (host polling on mapped memory).
-template <bool TAGGED>
-__global__ void pack_env_kernel(const DexsimState st, const DexsimStepIO io, const int64_t i, const int after_reset,
-                                double* __restrict__ out, const double tag) {
-    const int t = threadIdx.x;
-    const int64_t ld = st.ld;
-    const float* obs = (io.noisy_obs && io.obs_noise) ? io.noisy_obs : st.obs;
-    if (t < NOBS) out[t] = (double)obs[t * ld + i];
-    if (t == 45) out[45] = after_reset ? 0.0 : (io.reward64 ? io.reward64[i] : (double)io.reward[i]);
-    if (t == 46) out[46] = after_reset ? 0.0 : (double)io.terminated[i];
-    if (t == 47) out[47] = after_reset ? 0.0 : (double)io.truncated[i];
-    if (t == 48) out[48] = (double)__popc((unsigned)st.cmask[i]);
-    if (t == 49) out[49] = (double)st.step_count[i];
-    if (t >= 50 && t < 53) out[t] = st.op64[(t - 50) * ld + i];
-    if (t == 53) out[53] = st.size[i];
-    if (t == 54) out[54] = st.mass[i];
-    if (t == 55) out[55] = st.friction[i];
-    if (t >= 56 && t < 60) out[t] = (io.reward_comps && !after_reset) ? (double)io.reward_comps[(t - 56) * ld + i] : 0.0;
-    if (t == 60) out[60] = (io.finished && !after_reset) ? (double)io.finished[i] : 0.0;
-    if (t > 60 && t < 63) out[t] = 0.0;
-    if (!TAGGED) {
-        if (t == 63) out[63] = 0.0;
-    } else {
-        __threadfence_system();
-        __syncthreads();
-        if (t == 0) *reinterpret_cast<volatile double*>(out + 63) = tag;
-    }
-}
-
 // ---- RNG exposure ------------------------------------------------------------------------------------
 __global__ void fill_policy_kernel(const DexsimState st, const DexsimParams p, int policy_kind, float* __restrict__ out) {
     const int64_t n = st.n, ld = st.ld;
@@ -700,8 +721,9 @@ static inline int cuda_rc(cudaError_t e) { return e == cudaSuccess ? 0 : -(int)e
 
 template <bool DENSE, bool AOS>
 static void launch_step_variant(bool extras, int grid, cudaStream_t s, const DexsimState& st, const DexsimParams& p,
-                                const DexsimGroup* groups, const uint16_t* goe, const DexsimStepIO& io) {
-    if (extras) step_kernel<DENSE, AOS, true><<<grid, STEP_THREADS, 0, s>>>(st, p, groups, goe, io);
+                                const DexsimGroup* groups, const uint16_t* goe, const DexsimStepIO& io,
+                                double* pack_out, double pack_tag) {
+    if (extras) step_kernel<DENSE, AOS, true><<<grid, STEP_THREADS, 0, s>>>(st, p, groups, goe, io, pack_out, pack_tag);
     else        step_kernel<DENSE, AOS, false><<<grid, STEP_THREADS, 0, s>>>(st, p, groups, goe, io);
 }
 
@@ -808,7 +830,8 @@ static int launch_step_tma(const DexsimState* st, const DexsimParams* p, const D
 }
 
 static int launch_step(const DexsimState* st, const DexsimParams* p, const DexsimGroup* groups,
-                       const uint16_t* goe, const DexsimStepIO* io, cudaStream_t s) {
+                       const uint16_t* goe, const DexsimStepIO* io, cudaStream_t s,
+                       double* pack_out = nullptr, double pack_tag = 0.0) {
     int rc = check_state(st);
     if (rc) return rc;
     if (!io || !io->action || !io->reward || !io->terminated || !io->truncated || !io->num_contacts) return DEXSIM_E_NULL;
@@ -816,8 +839,9 @@ static int launch_step(const DexsimState* st, const DexsimParams* p, const Dexsi
     const bool fused_dyn = !io->dyn_noise && io->sigma_dyn != 0.0f;
     const bool fused_obs = !io->obs_noise && io->sigma_obs != 0.0f;
     if ((io->obs_noise != nullptr || fused_obs) != (io->noisy_obs != nullptr)) return DEXSIM_E_NULL;
+    if (pack_out && st->n != 1) return DEXSIM_E_SIZE;
     const bool extras = io->dyn_noise || io->obs_noise || io->reward_comps || io->reward64 || io->finished ||
-                        (p && p->auto_reset) || st->ep_return != nullptr || fused_dyn || fused_obs;
+                        (p && p->auto_reset) || st->ep_return != nullptr || fused_dyn || fused_obs || pack_out != nullptr;
     const bool group_sigma = (fused_dyn && io->sigma_dyn < 0.0f) || (fused_obs && io->sigma_obs < 0.0f);
     rc = check_params(p, p && (p->auto_reset || group_sigma), groups);
     if (rc) return rc;
@@ -844,10 +868,10 @@ static int launch_step(const DexsimState* st, const DexsimParams* p, const Dexsi
     if (impl == 2) return DEXSIM_E_PARAM;            // TMA pipeline was demanded but is not eligible
     const int grid = grid_for(st->n, STEP_THREADS, di.step_ctas, di.sm_count);
     const bool dense = p->reward_type == 1, aos = io->action_layout == 1;
-    if (dense) { if (aos) launch_step_variant<true, true>(extras, grid, s, *st, *p, groups, goe, *io);
-                 else     launch_step_variant<true, false>(extras, grid, s, *st, *p, groups, goe, *io); }
-    else       { if (aos) launch_step_variant<false, true>(extras, grid, s, *st, *p, groups, goe, *io);
-                 else     launch_step_variant<false, false>(extras, grid, s, *st, *p, groups, goe, *io); }
+    if (dense) { if (aos) launch_step_variant<true, true>(extras, grid, s, *st, *p, groups, goe, *io, pack_out, pack_tag);
+                 else     launch_step_variant<true, false>(extras, grid, s, *st, *p, groups, goe, *io, pack_out, pack_tag); }
+    else       { if (aos) launch_step_variant<false, true>(extras, grid, s, *st, *p, groups, goe, *io, pack_out, pack_tag);
+                 else     launch_step_variant<false, false>(extras, grid, s, *st, *p, groups, goe, *io, pack_out, pack_tag); }
     return cuda_rc(cudaGetLastError());
 }
 
@@ -938,6 +962,12 @@ int dexsim_step(const DexsimState* st, const DexsimParams* p, const DexsimGroup*
                 const uint16_t* group_of_env, const DexsimStepIO* io, void* stream) {
     if (!p) return DEXSIM_E_NULL;
     return launch_step(st, p, groups, group_of_env, io, (cudaStream_t)stream);
+}
+
+int dexsim_step_single(const DexsimState* st, const DexsimParams* p, const DexsimGroup* groups,
+                       const uint16_t* group_of_env, const DexsimStepIO* io, double* out64, double tag, void* stream) {
+    if (!p || !out64) return DEXSIM_E_NULL;
+    return launch_step(st, p, groups, group_of_env, io, (cudaStream_t)stream, out64, tag);
 }
 
 int dexsim_rollout(const DexsimState* st, const DexsimParams* p, const DexsimGroup* groups,

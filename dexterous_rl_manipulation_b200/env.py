@@ -528,9 +528,17 @@ class BatchedManipulationEnv:
         elif want_obs and (fused or not self.observation_noise_std > 0.0):
             io.sigma_obs = self.observation_noise_std if self.observation_noise_std > 0.0 else -1.0
             io.noisy_obs = self._noisy_obs.data_ptr()
+        post_step_noise = want_obs and obs_noise is None and not fused and self.observation_noise_std > 0.0
+        if self.single and not post_step_noise:
+            # one launch: the step and the packed read-back of what step() returns (dexsim_step_single)
+            tag = self._next_pack_tag()
+            _lib.check(self._lib.dexsim_step_single(self._state_ref, self._params_ref, self._groups_ptr, self._goe_ptr,
+                                                    self._io_ref, self._pack_host.data_ptr(), tag, self._stream()),
+                       "dexsim_step_single")
+            return self._single_wait_decode(tag, after_reset=False)
         _lib.check(self._lib.dexsim_step(self._state_ref, self._params_ref, self._groups_ptr, self._goe_ptr,
                                          self._io_ref, self._stream()), "dexsim_step")
-        if want_obs and obs_noise is None and not fused and self.observation_noise_std > 0.0:
+        if post_step_noise:
             # Philox observation noise is keyed by (episode, step count AFTER the step), so it is
             # drawn once the step has run (evaluation/robustness_tests.py:204-205)
             _lib.check(self._lib.dexsim_fill_normal(
@@ -598,19 +606,26 @@ class BatchedManipulationEnv:
     def _single_readback(self, after_reset, noisy):
         """num_envs == 1: one pack kernel + one 512-byte D2H copy -> the reference's return values
         (obs float32[45], reward float, terminated, truncated, info dict of envs/manipulation_env.py:266-283)."""
-        if getattr(self, "_pack_host", None) is None:
-            # page-locked and (unified addressing) mapped into the device: the pack kernel writes straight into it
-            self._pack_host = torch.zeros(64, dtype=torch.float64).pin_memory()
-            self._pack_np = self._pack_host.numpy()
-            self._pack_tag = 0.0
         io = _lib.DexsimStepIO.from_buffer_copy(self._io)
         if noisy:
             io.noisy_obs, io.obs_noise = self._noisy_obs.data_ptr(), self._noisy_obs.data_ptr()
         else:
             io.noisy_obs = io.obs_noise = None
-        self._pack_tag = tag = self._pack_tag + 1.0
+        tag = self._next_pack_tag()
         _lib.check(self._lib.dexsim_pack_env_tagged(self._state_ref, C.byref(io), 0, int(after_reset),
                                                     self._pack_host.data_ptr(), tag, self._stream()), "dexsim_pack_env_tagged")
+        return self._single_wait_decode(tag, after_reset)
+
+    def _next_pack_tag(self):
+        if getattr(self, "_pack_host", None) is None:
+            # page-locked and (unified addressing) mapped into the device: the pack code writes straight into it
+            self._pack_host = torch.zeros(64, dtype=torch.float64).pin_memory()
+            self._pack_np = self._pack_host.numpy()
+            self._pack_tag = 0.0
+        self._pack_tag += 1.0
+        return self._pack_tag
+
+    def _single_wait_decode(self, tag, after_reset):
         h = self._pack_np
         # the tag lands after the 63 data slots: poll it instead of paying a stream synchronize, but never
         # spin forever -- a failed launch surfaces through the synchronize below

@@ -271,6 +271,13 @@ int dexsim_pack_env(const DexsimState* st, const DexsimStepIO* io, int64_t index
 int dexsim_pack_env_tagged(const DexsimState* st, const DexsimStepIO* io, int64_t index, int32_t after_reset,
                            double* out64 /* device or mapped host [64] */, double tag, void* stream);
 
+/* dexsim_step for a batch of ONE env (st->n == 1) with the tagged read-back of env 0 done by the same launch: what
+ * DexterousManipulationEnv.step returns (envs/manipulation_env.py:184-283) in one kernel and no copy call when
+ * `io->action` and `out64` are mapped page-locked host memory.  Same arguments as dexsim_step + dexsim_pack_env_tagged. */
+int dexsim_step_single(const DexsimState* st, const DexsimParams* p, const DexsimGroup* groups,
+                       const uint16_t* group_of_env, const DexsimStepIO* io,
+                       double* out64 /* device or mapped host [64] */, double tag, void* stream);
+
 /* ---- RNG exposure (so tests can pre-draw exactly what the fused kernels draw) ---------------- */
 int dexsim_fill_policy_actions(const DexsimState* st, const DexsimParams* p, int32_t policy_kind,
                                float* actions /* [15, ld] for each env's CURRENT (episode, step) */,
