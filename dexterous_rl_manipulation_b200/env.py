@@ -242,6 +242,7 @@ class BatchedManipulationEnv:
         io.num_contacts, io.finished = self._ptr(self._num_contacts), self._ptr(self._finished)
         io.counters, io.ret_sums = self._ptr(self.counters), self._ptr(self.ret_sums)
         io.reward64 = self._ptr(self._reward64)
+        self._io_single = None
 
     @property
     def curriculum_config(self):
@@ -292,6 +293,7 @@ class BatchedManipulationEnv:
             self.ret_sums = torch.zeros(G, 2, dtype=torch.float64, device=self.device)
         self._params.num_groups = G
         self._io.counters, self._io.ret_sums = self._ptr(self.counters), self._ptr(self.ret_sums)
+        self._io_single = None                      # persistent copy used by the single-env fast path: rebuild lazily
         self._groups_ptr = self._groups_dev.data_ptr()
         self._groups_dirty = False
 
@@ -490,8 +492,37 @@ class BatchedManipulationEnv:
             if rc:
                 raise _lib.DexsimError(rc, "dexsim_step")
             return self._step_out
+        if (self.single and dyn_noise is None and obs_noise is None and not self._noisy_env
+                and not (isinstance(action, torch.Tensor) and action.is_cuda)
+                and torch.cuda.current_device() == self.device.index):
+            return self._step_single_fast(action)
         with torch.cuda.device(self.device):
             return self._step_general(action, dyn_noise, obs_noise)
+
+    def _step_single_fast(self, action):
+        """num_envs == 1, host action, no noise: the drop-in path under the reference's callers.  One ctypes call
+        (dexsim_step_single), persistent argument structs, result decoded from mapped host memory."""
+        io = self._io_single
+        if io is None:
+            if getattr(self, "_action_pin", None) is None:
+                self._action_pin = torch.zeros(16, dtype=torch.float32).pin_memory()
+                self._action_pin_np = self._action_pin.numpy()
+            if getattr(self, "_pack_host", None) is None:
+                self._next_pack_tag()                   # allocates the mapped result record
+            io = self._io_single = _lib.DexsimStepIO.from_buffer_copy(self._io)
+            io.action, io.action_layout = self._action_pin.data_ptr(), 1
+            io.dyn_noise = io.obs_noise = io.noisy_obs = None
+            io.sigma_dyn = io.sigma_obs = 0.0
+            self._io_single_ref = C.byref(io)
+            self._pack_ptr = self._pack_host.data_ptr()
+        # float64 / list actions are cast exactly like the general path's astype(np.float32)
+        self._action_pin_np[:15] = np.asarray(action).reshape(15)
+        self._pack_tag = tag = self._pack_tag + 1.0
+        rc = self._lib.dexsim_step_single(self._state_ref, self._params_ref, self._groups_ptr, self._goe_ptr,
+                                          self._io_single_ref, self._pack_ptr, tag, _raw_stream(self.device.index))
+        if rc:
+            raise _lib.DexsimError(rc, "dexsim_step_single")
+        return self._single_wait_decode(tag, False)
 
     def _step_general(self, action, dyn_noise, obs_noise):
         io = self._io
