@@ -394,6 +394,32 @@ def run_b200(args):
                                  "410 B algorithmic figure does not count"}
         del env_t, drv_t
 
+    # ---- configs[0] through the drop-in: ONE env behind the reference's Gymnasium API (NumPy action in, NumPy
+    #      observation / Python scalars / info dict out), heuristic-style host policy, dense reward, 200-step episodes ----
+    single_env = None
+    if rank == 0:
+        import numpy as np
+        env1 = dx.BatchedManipulationEnv(1, dev, reward_type="dense", max_episode_steps=MAX_EPISODE_STEPS, respawn=True)
+        rng1 = np.random.default_rng(SEED)
+        obs1, _ = env1.reset(seed=SEED)
+        def host_policy(_obs):                        # policies/heuristic_policy.py:55-62 in spirit: close + jitter
+            return np.clip(-0.5 + rng1.uniform(-1.0, 1.0, 15) * 0.1, -1.0, 1.0).astype(np.float32)
+        def run_steps(k):
+            nonlocal obs1
+            for _ in range(k):
+                obs1, r1, te1, tr1, _info = env1.step(host_policy(obs1))
+                if te1 or tr1:
+                    obs1, _ = env1.reset()            # fresh spawn (respawn=True), like a new env object per episode
+        run_steps(300)
+        n1 = 3000
+        t0 = time.perf_counter()
+        run_steps(n1)
+        dt1 = time.perf_counter() - t0
+        single_env = {"value": n1 / dt1, "unit": UNIT, "us_per_step": 1e6 * dt1 / n1, "env_steps": n1,
+                      "note": "num_envs=1 drop-in under the reference's reset/step API incl. the host policy and resets "
+                              "(dexsim_step_single: one launch per step, mapped host buffers)"}
+        del env1
+
     # ---- end to end: pinned host actions in, obs / reward / flags out ------------------------------
     h_pool = [torch.rand(E, 15).mul_(2).sub_(1).pin_memory() for _ in range(2)]
     for t in range(3):
@@ -495,7 +521,7 @@ def run_b200(args):
             },
             "e2e": e2e, "gpu_launches": launches, "gpu_launches_note": "step_tma_kernel launches inside the main timed region (one per step)",
             "roofline": roofline, "cpu_baseline": cpu_base,
-            "tracking_full": tracking_full, "fused_rollout": fused, "sweep": sweep, "clocks": clocks,
+            "tracking_full": tracking_full, "single_env_dropin": single_env, "fused_rollout": fused, "sweep": sweep, "clocks": clocks,
             "episodes": int(env.counters[:, 0].sum().item()),
         }
         os.write(json_fd, (json.dumps(line) + "\n").encode())
