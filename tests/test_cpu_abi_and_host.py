@@ -306,3 +306,44 @@ def test_bench_reference_arm_prints_one_contract_line():
     assert d["steps"] == 2 and d["warmup"] == 1 and d["value"] > 0 and d["vs_baseline"] is None
     assert d["cpu_baseline"]["kind"] in ("reference", "port") and d["cpu_baseline"]["cores"] == 2
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0 and "workload" in d["config"]
+
+
+def test_aggregate_metrics_equals_reference_aggregation():
+    """evaluation.aggregate_metrics (host side of every batched front-end) against the UNMODIFIED
+    EvaluationMetrics.compute_aggregate_metrics on synthetic episodes: labels come from classify_summary here and
+    from the reference's own classifier there, every aggregate key must agree."""
+    from oracle import ref_harness
+    if not ref_harness.available():
+        pytest.skip("reference (source or byte-compiled) not present")
+    R = ref_harness.load()
+    from dexterous_rl_manipulation_b200.evaluation import aggregate_metrics, count_rows
+    rng = np.random.default_rng(8)
+    T = 60
+    for trial in range(6):
+        episodes = []
+        for _ in range(int(rng.integers(1, 80))):
+            steps = int(rng.integers(1, T + 1))
+            kind = int(rng.integers(4))
+            if kind == 0:
+                counts = rng.integers(0, 6, steps)
+            elif kind == 1:
+                counts = np.minimum(np.arange(steps) // max(1, steps // 4), 5)
+            elif kind == 2:
+                counts = np.maximum(4 - np.arange(steps) // max(1, steps // 5), 0)
+            else:
+                counts = np.zeros(steps, np.int64)
+            success = bool(counts[-1] >= 3 and rng.integers(2))
+            hist = count_rows(counts)
+            ep = {"success": success, "episode_steps": steps, "num_contacts": int(counts[-1]), "final_contacts": int(counts[-1]),
+                  "contact_history": hist, "episode_reward": float(rng.normal())}
+            la, lb, tie = dx.classify_summary(success, steps, int(counts[-1]), int(counts[-1]), max_steps=T, **_summary(counts))
+            ep["failure_type"] = None if la == dx.LABEL_NONE else dx.LABELS_METRICS[la]
+            episodes.append(ep)
+        mine = aggregate_metrics(episodes, T)
+        ref = R.metrics.EvaluationMetrics(3).compute_aggregate_metrics([dict(e) for e in episodes], max_steps=T)
+        assert set(mine) == set(ref), set(mine) ^ set(ref)
+        for k, v in ref.items():
+            if isinstance(v, float):
+                assert mine[k] == pytest.approx(v, rel=1e-12, abs=1e-12), k
+            else:
+                assert mine[k] == v, (k, mine[k], v)
