@@ -8,7 +8,9 @@ One "step" = one env.step() of EVERY env of the job (E envs per GPU, weak scalin
 Workload (BASELINE.json configs[1] scaled to the metric's 1M-env end so the state is larger than
 L2): experiments/config_default.json -- dense reward, max_episode_steps 200,
 CurriculumScheduler(easy -> hard, threshold 0.3, window 15, min episodes 20, 5 steps) fed from
-the device counters, random policy actions U(-1,1) resident in HBM, auto-reset (respawn).
+the device counters, random policy actions U(-1,1) resident in HBM, auto-reset (respawn) with per-group
+episode counters (what the scheduler consumes).  Untimed before the W warm-up steps: a 100-step curriculum
+pre-roll (--preroll-steps) in which the scheduler climbs to its final level.
 
 Printed JSON (one line, rank 0):
   value      whole-job env-steps/s, inputs resident in HBM (API mode: dexsim_step per step)
@@ -16,7 +18,9 @@ Printed JSON (one line, rank 0):
              H2D + D2H copies inside the timed region
   roofline   step kernel: algorithmic 410 B/env-step / CUDA-event kernel time
   cpu_baseline   the reference's own Python loop on this box's host cores (bounded sample)
-  fused_rollout, sweep   extra measurements (in-kernel policy; other env counts)
+  tracking_full       the same loop with full per-env episode tracking (returns, failure labels)
+  single_env_dropin   configs[0]: ONE env behind the reference's reset/step API with a host policy
+  fused_rollout, sweep   extra measurements (in-kernel policy; other env counts, eager and CUDA-graph replay)
 `--impl reference` times the UNMODIFIED reference (byte-compiled in oracle/_ref) with one
 process per host core; it never touches CUDA.
 """
