@@ -64,3 +64,75 @@ def test_allreduce_is_identity_without_process_group():
     c = torch.arange(36, dtype=torch.int64).reshape(2, 18)
     out, _ = dx.distributed.allreduce_counters(c.clone())
     assert torch.equal(out, c)
+
+
+class _Obj:
+    def __init__(self, size, mass, friction):
+        self.size, self.mass, self.friction = size, mass, friction
+
+
+class _HeldOut:
+    """Duck type of evaluation/heldout_objects.py::HeldOutObjectSet."""
+
+    def __init__(self, n):
+        self.heldout_objects = [_Obj(0.03 + 0.01 * k, 0.1 + 0.01 * k, 0.3 + 0.02 * k) for k in range(n)]
+
+    def get_eval_config(self, k):
+        o = self.heldout_objects[k]
+        return dx.CurriculumConfig(object_size=o.size, object_mass=o.mass, friction_coefficient=o.friction)
+
+
+def _fake_shard(heldout_set, policy, n_eps, seeds, reward_type, max_episode_steps, device, policy_seed,
+                contact_history, actions, lo, hi):
+    """Stands in for the CUDA launch of one rank's slice: records are a pure function of the GLOBAL env index,
+    exactly the property the real shard has (Philox keys, reset seeds and groups depend on the global id only)."""
+    from dexterous_rl_manipulation_b200 import _lib
+    out = {}
+    for g in range(lo, hi):
+        rng = np.random.default_rng(1000 + g)
+        steps = int(rng.integers(1, max_episode_steps + 1))
+        counts = rng.integers(0, 6, steps).astype(np.uint8)
+        rec = np.zeros((), _lib.EPISODE_RECORD_DTYPE)
+        rec["env_gid"], rec["episode"], rec["steps"] = g, 0, steps
+        rec["success"] = int(counts[-1] >= 3)
+        rec["final_contacts"] = int(counts[-1])
+        rec["label_metrics"] = _lib.LABEL_NONE if rec["success"] else int(rng.integers(0, 6))
+        rec["label_taxonomy"] = _lib.LABEL_NONE if rec["success"] else int(rng.integers(0, 6))
+        rec["episode_reward"] = float(rng.normal())
+        out[g] = (rec, counts)
+    return out
+
+
+def _frontend_worker(rank, world, port, out_dir):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from dexterous_rl_manipulation_b200 import evaluation
+    evaluation._heldout_shard = _fake_shard
+    res = evaluation.evaluate_heldout_set_batched(_HeldOut(7), policy="heuristic", num_episodes_per_object=3, seed=11,
+                                                  max_episode_steps=40)
+    import pickle
+    with open(os.path.join(out_dir, f"res{rank}.pkl"), "wb") as fh:
+        pickle.dump(res, fh)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_heldout_front_end_gathers_the_single_process_result(tmp_path):
+    """evaluate_heldout_set_batched under a 2-rank gloo group: each rank evaluates its slice of the (object, episode)
+    batch, the records are all-gathered, and EVERY rank returns exactly the single-process result."""
+    import pickle
+    from dexterous_rl_manipulation_b200 import evaluation
+    world = 2
+    mp.spawn(_frontend_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    orig = evaluation._heldout_shard
+    evaluation._heldout_shard = _fake_shard
+    try:
+        single = evaluation.evaluate_heldout_set_batched(_HeldOut(7), policy="heuristic", num_episodes_per_object=3, seed=11,
+                                                         max_episode_steps=40)
+    finally:
+        evaluation._heldout_shard = orig
+    assert single["overall_stats"]["total_episodes"] == 21
+    for rank in range(world):
+        with open(tmp_path / f"res{rank}.pkl", "rb") as fh:
+            got = pickle.load(fh)
+        assert got == single, rank
