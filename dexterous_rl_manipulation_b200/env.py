@@ -323,6 +323,21 @@ class BatchedManipulationEnv:
             return self._group_cfgs[int(self._goe[i])]
         return self._group_cfgs[(self.env_gid0 + i) % len(self._group_cfgs)]
 
+    @property
+    def object_position(self):
+        """The reference's attribute (envs/manipulation_env.py:57,156-161): None until the first reset, then the
+        current position -- float32[3] for one env, a float64 CUDA view [num_envs, 3] for a batch.  Assigning None
+        makes the next reset sample a fresh spawn; assigning a position makes the next reset start from it."""
+        if not self._spawned:
+            return None if self._object_position_arg is None else self._object_position_arg
+        p = self._op64[:, :self.num_envs].t()
+        return p[0].cpu().numpy().astype(np.float32) if self.single else p
+
+    @object_position.setter
+    def object_position(self, value):
+        self._object_position_arg = None if value is None else np.asarray(value, np.float32)
+        self._spawned = False
+
     def _respawn_now(self):
         if self.respawn is not None:
             return bool(self.respawn)

@@ -1245,3 +1245,29 @@ def test_bench_b200_arm_prints_one_contract_line():
     e = d["e2e"]
     assert e["value"] > 0 and e["h2d_bytes_per_step"] == 262144 * 60 and e["d2h_bytes_per_step"] > 262144 * 164
     assert e["value"] < d["value"]                       # host buffers cross PCIe: never faster than the device-resident loop
+
+
+def test_object_position_attribute_follows_the_reference(dx):
+    """envs/manipulation_env.py:156-161: position None -> the next reset samples a spawn; a position -> the next reset
+    keeps it; a reused env keeps wherever the last episode left the object."""
+    env = dx.BatchedManipulationEnv(1, "cuda", reward_type="dense", max_episode_steps=50)
+    assert env.object_position is None
+    env.reset(seed=0)
+    p0 = env.object_position.copy()
+    assert np.allclose(p0, [-0.064868875, 0.072635785, 0.13121918])          # SURVEY.md 8c anchor of reset(seed=0)
+    for _ in range(5):
+        env.step(np.full(15, -0.5, np.float32))
+    p5 = env.object_position.copy()
+    assert p5[2] < p0[2]                                                      # the object falls
+    _, info = env.reset(seed=1)
+    assert np.array_equal(env.object_position, p5) and np.array_equal(info["object_position"], p5.astype(np.float64))
+    env.object_position = None
+    env.reset(seed=1)
+    assert not np.array_equal(env.object_position, p5)                        # fresh spawn
+    env.object_position = [0.01, -0.02, 0.07]
+    env.reset(seed=2)
+    assert np.array_equal(env.object_position, np.array([0.01, -0.02, 0.07], np.float32))
+    batch = dx.BatchedManipulationEnv(64, "cuda")
+    assert batch.object_position is None
+    batch.reset(seed=3)
+    assert tuple(batch.object_position.shape) == (64, 3) and batch.object_position.is_cuda
