@@ -338,6 +338,33 @@ class BatchedManipulationEnv:
         self._object_position_arg = None if value is None else np.asarray(value, np.float32)
         self._spawned = False
 
+    # read-only views of the reference env's state attributes (envs/manipulation_env.py:54-62): NumPy copies for
+    # one env, CUDA views [num_envs, ...] of the SoA state for a batch
+    def _rows(self, lo, hi, dtype=np.float32):
+        v = self._obs[lo:hi, :self.num_envs].t()
+        return v[0].cpu().numpy().astype(dtype) if self.single else v
+
+    @property
+    def joint_positions(self):
+        return self._rows(_L.ROW_JP, _L.ROW_JP + 15)
+
+    @property
+    def joint_velocities(self):
+        return self._rows(_L.ROW_JV, _L.ROW_JV + 15)
+
+    @property
+    def object_velocity(self):
+        return self._rows(_L.ROW_OV, _L.ROW_OV + 3)
+
+    @property
+    def contacts(self):
+        c = self._rows(_L.ROW_CONTACT, _L.ROW_CONTACT + 5)
+        return c.astype(bool) if self.single else c.to(torch.bool)
+
+    @property
+    def step_count(self):
+        return int(self._step_count[0]) if self.single else self._step_count[:self.num_envs]
+
     def _respawn_now(self):
         if self.respawn is not None:
             return bool(self.respawn)

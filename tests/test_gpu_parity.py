@@ -1267,7 +1267,14 @@ def test_object_position_attribute_follows_the_reference(dx):
     env.object_position = [0.01, -0.02, 0.07]
     env.reset(seed=2)
     assert np.array_equal(env.object_position, np.array([0.01, -0.02, 0.07], np.float32))
+    obs, _ = env.reset(seed=0)
+    obs, *_ = env.step(np.full(15, -0.5, np.float32))
+    assert np.array_equal(env.joint_positions, obs[0:15]) and np.array_equal(env.joint_velocities, obs[15:30])
+    assert np.array_equal(env.object_velocity, obs[37:40]) and np.array_equal(env.contacts, obs[40:45] > 0.5)
+    assert env.step_count == 1 and env.joint_positions.dtype == np.float32 and env.contacts.dtype == bool
     batch = dx.BatchedManipulationEnv(64, "cuda")
     assert batch.object_position is None
     batch.reset(seed=3)
     assert tuple(batch.object_position.shape) == (64, 3) and batch.object_position.is_cuda
+    assert tuple(batch.joint_positions.shape) == (64, 15) and tuple(batch.contacts.shape) == (64, 5)
+    assert tuple(batch.step_count.shape) == (64,) and int(batch.step_count.sum()) == 0
