@@ -72,13 +72,20 @@ def _reward_spec(reward_type, reward_shaping):
             return 0, default
         return (1 if reward_type == "dense" else 0), default
     names = ("distance_weight", "contact_weight", "closure_weight", "stability_weight")
-    if all(hasattr(reward_shaping, k) for k in names):
+    cls = type(reward_shaping).__name__
+    if all(hasattr(reward_shaping, k) for k in names) and (cls == "RewardShaping" or not callable(getattr(reward_shaping, "compute", None))):
         return 1, tuple(float(getattr(reward_shaping, k)) for k in names)
-    if type(reward_shaping).__name__ == "SparseReward":
+    if cls == "SparseReward":
         return 0, default
+    if callable(getattr(reward_shaping, "compute", None)):
+        # a user's own reward class (the duck type of envs/manipulation_env.py:318-325): arbitrary Python cannot be fused
+        # into the kernel; BatchedManipulationEnv calls it on the host for num_envs == 1
+        return _CUSTOM_REWARD, default
     raise NotImplementedError(
-        "reward_shaping objects other than RewardShaping(weights) / SparseReward cannot be fused "
-        "into the step kernel; there is no CPU path to call arbitrary Python reward code")
+        "reward_shaping must be RewardShaping(weights), SparseReward or an object with a compute(...) method")
+
+
+_CUSTOM_REWARD = -1
 
 
 class BatchedManipulationEnv:
@@ -131,6 +138,13 @@ class BatchedManipulationEnv:
         self.reward_type = reward_type
         self.reward_shaping = reward_shaping
         self._reward_code, self._weights = _reward_spec(reward_type, reward_shaping)
+        self._custom_reward = None
+        if self._reward_code == _CUSTOM_REWARD:
+            if int(num_envs) != 1:
+                raise NotImplementedError(
+                    "a custom Python reward_shaping object is called on the host and therefore only supported with "
+                    "num_envs == 1; batched envs fuse RewardShaping(weights) / SparseReward into the step kernel")
+            self._custom_reward, self._reward_code = reward_shaping, 1
         self.auto_reset = bool(auto_reset)
         self.respawn = respawn
         self.loop_max_steps = int(loop_max_steps)
@@ -426,6 +440,8 @@ class BatchedManipulationEnv:
                     self._ptr(mask), int(respawn), self._stream()), "dexsim_reset_philox")
             self._spawned = True
             self._did_reset = True
+            if self._custom_reward is not None and callable(getattr(self._custom_reward, "reset", None)):
+                self._custom_reward.reset()                  # envs/manipulation_env.py:177
             if mask is None:
                 self._rollout_steps = 0
                 if getattr(self, "_ep_log_count", None) is not None:
@@ -716,12 +732,22 @@ class BatchedManipulationEnv:
             "num_contacts": int(h[48]),
             "curriculum": {"object_size": float(h[53]), "object_mass": float(h[54]), "friction_coefficient": float(h[55])},
         }
-        if not after_reset and self._comps is not None:
+        reward = float(h[45])
+        if not after_reset and self._custom_reward is not None:
+            # envs/manipulation_env.py:297-325: finger tips as the reference builds them (float32 sum of a finger's
+            # joints, "* 0.1" in float32, broadcast into a float64 triple), then the user's compute()
+            jp = obs[0:15]
+            tips = np.stack([np.zeros(3) + np.sum(jp[3 * f:3 * f + 3]) * 0.1 for f in range(5)])
+            comps = self._custom_reward.compute(joint_positions=jp, finger_tips=tips, object_position=h[50:53].copy(),
+                                                contacts=obs[40:45].copy(), num_fingers=5, joints_per_finger=3)
+            reward = comps["total"]
+            info["reward_components"] = comps
+        elif not after_reset and self._comps is not None:
             info["reward_components"] = {"total": float(h[45]), "distance": float(h[56]), "contact": float(h[57]),
                                          "closure": float(h[58]), "stability": float(h[59])}
         if self.info_success and not after_reset:
             info["success"] = bool(h[46])
-        return obs, float(h[45]), bool(h[46]), bool(h[47]), info
+        return obs, reward, bool(h[46]), bool(h[47]), info
 
     def _emit_obs(self, reset=False, noisy=False):
         n = self.num_envs

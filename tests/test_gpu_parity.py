@@ -1278,3 +1278,46 @@ def test_object_position_attribute_follows_the_reference(dx):
     assert tuple(batch.object_position.shape) == (64, 3) and batch.object_position.is_cuda
     assert tuple(batch.joint_positions.shape) == (64, 15) and tuple(batch.contacts.shape) == (64, 5)
     assert tuple(batch.step_count.shape) == (64,) and int(batch.step_count.sum()) == 0
+
+
+def test_custom_python_reward_object_on_the_single_env_path(dx):
+    """a user's own reward class (the compute() duck type of envs/manipulation_env.py:318-325) is
+    called on the host for num_envs == 1 with exactly the arguments the reference passes; batched envs refuse it."""
+    from oracle import ref_harness
+    if not ref_harness.available():
+        pytest.skip("reference (source or byte-compiled) not present")
+    R = ref_harness.load()
+
+    class ShapedByHeight:
+        def __init__(self):
+            self.calls, self.resets = 0, 0
+
+        def reset(self):
+            self.resets += 1
+
+        def compute(self, joint_positions, finger_tips, object_position, contacts, num_fingers, joints_per_finger):
+            self.calls += 1
+            d = np.linalg.norm(finger_tips - object_position, axis=1)
+            total = float(np.exp(-3.0 * d.mean()) + 0.25 * contacts.sum() - 0.1 * abs(float(object_position[2]))
+                          + 0.01 * float(np.abs(joint_positions).sum()))
+            return {"total": total, "mean_distance": float(d.mean()), "n": int(num_fingers * joints_per_finger)}
+
+    r_ref, r_new = ShapedByHeight(), ShapedByHeight()
+    ref = R.DexterousManipulationEnv(reward_shaping=r_ref, max_episode_steps=40, curriculum_config=R.CurriculumConfig.easy())
+    new = dx.BatchedManipulationEnv(1, "cuda", reward_shaping=r_new, max_episode_steps=40, curriculum_config=dx.CurriculumConfig.easy())
+    rng = np.random.default_rng(5)
+    for seed in (3, 4):
+        o0, _ = ref.reset(seed=seed)
+        o1, _ = new.reset(seed=seed)
+        assert np.array_equal(o0, o1)
+        for t in range(40):
+            a = rng.uniform(-1.0, 0.3, 15).astype(np.float32)
+            s0, s1 = ref.step(a), new.step(a)
+            assert np.array_equal(s0[0], s1[0]) and s0[2] == s1[2] and s0[3] == s1[3]
+            assert s1[1] == pytest.approx(s0[1], rel=1e-12, abs=1e-12)
+            assert s1[4]["reward_components"]["mean_distance"] == pytest.approx(s0[4]["reward_components"]["mean_distance"], rel=1e-12)
+            if s0[2] or s0[3]:
+                break
+    assert r_new.calls == r_ref.calls > 10 and r_new.resets == r_ref.resets == 2
+    with pytest.raises(NotImplementedError):
+        dx.BatchedManipulationEnv(8, "cuda", reward_shaping=ShapedByHeight())
