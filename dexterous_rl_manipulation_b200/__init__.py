@@ -9,7 +9,7 @@ Importing the package loads libdexsim_b200.so and raises if it is missing: no CP
 from . import _lib
 from ._lib import (CNT_EPISODES, CNT_LABEL_METRICS, CNT_LABEL_TAXONOMY, CNT_SUCCESSES, CNT_SUM_FINAL_CONTACTS,
                    CNT_SUM_STEPS, CNT_SUM_STEPS_SQ, CNT_VAR_TIES, LABEL_NONE, LABELS_METRICS, LABELS_TAXONOMY,
-                   NCOUNTERS, DexsimError, classify_summary)
+                   NCOUNTERS, DexsimError, classify_counts, classify_summary)
 from .config import CurriculumConfig, group_from_config, group_table
 
 import sys as _sys
@@ -30,7 +30,7 @@ DexterousManipulationEnv = BatchedManipulationEnv   # the reference's class name
 
 __all__ = [
     "BatchedManipulationEnv", "DexterousManipulationEnv", "Box", "CurriculumConfig", "group_from_config",
-    "group_table", "classify_summary", "evaluation", "training", "BatchedCurriculumDriver", "CurriculumScheduler", "DexsimError", "distributed", "LABELS_METRICS", "LABELS_TAXONOMY",
+    "group_table", "classify_summary", "classify_counts", "evaluation", "training", "BatchedCurriculumDriver", "CurriculumScheduler", "DexsimError", "distributed", "LABELS_METRICS", "LABELS_TAXONOMY",
     "LABEL_NONE", "NCOUNTERS", "CNT_EPISODES", "CNT_SUCCESSES", "CNT_SUM_STEPS", "CNT_SUM_FINAL_CONTACTS",
     "CNT_LABEL_METRICS", "CNT_LABEL_TAXONOMY", "CNT_VAR_TIES", "CNT_SUM_STEPS_SQ",
 ]

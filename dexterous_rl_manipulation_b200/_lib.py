@@ -11,7 +11,7 @@ import numpy as _np
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("DEXSIM_LIB_PATH") or os.path.join(HERE, "libdexsim_b200.so")   # env override: kernel experiments only
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 NJ, NF, OBS = 15, 5, 45
 NCOUNTERS = 18
 MAX_GROUPS = 256
@@ -25,6 +25,7 @@ EPISODE_RECORD_DTYPE = _np.dtype([("env_gid", "u4"), ("episode", "u4"), ("steps"
                                   ("final_contacts", "u1"), ("label_metrics", "u1"), ("label_taxonomy", "u1"),
                                   ("episode_reward", "f8"), ("t_end", "u4"), ("var_tie", "u4")])
 HOST_SKIP_QUAT = 1
+SCHED_WORDS = 64
 ROLLOUT_NO_DYN_NOISE = 1
 
 # value strings of FailureType (evaluation/metrics.py:15-22) / FailureMode
@@ -65,7 +66,7 @@ class DexsimStepIO(C.Structure):
                 ("reward", C.c_void_p), ("reward_comps", C.c_void_p), ("terminated", C.c_void_p),
                 ("truncated", C.c_void_p), ("num_contacts", C.c_void_p), ("finished", C.c_void_p),
                 ("counters", C.c_void_p), ("ret_sums", C.c_void_p), ("reward64", C.c_void_p),
-                ("sigma_dyn", C.c_float), ("sigma_obs", C.c_float)]
+                ("sigma_dyn", C.c_float), ("sigma_obs", C.c_float), ("sched", C.c_void_p)]
 
 
 class DexsimEpisodeRecord(C.Structure):
@@ -140,7 +141,7 @@ def lib():
     L.dexsim_pack_env_tagged.argtypes = [C.POINTER(DexsimState), C.POINTER(DexsimStepIO), i64, i32, vp, C.c_double, vp]
     L.dexsim_step_single.argtypes = [C.POINTER(DexsimState), C.POINTER(DexsimParams), vp, vp, C.POINTER(DexsimStepIO), vp,
                                      C.c_double, vp]
-    L.dexsim_classify_summary.argtypes = [C.POINTER(DexsimEpisodeSummary), i32, i32, C.POINTER(i32),
+    L.dexsim_classify_summary.argtypes = [C.POINTER(DexsimEpisodeSummary), vp, i32, i32, C.POINTER(i32),
                                           C.POINTER(i32), C.POINTER(i32)]
     L.dexsim_step_host.argtypes = [C.POINTER(DexsimState), C.POINTER(DexsimParams), vp, vp, C.POINTER(DexsimStepIO),
                                    vp, vp, vp, vp, vp, vp, i32, i32, vp]
@@ -178,13 +179,36 @@ def check(code, where):
 
 
 def classify_summary(success, episode_steps, num_contacts, final_contacts, hist_len, max_count, sum_counts,
-                     sum_sq_counts, first5_sum, last5_sum, max_steps=200, success_threshold=3):
+                     sum_sq_counts, first5_sum, last5_sum, max_steps=200, success_threshold=3, counts=None):
     """Host entry point: both failure labels from an episode summary.
-    Returns (metrics.py label code, taxonomy label code, var_tie); LABEL_NONE (255) = success."""
+    Returns (metrics.py label code, taxonomy label code, var_tie); LABEL_NONE (255) = success.
+    ``counts``: the per-step contact counts (len == hist_len).  With them an exact variance tie is decided by
+    NumPy's own np.var arithmetic (var_tie == 2, labels bit-exact); without them var_tie == 1 marks the label
+    as resolved in exact arithmetic only."""
     s = DexsimEpisodeSummary(int(bool(success)), int(episode_steps), int(num_contacts), int(final_contacts),
                              int(hist_len), int(max_count), int(sum_counts), int(sum_sq_counts), int(first5_sum),
                              int(last5_sum))
     a, b, t = C.c_int32(), C.c_int32(), C.c_int32()
-    check(lib().dexsim_classify_summary(C.byref(s), int(max_steps), int(success_threshold), C.byref(a), C.byref(b),
+    ptr = None
+    if counts is not None:
+        buf = _np.ascontiguousarray(counts, dtype=_np.uint8)
+        if buf.shape != (int(hist_len),):
+            raise ValueError("counts must hold hist_len entries")
+        ptr = buf.ctypes.data
+    check(lib().dexsim_classify_summary(C.byref(s), ptr, int(max_steps), int(success_threshold), C.byref(a), C.byref(b),
                                         C.byref(t)), "dexsim_classify_summary")
     return a.value, b.value, t.value
+
+
+def classify_counts(success, episode_steps, num_contacts, final_contacts, counts, max_steps=200, success_threshold=3):
+    """Both failure labels of one episode from its per-step contact counts -- what
+    EvaluationMetrics.classify_failure (evaluation/metrics.py:39-96) and FailureClassifier.classify
+    (evaluation/failure_taxonomy.py:156-239) return for ``contact_history = count-encoded rows``.
+    Returns (metrics label code, taxonomy label code); bit-exact including variance ties."""
+    c = _np.ascontiguousarray(counts, dtype=_np.uint8)
+    n = int(c.shape[0])
+    w = c.astype(_np.int64)
+    la, lb, _ = classify_summary(success, episode_steps, num_contacts, final_contacts, n, int(w.max()) if n else 0,
+                                 int(w.sum()), int((w * w).sum()), int(w[:5].sum()), int(w[-5:].sum()) if n else 0,
+                                 max_steps, success_threshold, counts=c)
+    return la, lb

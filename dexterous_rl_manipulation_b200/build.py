@@ -5,6 +5,8 @@ produces ``dexterous_rl_manipulation_b200/libdexsim_b200.so`` next to this file.
 cross-compiles without a GPU.  ``-fmad=false`` is part of the numerics contract: the reference
 rounds every product and sum separately (DESIGN.md "Numerics").
 """
+import hashlib
+import json
 import os
 import shutil
 import subprocess
@@ -15,6 +17,7 @@ SRC = os.path.join(HERE, "csrc", "dexsim_kernels.cu")
 DEPS = [SRC] + [os.path.join(HERE, "csrc", h) for h in ("dexsim_core.cuh", "dexsim_step_tma.cuh", "dexsim_rollout_split.cuh")] \
     + [os.path.join(HERE, "..", "include", "dexsim.h")]
 OUT = os.path.join(HERE, "libdexsim_b200.so")
+INFO = os.path.join(HERE, "BUILD_INFO.json")       # written next to the library: source hash + the nvcc command line
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
@@ -33,23 +36,55 @@ def nvcc_path():
     return cand
 
 
+def sources_sha256():
+    """Hash of everything the library is compiled from (file names + contents, fixed order)."""
+    h = hashlib.sha256()
+    for d in DEPS:
+        h.update(os.path.basename(d).encode() + b"\0")
+        with open(d, "rb") as fh:
+            h.update(fh.read())
+    return h.hexdigest()
+
+
+def build_info():
+    """What the library next to this file was built from, and whether that is the tree's current source."""
+    info = {}
+    try:
+        with open(INFO) as fh:
+            info = json.load(fh)
+    except (OSError, ValueError):
+        pass
+    try:
+        info["tree_sha256"] = sources_sha256()
+    except OSError:
+        info["tree_sha256"] = None          # sources not shipped: nothing to compare with
+    info["fresh"] = bool(info.get("sources_sha256")) and info.get("sources_sha256") == info["tree_sha256"]
+    return info
+
+
 def needs_build():
     if not os.path.exists(OUT):
         return True
-    t = os.path.getmtime(OUT)
-    return any(os.path.exists(d) and os.path.getmtime(d) > t for d in DEPS)
+    return not build_info()["fresh"]
 
 
-def build(force=False, verbose=False):
-    if not force and not needs_build():
+def build(force=False, verbose=False, out=None, defines=()):
+    """``out`` / ``defines``: experiment builds (``-DNAME`` variants written somewhere else, loaded through
+    DEXSIM_LIB_PATH by the timing tools); the product is the default call."""
+    if out is None and not force and not needs_build():
         return OUT
-    cmd = [nvcc_path()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", OUT, SRC]
+    out = out or OUT
+    cmd = [nvcc_path()] + NVCC_FLAGS + [f"-D{d}" for d in defines] + (["-Xptxas", "-v"] if verbose else []) + ["-o", out, SRC]
     proc = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if verbose or proc.returncode != 0:
         sys.stderr.write(proc.stdout)
     if proc.returncode != 0:
         raise RuntimeError("nvcc failed building libdexsim_b200.so")
-    return OUT
+    if out == OUT:
+        with open(INFO, "w") as fh:
+            json.dump({"sources_sha256": sources_sha256(), "nvcc": " ".join(cmd[:1] + [c for c in cmd[1:] if c != out and c != SRC]),
+                       "flags": NVCC_FLAGS, "defines": list(defines)}, fh, indent=1)
+    return out
 
 
 if __name__ == "__main__":

@@ -318,10 +318,16 @@ DEXSIM_D void normal_rows(uint64_t seed, uint32_t gid, uint32_t episode, uint32_
 //   w1: [16:0] sum of squares  [31:17] last five counts, 3 bits each (newest in the low bits)
 struct EpStats { uint32_t w0, w1; };
 
+// The packed sums hold episodes of up to EPSTATS_MAX_STEPS steps (5,242 steps of 5 contacts reach 2^17 - 1 in the sum of
+// squares); the entry points reject longer tracked episodes (DEXSIM_E_PARAM) and the fields saturate instead of wrapping
+// if a caller steps a tracked env past that without resetting it.
+constexpr int EPSTATS_MAX_STEPS = 5242;
+
 DEXSIM_HD void epstats_push(EpStats& s, int hist_len_before, int n_c) {
     uint32_t sum = s.w0 & 0xFFFFu, first5 = (s.w0 >> 16) & 0x1Fu, mx = (s.w0 >> 21) & 0x7u;
     uint32_t sq = s.w1 & 0x1FFFFu, ring = s.w1 >> 17;
     sum += (uint32_t)n_c; sq += (uint32_t)(n_c * n_c);
+    sum = sum > 0xFFFFu ? 0xFFFFu : sum; sq = sq > 0x1FFFFu ? 0x1FFFFu : sq;
     if (hist_len_before < 5) first5 += (uint32_t)n_c;
     mx = ((uint32_t)n_c > mx) ? (uint32_t)n_c : mx;
     ring = ((ring << 3) | (uint32_t)n_c) & 0x7FFFu;
@@ -336,19 +342,98 @@ DEXSIM_HD void epstats_unpack(const EpStats& s, int& sum, int& sq, int& first5, 
     last5 = (int)((ring & 7u) + ((ring >> 3) & 7u) + ((ring >> 6) & 7u) + ((ring >> 9) & 7u) + ((ring >> 12) & 7u));
 }
 
-// Both classifiers from the summary.  var = (n*Q - S^2)/n^2 is compared as integers; an exact
-// tie with a threshold (where numpy's float64 pairwise sum may land on either side) sets
-// var_tie and is resolved as in exact arithmetic.  The slippage trend reproduces
-// np.mean(last5) - np.mean(first5) with two IEEE divisions and one subtraction (SURVEY.md 8a-12).
+// ---- np.var of the per-step contact counts, bit for bit -----------------------------------------------------
+// Both classifiers threshold np.var(contact_counts) (evaluation/metrics.py:77-78, evaluation/failure_taxonomy.py:189,
+// :219-230).  For a list of ints NumPy computes (numpy/_core/_methods.py::_var, numpy 2.3.5): float64 mean = sum / n
+// (the integer sum is exact), x = (count - mean)^2 element-wise, then the float64 PAIRWISE sum of x
+// (numpy/_core/src/umath/loops_utils.h.src: plain loop below 8 elements, 8 interleaved accumulators up to 128,
+// recursive halving rounded down to a multiple of 8 above), divided by n.  The order of the counts matters for the
+// last bits, so this needs the history itself; the packed summary cannot reproduce it.
+struct CountsView {               // per-step contact counts of ONE episode: count(k) = base[k * stride]
+    const uint8_t* base;
+    int64_t stride;
+    DEXSIM_HD double sq_dev(int64_t k, double mean) const {
+#if defined(__CUDA_ARCH__)
+        const double d = __dsub_rn((double)base[k * stride], mean);
+        return __dmul_rn(d, d);
+#else
+        const double d = (double)base[k * stride] - mean;
+        return d * d;
+#endif
+    }
+};
+
+DEXSIM_HD double np_add(double a, double b) {
+#if defined(__CUDA_ARCH__)
+    return __dadd_rn(a, b);
+#else
+    return a + b;
+#endif
+}
+
+// pairwise sum of the squared deviations of counts [lo, lo + n).  Recursive like NumPy's (depth log2(n / 128): 1 for the
+// 200-step episodes of every shipped config); only ever reached on an exact variance tie, so it is kept out of line.
+#if defined(__CUDACC__)
+__host__ __device__ __noinline__
+#endif
+static double np_pairwise_sq_sum(const CountsView& c, int64_t lo, int64_t n, double mean) {
+    if (n < 8) {
+        double res = -0.0;
+        for (int64_t i = 0; i < n; ++i) res = np_add(res, c.sq_dev(lo + i, mean));
+        return res;
+    }
+    if (n <= 128) {
+        double r[8];
+        for (int k = 0; k < 8; ++k) r[k] = c.sq_dev(lo + k, mean);
+        int64_t i;
+        for (i = 8; i < n - (n % 8); i += 8)
+            for (int k = 0; k < 8; ++k) r[k] = np_add(r[k], c.sq_dev(lo + i + k, mean));
+        double res = np_add(np_add(np_add(r[0], r[1]), np_add(r[2], r[3])), np_add(np_add(r[4], r[5]), np_add(r[6], r[7])));
+        for (; i < n; ++i) res = np_add(res, c.sq_dev(lo + i, mean));
+        return res;
+    }
+    int64_t n2 = n / 2;
+    n2 -= n2 % 8;
+    const double left = np_pairwise_sq_sum(c, lo, n2, mean);
+    return np_add(left, np_pairwise_sq_sum(c, lo + n2, n - n2, mean));
+}
+
+#if defined(__CUDACC__)
+__host__ __device__ __noinline__
+#endif
+static double np_var_counts(const CountsView& c, int64_t n) {
+    long long isum = 0;
+    for (int64_t i = 0; i < n; ++i) isum += c.base[i * c.stride];
+#if defined(__CUDA_ARCH__)
+    const double mean = __ddiv_rn((double)isum, (double)n);
+    return __ddiv_rn(np_pairwise_sq_sum(c, 0, n, mean), (double)n);
+#else
+    const double mean = (double)isum / (double)n;
+    return np_pairwise_sq_sum(c, 0, n, mean) / (double)n;
+#endif
+}
+
+// Both classifiers from the summary.  var = (n*Q - S^2)/n^2 is compared as integers, which decides every case
+// except an EXACT tie with a threshold: there NumPy's float64 pairwise sum may land on either side
+// (SURVEY.md 8a-12).  With the history at hand (`counts`, hist_len entries) a tie is decided by np.var itself
+// (np_var_counts) and var_tie = 2; without it the tie is resolved as in exact arithmetic and var_tie = 1 flags the
+// label as unconfirmed (DEXSIM_CNT_VAR_TIES counts those).  The slippage trend reproduces
+// np.mean(last5) - np.mean(first5) with two IEEE divisions and one subtraction.
 DEXSIM_HD void classify_summary(const DexsimEpisodeSummary& e, int max_steps, int thr,
-                                int& label_a, int& label_b, int& var_tie) {
+                                int& label_a, int& label_b, int& var_tie, const CountsView* counts = nullptr) {
     var_tie = 0;
     label_a = label_b = DEXSIM_LABEL_NONE;
     if (e.success) return;                                        // metrics.py:53-55, failure_taxonomy.py:171-173
     const long long n = e.hist_len;
     const long long vnum = n * (long long)e.sum_sq_counts - (long long)e.sum_counts * e.sum_counts;  // var * n^2
-    const bool var_gt2 = vnum > 2 * n * n, var_lt1 = vnum < n * n;
+    bool var_gt2 = vnum > 2 * n * n, var_lt1 = vnum < n * n;
     const bool tie2 = (n > 5) && (vnum == 2 * n * n), tie1 = (n > 1) && (vnum == n * n);
+    const int tie_flag = (counts && counts->base) ? 2 : 1;
+    if ((tie2 || tie1) && tie_flag == 2) {
+        const double v = np_var_counts(*counts, n);
+        var_gt2 = v > 2.0;                                        // metrics.py:78, failure_taxonomy.py:219
+        var_lt1 = v < 1.0;                                        // failure_taxonomy.py:228
+    }
 #if defined(__CUDA_ARCH__)
     const double trend = __dsub_rn(__ddiv_rn((double)e.last5_sum, 5.0), __ddiv_rn((double)e.first5_sum, 5.0));
 #else
@@ -362,11 +447,9 @@ DEXSIM_HD void classify_summary(const DexsimEpisodeSummary& e, int max_steps, in
         else {
             lab = -1;
             if (n > 5) {
+                if (tie2) var_tie = tie_flag;
                 if (var_gt2) lab = DEXSIM_LABEL_UNSTABLE;
-                else {
-                    if (tie2) var_tie = 1;
-                    if (n > 10 && trend < -1.0) lab = DEXSIM_LABEL_SLIPPAGE;
-                }
+                else if (n > 10 && trend < -1.0) lab = DEXSIM_LABEL_SLIPPAGE;
             }
             if (lab < 0) lab = (e.num_contacts > 0 && e.num_contacts < thr) ? DEXSIM_LABEL_MISALIGNED
                                                                             : DEXSIM_LABEL_INSUFFICIENT;
@@ -384,12 +467,14 @@ DEXSIM_HD void classify_summary(const DexsimEpisodeSummary& e, int max_steps, in
             lab = -1;
             if (n > 5) {
                 if (n > 10 && trend < -1.0 && max_c >= 1) lab = DEXSIM_LABEL_SLIPPAGE;
-                else if (var_gt2) lab = DEXSIM_LABEL_UNSTABLE;
-                else if (tie2) var_tie = 1;
+                else {
+                    if (tie2) var_tie = tie_flag;
+                    if (var_gt2) lab = DEXSIM_LABEL_UNSTABLE;
+                }
             }
             if (lab < 0 && e.num_contacts >= 1 && e.num_contacts <= 2) {
                 const bool lt1 = has_var ? var_lt1 : true;
-                if (has_var && tie1) var_tie = 1;
+                if (has_var && tie1) var_tie = tie_flag;
                 if (lt1) lab = DEXSIM_LABEL_MISALIGNED;
             }
             if (lab < 0) lab = DEXSIM_LABEL_INSUFFICIENT;

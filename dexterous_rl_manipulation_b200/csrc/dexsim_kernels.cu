@@ -22,6 +22,7 @@ namespace dexsim {
 #define DEXSIM_STEP_MIN_BLOCKS 2
 #endif
 constexpr int STEP_THREADS = 256;
+
 constexpr int SMEM_GROUPS_MAX = 64;     // group table + block counters are staged in smem up to this many groups
 
 // ---- state <-> registers -----------------------------------------------------------------------
@@ -116,7 +117,7 @@ __device__ __forceinline__ void record_episode(unsigned long long* cnt, double* 
     if (final_c) atomicAdd(&cnt[DEXSIM_CNT_SUM_FINAL_CONTACTS], (unsigned long long)final_c);
     if (la != DEXSIM_LABEL_NONE) atomicAdd(&cnt[DEXSIM_CNT_LABEL_METRICS + la], 1ull);
     if (lb != DEXSIM_LABEL_NONE) atomicAdd(&cnt[DEXSIM_CNT_LABEL_TAXONOMY + lb], 1ull);
-    if (tie) atomicAdd(&cnt[DEXSIM_CNT_VAR_TIES], 1ull);
+    if (tie == 1) atomicAdd(&cnt[DEXSIM_CNT_VAR_TIES], 1ull);       // 2 = decided by np.var on the history: not in doubt
     if (rs) { atomicAdd(&rs[0], ret); atomicAdd(&rs[1], __dmul_rn(ret, ret)); }
 }
 
@@ -147,6 +148,8 @@ __device__ __forceinline__ void finish_episode(const EnvRegs& e, const DexsimPar
     epstats_unpack(es, sum, sq, f5, l5, mx);
     s.max_count = mx; s.sum_counts = sum; s.sum_sq_counts = sq; s.first5_sum = f5; s.last5_sum = l5;
     int la, lb, tie;
+    // an exact variance tie is only flagged here (tie == 1); when the launch records the history, resolve_ties_kernel
+    // decides it afterwards with np.var's own arithmetic -- kept out of this kernel's registers and stack
     classify_summary(s, p.loop_max_steps > 0 ? p.loop_max_steps : p.max_episode_steps, p.success_threshold, la, lb, tie);
     if (cnt) record_episode(cnt, rs, s.success, e.sc, n_c, la, lb, tie, ep_return);
     if (log && log->rec) {
@@ -174,6 +177,17 @@ __device__ __forceinline__ void finish_and_reset(EnvRegs& e, const DexsimParams&
     env_reset(e, jp0, size, friction, pos, /*keep_pos=*/!p.respawn);
     ep_return = 0.0;
     es.w0 = 0u; es.w1 = 0u;
+}
+
+// Observation entry `row` (envs/manipulation_env.py:254-264) of an env held in registers; `row` is a compile-time
+// constant wherever this is called from an unrolled loop.
+__device__ __forceinline__ float obs_entry(const EnvRegs& e, const int row) {
+    if (row < DEXSIM_ROW_JV) return e.jp[row - DEXSIM_ROW_JP];
+    if (row < DEXSIM_ROW_OP) return e.jv[row - DEXSIM_ROW_JV];
+    if (row < DEXSIM_ROW_QUAT) return (float)e.op[row - DEXSIM_ROW_OP];
+    if (row < DEXSIM_ROW_OV) return row == DEXSIM_ROW_QUAT ? 1.0f : 0.0f;
+    if (row < DEXSIM_ROW_CONTACT) return e.ov[row - DEXSIM_ROW_OV];
+    return ((e.cmask >> (row - DEXSIM_ROW_CONTACT)) & 1u) ? 1.0f : 0.0f;
 }
 
 }  // namespace dexsim
@@ -230,17 +244,6 @@ __global__ void pack_env_kernel(const DexsimState st, const DexsimStepIO io, con
 // memory with coalesced float4 reads (15 is odd, so the per-thread reads are bank-conflict free).
 // EXTRAS: noise, reward components, episode tracking, auto-reset -- the plain path carries none
 // of their registers or branches.
-// Observation entry `row` (envs/manipulation_env.py:254-264) of an env held in registers; `row` is a compile-time
-// constant wherever this is called from an unrolled loop.
-__device__ __forceinline__ float obs_entry(const EnvRegs& e, const int row) {
-    if (row < DEXSIM_ROW_JV) return e.jp[row - DEXSIM_ROW_JP];
-    if (row < DEXSIM_ROW_OP) return e.jv[row - DEXSIM_ROW_JV];
-    if (row < DEXSIM_ROW_QUAT) return (float)e.op[row - DEXSIM_ROW_OP];
-    if (row < DEXSIM_ROW_OV) return row == DEXSIM_ROW_QUAT ? 1.0f : 0.0f;
-    if (row < DEXSIM_ROW_CONTACT) return e.ov[row - DEXSIM_ROW_OV];
-    return ((e.cmask >> (row - DEXSIM_ROW_CONTACT)) & 1u) ? 1.0f : 0.0f;
-}
-
 template <bool DENSE, bool AOS, bool EXTRAS>
 __global__ void __launch_bounds__(STEP_THREADS, DEXSIM_STEP_MIN_BLOCKS)
 step_kernel(const DexsimState st, const DexsimParams p, const DexsimGroup* __restrict__ groups,
@@ -269,7 +272,9 @@ step_kernel(const DexsimState st, const DexsimParams p, const DexsimGroup* __res
             const int64_t tile_floats = (((n - base) < STEP_THREADS) ? (n - base) : STEP_THREADS) * NJ;
             const float* __restrict__ src = io.action + base * NJ;
             __syncthreads();                         // previous tile fully consumed
-            const int64_t nvec = tile_floats >> 2;
+            // float4 reads need a 16-byte aligned base (a tile starts 256 * 60 bytes further, still aligned); any
+            // other base (e.g. an [n,15] slice starting at an odd env) takes the scalar loop below for the whole tile
+            const int64_t nvec = (reinterpret_cast<uintptr_t>(io.action) & 15u) ? 0 : (tile_floats >> 2);
             for (int64_t v = threadIdx.x; v < nvec; v += STEP_THREADS)
                 reinterpret_cast<float4*>(sh_act)[v] = __ldg(reinterpret_cast<const float4*>(src) + v);
             for (int64_t r = (nvec << 2) + threadIdx.x; r < tile_floats; r += STEP_THREADS) sh_act[r] = __ldg(src + r);
@@ -632,6 +637,54 @@ rollout_kernel(const DexsimState st, const DexsimParams p, const DexsimGroup* __
     }
 }
 
+// ---- exact variance ties -----------------------------------------------------------------------------------
+// Runs after a rollout launch that recorded both the episode log and the per-step contact-count history: every
+// logged episode whose label met an exact variance tie (var_tie == 1, decided in exact arithmetic by the rollout
+// kernel) is classified again with np.var's own pairwise float64 arithmetic on its history (classify_summary with
+// counts), the record and the per-group label counters are corrected and var_tie becomes 2.  Idempotent; ties are
+// rare (no shipped config produces one), so this is a scan of the log and nothing else.
+__global__ void resolve_ties_kernel(const DexsimParams p, const uint16_t* __restrict__ group_of_env, const DexsimRolloutIO rio,
+                                    const int64_t n, const int64_t ld) {
+    const unsigned long long produced = *reinterpret_cast<const unsigned long long*>(rio.ep_log_count);
+    const long long kept = produced < (unsigned long long)rio.ep_log_capacity ? (long long)produced : rio.ep_log_capacity;
+    for (long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x; q < kept; q += (long long)gridDim.x * blockDim.x) {
+        DexsimEpisodeRecord rec = rio.ep_log[q];
+        if (rec.var_tie != 1u) continue;
+        const int64_t i = (int64_t)(uint32_t)(rec.env_gid - (uint32_t)p.env_gid0);   // gids wrap at 2^32 like the Philox counter word
+        const int64_t first = (int64_t)rec.t_end + 1 - rec.steps;                     // history row of the episode's first step
+        if (i >= n || first < 0 || (int64_t)rec.t_end >= rio.hist_steps) continue;
+        const CountsView cv{rio.hist + first * ld + i, ld};
+        DexsimEpisodeSummary s;
+        s.success = rec.success; s.episode_steps = rec.steps; s.num_contacts = rec.final_contacts;
+        s.final_contacts = rec.final_contacts; s.hist_len = rec.steps;
+        int sum = 0, sq = 0, mx = 0, f5 = 0, l5 = 0;
+        for (int t = 0; t < rec.steps; ++t) {
+            const int c = cv.base[(int64_t)t * ld];
+            sum += c; sq += c * c; mx = c > mx ? c : mx;
+            if (t < 5) f5 += c;
+            if (t >= rec.steps - 5) l5 += c;
+        }
+        s.sum_counts = sum; s.sum_sq_counts = sq; s.max_count = mx; s.first5_sum = f5; s.last5_sum = l5;
+        int la, lb, tie;
+        classify_summary(s, p.loop_max_steps > 0 ? p.loop_max_steps : p.max_episode_steps, p.success_threshold, la, lb, tie, &cv);
+        if (rio.counters) {
+            const int g = group_of_env ? (int)group_of_env[i] : (int)(rec.env_gid % (uint32_t)p.num_groups);
+            unsigned long long* cnt = reinterpret_cast<unsigned long long*>(rio.counters) + (int64_t)g * DEXSIM_NCOUNTERS;
+            if (la != rec.label_metrics) {
+                if (rec.label_metrics != DEXSIM_LABEL_NONE) atomicAdd(&cnt[DEXSIM_CNT_LABEL_METRICS + rec.label_metrics], ~0ull);
+                if (la != DEXSIM_LABEL_NONE) atomicAdd(&cnt[DEXSIM_CNT_LABEL_METRICS + la], 1ull);
+            }
+            if (lb != rec.label_taxonomy) {
+                if (rec.label_taxonomy != DEXSIM_LABEL_NONE) atomicAdd(&cnt[DEXSIM_CNT_LABEL_TAXONOMY + rec.label_taxonomy], ~0ull);
+                if (lb != DEXSIM_LABEL_NONE) atomicAdd(&cnt[DEXSIM_CNT_LABEL_TAXONOMY + lb], 1ull);
+            }
+            atomicAdd(&cnt[DEXSIM_CNT_VAR_TIES], ~0ull);                  // no longer in doubt
+        }
+        rec.label_metrics = (uint8_t)la; rec.label_taxonomy = (uint8_t)lb; rec.var_tie = 2u;
+        rio.ep_log[q] = rec;
+    }
+}
+
 // ---- single-env read-back ------------------------------------------------------------------------------
 // ---- RNG exposure ------------------------------------------------------------------------------------
 __global__ void fill_policy_kernel(const DexsimState st, const DexsimParams p, int policy_kind, float* __restrict__ out) {
@@ -698,10 +751,17 @@ static int check_state(const DexsimState* st) {
     return 0;
 }
 
-static int check_params(const DexsimParams* p, bool need_groups, const DexsimGroup* groups) {
+static int check_params(const DexsimParams* p, bool need_groups, const DexsimGroup* groups, bool tracked = false) {
     if (!p) return DEXSIM_E_NULL;
     if (p->reward_type != 0 && p->reward_type != 1) return DEXSIM_E_PARAM;
     if (p->max_episode_steps < 0 || p->success_threshold < 0) return DEXSIM_E_PARAM;
+    if (tracked) {
+        // the packed per-env history summary (EpStats) holds episodes of up to EPSTATS_MAX_STEPS steps; an episode
+        // ends at the caller's loop bound or one step after max_episode_steps (truncation is reported one step late)
+        const int64_t longest = (p->loop_max_steps > 0 && p->loop_max_steps <= p->max_episode_steps)
+                                    ? p->loop_max_steps : (int64_t)p->max_episode_steps + 1;
+        if (longest > EPSTATS_MAX_STEPS) return DEXSIM_E_PARAM;
+    }
     if (need_groups) {
         if (p->num_groups < 1 || p->num_groups > DEXSIM_MAX_GROUPS) return DEXSIM_E_GROUPS;
         if (!groups) return DEXSIM_E_NULL;
@@ -727,13 +787,12 @@ static void launch_step_variant(bool extras, int grid, cudaStream_t s, const Dex
     else        step_kernel<DENSE, AOS, false><<<grid, STEP_THREADS, 0, s>>>(st, p, groups, goe, io);
 }
 
-template <bool DENSE, bool AOS, int TRACK, int STAGES, int GROUPS>
+template <bool DENSE, bool AOS, int TRACK, bool EXTRA, int STAGES>
 static int launch_tma_variant(int sm_count, cudaStream_t s, const DexsimState& st, const DexsimParams& p,
                               const DexsimGroup* groups, const uint16_t* goe, const DexsimStepIO& io,
                               const StepMaps& maps, int num_tiles) {
-    auto kern = step_tma_kernel<DENSE, AOS, TRACK, STAGES, GROUPS>;
-    constexpr int TMA_THREADS = tma_threads(GROUPS);
-    const size_t smem = (size_t)STAGES * STAGE_BYTES + (STAGES * GROUPS + STAGES) * sizeof(uint64_t) +
+    auto kern = step_tma_kernel<DENSE, AOS, TRACK, EXTRA, STAGES>;
+    const size_t smem = (size_t)STAGES * STAGE_BYTES + 2 * STAGES * (sizeof(uint64_t) + sizeof(int)) +
                         (TRACK ? TMA_GROUPS_MAX * (DEXSIM_NCOUNTERS * sizeof(unsigned long long) + 2 * sizeof(double)) : 0);
     // per template instantiation and per device: the shared-memory opt-in is a per-device function attribute
     static thread_local int occupancy[64] = {0};
@@ -766,25 +825,27 @@ static int step_impl_choice() {
     }
     return g_step_impl;
 }
-// Pipeline shape "<stages>x<compute groups>".  2x1 (3 CTAs per SM) is the product; 3x1 and 3x2 measured within
-// 1 % of it on B200 and are only built with -DDEXSIM_TMA_EXTRA_SHAPES, selected by
-// DEXSIM_TMA_SHAPE=3x1|3x2 for experiments.
-static int tma_shape_choice() {
-#ifdef DEXSIM_TMA_EXTRA_SHAPES
-    static int shape = -1;
-    if (shape < 0) {
-        const char* e = getenv("DEXSIM_TMA_SHAPE");
-        shape = (e && !strcmp(e, "3x1")) ? 31 : (e && !strcmp(e, "3x2")) ? 32 : 21;
+
+// Smallest batch the auto choice sends down the TMA pipeline (DEXSIM_TMA_MIN_ENVS overrides it for experiments).
+// Measured on B200 (tools/time_small.py, us per step, register-resident vs pipeline, hard curriculum):
+//   plain:   65,536 envs 6.2 vs 9.0;  98,304 9.6 vs 10.3;  131,072 10.3 vs 10.4;  196,608 14.4 vs 12.3;  262,144 18.5 vs 15.3
+//   counts:  65,536 10.2 vs 11.4;  98,304 13.7 vs 12.6;  131,072 15.1 vs 14.0;  196,608 20.2 vs 16.7
+//   tracked: 65,536 11.1 vs 12.6;  98,304 15.5 vs 13.6;  131,072 16.7 vs 16.1;  196,608 22.6 vs 19.1
+// Below the crossover the batch is L2-resident and a step is a launch plus one load-compute-store round trip, which
+// the register-resident kernel (more warps in flight, no ring to fill and drain) finishes sooner.
+static int64_t tma_min_envs(int track, bool extra) {
+    static int64_t forced = -2;
+    if (forced == -2) {
+        const char* e = getenv("DEXSIM_TMA_MIN_ENVS");
+        forced = e ? atoll(e) : -1;
     }
-    return shape;
-#else
-    return 21;
-#endif
+    int64_t v = forced >= 0 ? forced : ((track == 0 && !extra) ? 163840 : 81920);
+    return v < TILE ? TILE : v;
 }
 
 // track: 0 = plain step, 1 = full episode tracking (returns + history summaries -> labels), 2 = counts only
 static int launch_step_tma(const DexsimState* st, const DexsimParams* p, const DexsimGroup* groups, const uint16_t* goe,
-                           const DexsimStepIO* io, cudaStream_t s, int track, int sm_count) {
+                           const DexsimStepIO* io, cudaStream_t s, int track, bool extra, int sm_count) {
     // Tensor maps are pure functions of (base pointers, n, ld): a stepping loop re-encodes nothing.  One cached set
     // per host thread; the SoA action map is keyed by the action pointer too (AoS actions use 1-D bulk copies).
     struct MapCache { const void* obs; const void* op64; const void* act; int64_t n, ld; bool valid; StepMaps maps; };
@@ -808,23 +869,16 @@ static int launch_step_tma(const DexsimState* st, const DexsimParams* p, const D
     const StepMaps& maps = cache.maps;
     const int num_tiles = (int)((st->n + TILE - 1) / TILE);
     const bool dense = p->reward_type == 1;
-    const int shape = tma_shape_choice();
-    (void)shape;
-#ifdef DEXSIM_TMA_EXTRA_SHAPES
-#define DEXSIM_TMA_CASE(D, A, T)                                                                                 \
-    if (dense == D && aos == A && track == T)                                                                    \
-        return shape == 32 ? launch_tma_variant<D, A, T, 3, 2>(sm_count, s, *st, *p, groups, goe, *io, maps, num_tiles) \
-             : shape == 31 ? launch_tma_variant<D, A, T, 3, 1>(sm_count, s, *st, *p, groups, goe, *io, maps, num_tiles) \
-                           : launch_tma_variant<D, A, T, 2, 1>(sm_count, s, *st, *p, groups, goe, *io, maps, num_tiles);
-#else
-#define DEXSIM_TMA_CASE(D, A, T)                                                                                 \
-    if (dense == D && aos == A && track == T)                                                                    \
-        return launch_tma_variant<D, A, T, 2, 1>(sm_count, s, *st, *p, groups, goe, *io, maps, num_tiles);
-#endif
-    DEXSIM_TMA_CASE(true, true, 0) DEXSIM_TMA_CASE(true, true, 1) DEXSIM_TMA_CASE(true, true, 2)
-    DEXSIM_TMA_CASE(true, false, 0) DEXSIM_TMA_CASE(true, false, 1) DEXSIM_TMA_CASE(true, false, 2)
-    DEXSIM_TMA_CASE(false, true, 0) DEXSIM_TMA_CASE(false, true, 1) DEXSIM_TMA_CASE(false, true, 2)
-    DEXSIM_TMA_CASE(false, false, 0) DEXSIM_TMA_CASE(false, false, 1) DEXSIM_TMA_CASE(false, false, 2)
+#define DEXSIM_TMA_CASE(D, A, T, X)                                                                                 \
+    if (dense == D && aos == A && track == T && extra == X)                                                         \
+        return launch_tma_variant<D, A, T, X, DEXSIM_TMA_STAGES>(sm_count, s, *st, *p, groups, goe, *io, maps, num_tiles);
+    DEXSIM_TMA_CASE(true, true, 0, false) DEXSIM_TMA_CASE(true, true, 1, false) DEXSIM_TMA_CASE(true, true, 2, false)
+    DEXSIM_TMA_CASE(true, false, 0, false) DEXSIM_TMA_CASE(true, false, 1, false) DEXSIM_TMA_CASE(true, false, 2, false)
+    DEXSIM_TMA_CASE(false, true, 0, false) DEXSIM_TMA_CASE(false, true, 1, false) DEXSIM_TMA_CASE(false, true, 2, false)
+    DEXSIM_TMA_CASE(false, false, 0, false) DEXSIM_TMA_CASE(false, false, 1, false) DEXSIM_TMA_CASE(false, false, 2, false)
+    // noise / reward components: the reference's [n,15] action layout only (SoA callers take the register kernel)
+    DEXSIM_TMA_CASE(true, true, 0, true) DEXSIM_TMA_CASE(true, true, 1, true) DEXSIM_TMA_CASE(true, true, 2, true)
+    DEXSIM_TMA_CASE(false, true, 0, true) DEXSIM_TMA_CASE(false, true, 1, true) DEXSIM_TMA_CASE(false, true, 2, true)
 #undef DEXSIM_TMA_CASE
     return 1;
 }
@@ -843,26 +897,31 @@ static int launch_step(const DexsimState* st, const DexsimParams* p, const Dexsi
     const bool extras = io->dyn_noise || io->obs_noise || io->reward_comps || io->reward64 || io->finished ||
                         (p && p->auto_reset) || st->ep_return != nullptr || fused_dyn || fused_obs || pack_out != nullptr;
     const bool group_sigma = (fused_dyn && io->sigma_dyn < 0.0f) || (fused_obs && io->sigma_obs < 0.0f);
-    rc = check_params(p, p && (p->auto_reset || group_sigma), groups);
+    rc = check_params(p, p && (p->auto_reset || group_sigma), groups, st->ep_return != nullptr && p && p->auto_reset);
     if (rc) return rc;
     if (st->n == 0) return 0;
     DeviceInfo di;
     rc = device_info_cached(di);
     if (rc) return rc;
-    // TMA pipeline: everything except the noise / reward-component outputs; needs 16-byte aligned bases
+    // TMA pipeline: needs 16-byte aligned bases for everything its bulk copies touch; noise / reward-component /
+    // float64-reward calls ride it too (their rows are accessed directly) when the actions are [n,15]
     const int impl = step_impl_choice();
-    const int track = !extras ? 0 : (st->ep_return != nullptr ? 1 : 2);
-    const bool tma_ok = !io->dyn_noise && !io->obs_noise && !fused_dyn && !fused_obs && !io->reward_comps && !io->reward64 &&
+    const bool extra_io = io->dyn_noise || io->obs_noise || io->reward_comps || io->reward64 || fused_dyn || fused_obs;
+    const bool tracked = (p && p->auto_reset) || st->ep_return != nullptr || io->finished != nullptr;
+    const int track = !tracked ? 0 : (st->ep_return != nullptr ? 1 : 2);
+    const bool tma_ok = (!extra_io || io->action_layout == 1) && pack_out == nullptr &&
                         st->n >= TILE && st->n < (int64_t)0x7FFFFF00 &&
                         !(reinterpret_cast<uintptr_t>(io->action) & 15u) && !(reinterpret_cast<uintptr_t>(io->reward) & 15u) &&
                         !(reinterpret_cast<uintptr_t>(st->thr) & 15u) && !(reinterpret_cast<uintptr_t>(st->damp) & 15u) &&
                         !(reinterpret_cast<uintptr_t>(st->step_count) & 15u) && !(reinterpret_cast<uintptr_t>(st->cmask) & 15u) &&
                         !(reinterpret_cast<uintptr_t>(io->terminated) & 15u) && !(reinterpret_cast<uintptr_t>(io->truncated) & 15u) &&
-                        !(reinterpret_cast<uintptr_t>(io->num_contacts) & 15u) &&
+                        !(reinterpret_cast<uintptr_t>(io->num_contacts) & 15u) && !(reinterpret_cast<uintptr_t>(st->episode) & 15u) &&
                         (track != 1 || (!(reinterpret_cast<uintptr_t>(st->ep_return) & 15u) && !(reinterpret_cast<uintptr_t>(st->ep_stats) & 15u))) &&
                         !(reinterpret_cast<uintptr_t>(io->finished) & 15u);
-    if (impl != 1 && tma_ok) {
-        rc = launch_step_tma(st, p, groups, goe, io, s, track, di.sm_count);
+    // auto: below the crossover the batch is L2-resident and one step is a launch plus one load-compute-store round trip;
+    // the register-resident kernel has the shorter round trip there (measured on B200)
+    if (impl != 1 && tma_ok && (impl == 2 || st->n >= tma_min_envs(track, extra_io))) {
+        rc = launch_step_tma(st, p, groups, goe, io, s, track, extra_io, di.sm_count);
         if (rc <= 0) return rc;                      // launched (0) or CUDA error (< 0); 1 = not available
     }
     if (impl == 2) return DEXSIM_E_PARAM;            // TMA pipeline was demanded but is not eligible
@@ -889,7 +948,7 @@ const char* dexsim_error_string(int code) {
         case DEXSIM_E_NULL: return "dexsim: required pointer is NULL";
         case DEXSIM_E_SIZE: return "dexsim: bad size (need n >= 0, ld >= n, ld % 32 == 0, k_steps >= 1)";
         case DEXSIM_E_ALIGN: return "dexsim: array base not 16-byte aligned";
-        case DEXSIM_E_PARAM: return "dexsim: bad enum or flag value";
+        case DEXSIM_E_PARAM: return "dexsim: bad enum, flag or parameter value (tracked episodes hold at most 5,242 steps)";
         case DEXSIM_E_GROUPS: return "dexsim: num_groups out of range";
         case DEXSIM_E_GEOMETRY: return "dexsim: only num_fingers=5, joints_per_finger=3 is supported";
         default: break;
@@ -975,7 +1034,7 @@ int dexsim_rollout(const DexsimState* st, const DexsimParams* p, const DexsimGro
                    void* stream) {
     int rc = check_state(st);
     if (rc) return rc;
-    rc = check_params(p, true, groups);
+    rc = check_params(p, true, groups, st->ep_return != nullptr);
     if (rc) return rc;
     if (!rio) return DEXSIM_E_NULL;
     if (k_steps < 1) return DEXSIM_E_SIZE;
@@ -1012,13 +1071,19 @@ int dexsim_rollout(const DexsimState* st, const DexsimParams* p, const DexsimGro
         if (sblocks > 0x7FFFFFFFll) return DEXSIM_E_SIZE;
         if (dense) rollout_split_kernel<true><<<(int)sblocks, SPLIT_THREADS, 0, s>>>(*st, *p, groups, group_of_env, k_steps, policy_kind, *rio);
         else rollout_split_kernel<false><<<(int)sblocks, SPLIT_THREADS, 0, s>>>(*st, *p, groups, group_of_env, k_steps, policy_kind, *rio);
-        return cuda_rc(cudaGetLastError());
-    }
-    if (dense && learner) rollout_kernel<true, true><<<(int)blocks, threads, smem, s>>>(*st, *p, groups, group_of_env, k_steps, policy_kind, *rio);
+    } else if (dense && learner) rollout_kernel<true, true><<<(int)blocks, threads, smem, s>>>(*st, *p, groups, group_of_env, k_steps, policy_kind, *rio);
     else if (dense) rollout_kernel<true, false><<<(int)blocks, threads, smem, s>>>(*st, *p, groups, group_of_env, k_steps, policy_kind, *rio);
     else if (learner) rollout_kernel<false, true><<<(int)blocks, threads, smem, s>>>(*st, *p, groups, group_of_env, k_steps, policy_kind, *rio);
     else rollout_kernel<false, false><<<(int)blocks, threads, smem, s>>>(*st, *p, groups, group_of_env, k_steps, policy_kind, *rio);
-    return cuda_rc(cudaGetLastError());
+    rc = cuda_rc(cudaGetLastError());
+    if (rc) return rc;
+    if (rio->ep_log && rio->hist && rio->ep_log_capacity > 0) {
+        // exact variance ties flagged by the launch above are decided with np.var's arithmetic on the recorded history
+        const long long rblocks = (rio->ep_log_capacity + 255) / 256;
+        resolve_ties_kernel<<<(int)(rblocks > 4096 ? 4096 : rblocks), 256, 0, s>>>(*p, group_of_env, *rio, st->n, st->ld);
+        rc = cuda_rc(cudaGetLastError());
+    }
+    return rc;
 }
 
 int dexsim_pack_env(const DexsimState* st, const DexsimStepIO* io, int64_t index, int32_t after_reset, double* out64,
@@ -1067,11 +1132,13 @@ int dexsim_fill_normal(const DexsimState* st, const DexsimParams* p, int32_t rng
     return cuda_rc(cudaGetLastError());
 }
 
-int dexsim_classify_summary(const DexsimEpisodeSummary* s, int32_t max_steps, int32_t success_threshold,
-                            int32_t* label_metrics, int32_t* label_taxonomy, int32_t* var_tie) {
+int dexsim_classify_summary(const DexsimEpisodeSummary* s, const uint8_t* counts, int32_t max_steps,
+                            int32_t success_threshold, int32_t* label_metrics, int32_t* label_taxonomy, int32_t* var_tie) {
     if (!s || !label_metrics || !label_taxonomy) return DEXSIM_E_NULL;
+    if (s->hist_len < 0) return DEXSIM_E_SIZE;
     int la, lb, tie;
-    classify_summary(*s, max_steps, success_threshold, la, lb, tie);
+    const CountsView cv{counts, 1};
+    classify_summary(*s, max_steps, success_threshold, la, lb, tie, &cv);
     *label_metrics = la; *label_taxonomy = lb;
     if (var_tie) *var_tie = tie;
     return 0;
@@ -1166,6 +1233,7 @@ int dexsim_step_host(const DexsimState* st, const DexsimParams* p, const DexsimG
         if (sio.reward_comps) sio.reward_comps += lo;
         if (sio.reward64) sio.reward64 += lo;
         if (sio.finished) sio.finished += lo;
+        if (sio.sched) sio.sched = (2 * (c + 1) + 1 < DEXSIM_SCHED_WORDS) ? io->sched + 2 * (c + 1) : nullptr;   // chunks run concurrently
         cudaError_t err;
         if (aos) err = cudaMemcpyAsync(d_action, h_action + lo * NJ, (size_t)m * NJ * sizeof(float), cudaMemcpyHostToDevice, s);
         else err = cudaMemcpy2DAsync(d_action, (size_t)ld * 4, h_action + lo, (size_t)ld * 4, (size_t)m * 4, NJ, cudaMemcpyHostToDevice, s);

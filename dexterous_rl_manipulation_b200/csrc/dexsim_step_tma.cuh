@@ -24,10 +24,13 @@ namespace dexsim {
 #ifndef DEXSIM_TMA_TILE
 #define DEXSIM_TMA_TILE 128
 #endif
+#ifndef DEXSIM_TMA_STAGES
+#define DEXSIM_TMA_STAGES 2                        // stages per CTA: 2 (three CTAs per SM) or 3 (two CTAs per SM)
+#endif
 constexpr int TILE = DEXSIM_TMA_TILE;              // envs per tile: 128, or 96 (24.7 KB stages, four CTAs per SM)
 static_assert(TILE % 32 == 0 && TILE <= 256, "a tile is a whole number of warps and one TMA box wide");
-constexpr int TMA_COMPUTE_THREADS = TILE;          // one compute group = one thread per env of a tile
-__host__ __device__ constexpr int tma_threads(int groups) { return groups * TMA_COMPUTE_THREADS + 32; }
+constexpr int TMA_COMPUTE_THREADS = TILE;          // one thread per env of a tile
+constexpr int TMA_THREADS = TMA_COMPUTE_THREADS + 32;   // + the producer warp
 constexpr int TMA_GROUPS_MAX = 16;     // per-CTA counter staging (keeps 3 CTAs per SM with 2 stages)
 
 // byte offsets inside one stage (all multiples of 128: TMA box destinations need 128-byte alignment)
@@ -47,11 +50,12 @@ constexpr int OFF_EPRET = OFF_NC + TILE;            // [128] f64, in/out (tracki
 constexpr int OFF_EPST0 = OFF_EPRET + TILE * 8;     // [128] u32, in/out (tracking)
 constexpr int OFF_EPST1 = OFF_EPST0 + TILE * 4;     // [128] u32, in/out (tracking)
 constexpr int OFF_FIN = OFF_EPST1 + TILE * 4;       // [128] u8, out (auto-reset)
-constexpr int STAGE_BYTES = (OFF_FIN + TILE + 127) / 128 * 128;      // every stage starts 128-byte aligned
+constexpr int OFF_EPISODE = OFF_FIN + TILE;         // [128] u32, in (in-kernel noise: Philox counter word)
+constexpr int STAGE_BYTES = (OFF_EPISODE + TILE * 4 + 127) / 128 * 128;      // every stage starts 128-byte aligned
 static_assert(OFF_OV % 128 == 0 && OFF_OP64 % 128 == 0 && OFF_ACT % 128 == 0, "tensor-map box destinations");
 static_assert(OFF_THR % 16 == 0 && OFF_DAMP % 16 == 0 && OFF_SC % 16 == 0 && OFF_REWARD % 16 == 0 && OFF_CMASK % 16 == 0 &&
               OFF_TERM % 16 == 0 && OFF_TRUNC % 16 == 0 && OFF_NC % 16 == 0 && OFF_EPRET % 16 == 0 && OFF_EPST0 % 16 == 0 &&
-              OFF_EPST1 % 16 == 0 && OFF_FIN % 16 == 0, "1-D bulk copy destinations");
+              OFF_EPST1 % 16 == 0 && OFF_FIN % 16 == 0 && OFF_EPISODE % 16 == 0, "1-D bulk copy destinations");
 
 struct StepMaps {             // tensor maps live in kernel parameter space (__grid_constant__)
     CUtensorMap obs_jpjv;     // obs [45, ld] f32, box {128, 30}
@@ -108,44 +112,136 @@ __device__ __forceinline__ uint32_t tile_cols(int64_t n, int64_t base) {
     return left >= TILE ? (uint32_t)TILE : (uint32_t)((left + 31) & ~(int64_t)31);
 }
 
-// "Stage filled" barriers.  A parity wait can only tell the last two phases of a barrier apart, so every barrier
-// must be watched phase by phase by ONE waiter.  With two compute groups a stage alternates between them
-// (3 stages, tile k -> stage k % 3, group k % 2), hence one barrier per (stage, group): tile k uses barrier
-// k % (S * G) and it is that barrier's (k / (S * G))-th fill.  (S and G are coprime or G == 1.)
-template <int STAGES, int GROUPS>
-__device__ __forceinline__ int full_index(int k) { return GROUPS == 1 ? k % STAGES : k % (STAGES * GROUPS); }
-template <int STAGES, int GROUPS>
-__device__ __forceinline__ uint32_t full_parity(int k) {
-    return (uint32_t)((GROUPS == 1 ? k / STAGES : k / (STAGES * GROUPS)) & 1);
+// ---- warp-cooperative episode reset (experiment, built only with -DDEXSIM_RESET_COOP) -------------------------
+// Episodes end at scattered times, so a warp typically has one or two lanes that must reset while the other thirty
+// wait (ncu, round 1: finish_and_reset ran with 1-2 active lanes, ~8 % of the executed instructions in a quiet phase).
+// This variant flattens the (resetting env, Philox block) pairs of a warp into work items spread over its 32 lanes:
+// one lane draws ONE block for ONE env and writes the results where they belong -- joints into the stage, position /
+// parameters to their rows -- so m resetting lanes cost ceil(5 m / 32) block evaluations of warp time instead of 5.
+// Bit-identical to reset_draws() + env_reset() (all GPU parity tests pass with it), but MEASURED SLOWER than the
+// owner-lane form on B200 at every reset rate (1 Mi envs, dynamic tiles, us per step, owner-lane vs cooperative):
+// 0.45 % resets per env-step 69.4 vs 70.6 (counts) and 77.4 vs 79.9 (full tracking); 6.8 % resets per env-step 99.2 vs
+// 104.1 and 119.7 vs 131.9 -- the shuffles, the rank search and the read-back of the new state through shared memory
+// cost more than the serialised Philox blocks they save.  The product therefore resets on the owning lane.
+//   rm: ballot of resetting lanes; episode / g: each lane's NEW episode index and group (read by shuffle).
+//   keep-position mode (p.respawn == 0): the owner has stored (double)(float)position into the stage before the call.
+__device__ __forceinline__ void warp_reset_draws(const unsigned rm, const int lane, const int wcol0, const int64_t base,
+                                                 unsigned char* sp, const DexsimState& st, const DexsimParams& p,
+                                                 const DexsimGroup* __restrict__ groups, const uint32_t episode,
+                                                 const int g, const bool any_ranged) {
+    float* s_jpjv = reinterpret_cast<float*>(sp + OFF_JPJV);
+    double* s_op = reinterpret_cast<double*>(sp + OFF_OP64);
+    double* s_thr = reinterpret_cast<double*>(sp + OFF_THR);
+    int* s_sc = reinterpret_cast<int*>(sp + OFF_SC);
+    float* __restrict__ obs = st.obs;
+    const int64_t ld = st.ld;
+    const int nb = any_ranged ? 7 : 5;
+    const int items = __popc(rm) * nb;
+    for (int t0 = 0; t0 < items; t0 += 32) {
+        const int t = t0 + lane;
+        const bool act = t < items;
+        const int r = act ? (any_ranged ? t / 7 : t / 5) : 0;
+        const int b = t - r * nb;
+        const int src = (int)__fns(rm, 0u, r + 1);                    // lane of the r-th resetting env
+        const uint32_t ep = __shfl_sync(0xffffffffu, episode, src);
+        const int gi = __shfl_sync(0xffffffffu, g, src);
+        if (!act) continue;
+        const int c = wcol0 + src;
+        const int64_t i = base + c;
+        const uint32_t gid = (uint32_t)(p.env_gid0 + i);
+        const DexsimGroup& grp = groups[gi];
+        if (b < 4) {                                                  // joints 4b .. 4b+3 (reset_draws blocks 0-3)
+            const U4 o = rng_block(p.seed, gid, ep, 0u, STREAM_RESET, (uint32_t)b);
+            const uint32_t w[4] = {o.x, o.y, o.z, o.w};
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int j = 4 * b + k;
+                if (j < NJ) {
+                    s_jpjv[j * TILE + c] = (float)__dadd_rn(-0.1, __dmul_rn(0.2, (double)u24(w[k])));
+                    s_jpjv[(NJ + j) * TILE + c] = 0.0f;
+                }
+            }
+        } else if (b == 4) {                                          // spawn position (block 4) + the rows a reset zeroes
+            double np3[3];
+            if (p.respawn) {
+                const U4 o = rng_block(p.seed, gid, ep, 0u, STREAM_RESET, 4u);
+                const uint32_t w[3] = {o.x, o.y, o.z};
+#pragma unroll
+                for (int k = 0; k < 3; ++k)
+                    np3[k] = (double)(float)lerp_rn(grp.spawn_lo[k], grp.spawn_hi[k], __dmul_rn((double)w[k], 0x1p-32));
+            } else {
+#pragma unroll
+                for (int k = 0; k < 3; ++k) np3[k] = s_op[k * TILE + c];
+            }
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                s_op[k * TILE + c] = np3[k];
+                st.op64[k * ld + i] = np3[k];
+                obs[(DEXSIM_ROW_OP + k) * ld + i] = (float)np3[k];
+                obs[(DEXSIM_ROW_OV + k) * ld + i] = 0.0f;
+            }
+            s_sc[c] = 0;
+            if (!any_ranged) {                                        // fixed curricula: the group's constants
+                st.size[i] = grp.size; st.mass[i] = grp.mass; st.friction[i] = grp.friction;
+                const double thr = __dmul_rn(grp.size, 1.5);
+                st.thr[i] = thr; s_thr[c] = thr;
+                st.damp[i] = (float)__dsub_rn(1.0, __dmul_rn(__dmul_rn(grp.friction, 0.1), 0.01));
+            }
+        } else if (b == 5) {                                          // size, mass (block 5)
+            double size = grp.size, mass = grp.mass;
+            if (grp.size_ranged | grp.mass_ranged) {
+                const U4 o = rng_block(p.seed, gid, ep, 0u, STREAM_RESET, 5u);
+                if (grp.size_ranged) size = lerp_rn(grp.size_lo, grp.size_hi, u53(o.x, o.y));
+                if (grp.mass_ranged) mass = lerp_rn(grp.mass_lo, grp.mass_hi, u53(o.z, o.w));
+            }
+            st.size[i] = size; st.mass[i] = mass;
+            const double thr = __dmul_rn(size, 1.5);
+            st.thr[i] = thr; s_thr[c] = thr;
+        } else {                                                      // friction (block 6)
+            double friction = grp.friction;
+            if (grp.fric_ranged) {
+                const U4 o = rng_block(p.seed, gid, ep, 0u, STREAM_RESET, 6u);
+                friction = lerp_rn(grp.fric_lo, grp.fric_hi, u53(o.x, o.y));
+            }
+            st.friction[i] = friction;
+            st.damp[i] = (float)__dsub_rn(1.0, __dmul_rn(__dmul_rn(friction, 0.1), 0.01));
+        }
+    }
 }
 
 // DENSE: reward type.  AOS: action layout [n,15].  TRACK: 0 = plain step; 1 = episode tracking (return + history
 // summary per env -> failure labels), auto-reset, counters; 2 = auto-reset and counters only (what a curriculum
 // needs: episodes, successes, lengths) without the per-env return / history arrays.
-// GROUPS: compute groups per CTA.  With 2 groups (8 compute warps, 3 stages, 2 CTAs per SM) group g works on the
-// CTA's tiles k = g, g + 2, ... so that two tiles are in their compute phase while a third one loads.
-template <bool DENSE, bool AOS, int TRACK, int STAGES, int GROUPS>
-__global__ void __launch_bounds__(tma_threads(GROUPS), (GROUPS == 2) ? 2 : ((STAGES == 2) ? (TILE <= 96 ? 4 : 3) : 2))
+// EXTRA: observation / dynamics noise (pre-drawn tensors or Philox normals drawn here), reward components and the
+// float64 reward -- CombinedNoiseWrapper.step (evaluation/robustness_tests.py:177-207) on the same pipeline; their
+// rows go straight from registers to HBM (coalesced 128-byte row segments per warp), the stage ring is unchanged.
+// Tiles are handed out dynamically when the caller supplies DexsimStepIO.sched (two zeroed device words): a CTA's first
+// tile is its block index, every further one comes from a global counter.  SMs do not progress at the same rate (ncu,
+// round 2: 125k .. 152k active cycles per SM under the static round-robin, the launch lasting as long as the slowest),
+// and tiles with episode resets take longer than others; with the counter every SM works until the batch is done.
+template <bool DENSE, bool AOS, int TRACK, bool EXTRA, int STAGES>
+__global__ void __launch_bounds__(TMA_THREADS, (STAGES == 2) ? (TILE <= 96 ? 4 : 3) : 2)
 step_tma_kernel(const DexsimState st, const DexsimParams p, const DexsimGroup* __restrict__ groups,
                 const uint16_t* __restrict__ group_of_env, const DexsimStepIO io,
                 const __grid_constant__ StepMaps maps, const int num_tiles) {
     extern __shared__ __align__(1024) unsigned char smem[];
     unsigned char* stage_base = smem;
-    constexpr int NFULL = STAGES * GROUPS;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);      // full[S * G], out_ready[S]
-    unsigned long long* sh_cnt = reinterpret_cast<unsigned long long*>(bars + NFULL + STAGES);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);      // full[S], out_ready[S]
+    int* s_tile = reinterpret_cast<int*>(bars + 2 * STAGES);                         // tile held by each stage, -1 = no more
+    unsigned long long* sh_cnt = reinterpret_cast<unsigned long long*>(s_tile + 2 * STAGES);
     double* sh_rs = reinterpret_cast<double*>(sh_cnt + (TRACK ? TMA_GROUPS_MAX * DEXSIM_NCOUNTERS : 0));
 
-    constexpr int TMA_THREADS = tma_threads(GROUPS);
-    constexpr int PRODUCER_TID = GROUPS * TMA_COMPUTE_THREADS;
+    constexpr int PRODUCER_TID = TMA_COMPUTE_THREADS;
     const int tid = threadIdx.x;
     const int64_t n = st.n, ld = st.ld;
     const bool count_episodes = TRACK && p.auto_reset && io.counters != nullptr;
     const bool staged_cnt = count_episodes && p.num_groups <= TMA_GROUPS_MAX;
+    // in-kernel noise reads each env's episode counter (Philox counter word) every step: it rides the stage ring
+    const bool load_episode = EXTRA && ((!io.dyn_noise && io.sigma_dyn != 0.0f) || (!io.obs_noise && io.noisy_obs && io.sigma_obs != 0.0f));
 
     if (tid == 0) {
-        for (int b = 0; b < NFULL; ++b) mbar_init(smem_u32(&bars[b]), 1);
-        for (int s = 0; s < STAGES; ++s) mbar_init(smem_u32(&bars[NFULL + s]), TMA_COMPUTE_THREADS);
+        for (int b = 0; b < STAGES; ++b) mbar_init(smem_u32(&bars[b]), 1);
+        for (int b = 0; b < STAGES; ++b) mbar_init(smem_u32(&bars[STAGES + b]), TMA_COMPUTE_THREADS);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (TRACK && staged_cnt) {
@@ -154,14 +250,12 @@ step_tma_kernel(const DexsimState st, const DexsimParams p, const DexsimGroup* _
     }
     __syncthreads();
 
-    const int my_tiles = (num_tiles > (int)blockIdx.x) ? (num_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
-
     if (tid >= PRODUCER_TID) {
         // ===== producer warp: one lane issues every bulk copy of this CTA =====
         if (tid == PRODUCER_TID) {
-            auto issue_stores = [&](int k) {
-                const int s = k % STAGES;
-                const int64_t base = ((int64_t)blockIdx.x + (int64_t)k * gridDim.x) * TILE;
+            unsigned int* sched = io.sched;
+            auto issue_stores = [&](int s, int tile) {
+                const int64_t base = (int64_t)tile * TILE;
                 const uint32_t sb = smem_u32(stage_base + (size_t)s * STAGE_BYTES);
                 const uint32_t cols = tile_cols(n, base);
                 tma_store_2d(&maps.obs_jpjv, (int)base, DEXSIM_ROW_JP, sb + OFF_JPJV);
@@ -178,25 +272,37 @@ step_tma_kernel(const DexsimState st, const DexsimParams p, const DexsimGroup* _
                 if (TRACK && io.finished) bulk_store(io.finished + base, sb + OFF_FIN, cols);
                 bulk_commit();
             };
-            for (int k = 0; k < my_tiles; ++k) {
+            unsigned held = 0u;                        // bit s: stage s still holds the outputs of tile s_tile[s]
+            int tile = (int)blockIdx.x;                // first tile: static
+            int k = 0;
+            for (;; ++k) {
                 const int s = k % STAGES, use = k / STAGES;
                 const uint32_t sb = smem_u32(stage_base + (size_t)s * STAGE_BYTES);
-                const uint32_t full = smem_u32(&bars[full_index<STAGES, GROUPS>(k)]);
-                if (use > 0) {
+                const uint32_t full = smem_u32(&bars[s]);
+                if ((held >> s) & 1u) {
                     // the tile that used this stage last: wait for its outputs, send them, and let
                     // the copy engine finish READING the stage before new data lands in it
-                    mbar_wait(smem_u32(&bars[NFULL + s]), (uint32_t)((use - 1) & 1));
-                    issue_stores(k - STAGES);
+                    mbar_wait(smem_u32(&bars[STAGES + s]), (uint32_t)((use - 1) & 1));
+                    issue_stores(s, s_tile[s]);
+                    held &= ~(1u << s);
                     bulk_wait_read0();
                 }
-                const int64_t base = ((int64_t)blockIdx.x + (int64_t)k * gridDim.x) * TILE;
+                if (tile >= num_tiles) {               // no more work: tell the compute warps and leave
+                    s_tile[s] = -1;
+                    mbar_arrive(full);
+                    break;
+                }
+                s_tile[s] = tile;
+                held |= 1u << s;
+                const int64_t base = (int64_t)tile * TILE;
                 const uint32_t cols = tile_cols(n, base);
                 const bool full_tile = (n - base) >= TILE;
                 uint32_t tx = (30 + 3) * TILE * 4 + 3 * TILE * 8 + cols * (8 + 4 + 4 + 1);
                 if (AOS) tx += full_tile ? NJ * TILE * 4 : 0;
                 else tx += NJ * TILE * 4;
                 if (TRACK == 1) tx += cols * (8 + 4 + 4);
-                mbar_expect_tx(full, tx);
+                if (load_episode) tx += cols * 4;
+                mbar_expect_tx(full, tx);              // release: s_tile[s] is visible to whoever sees this phase complete
                 tma_load_2d(sb + OFF_JPJV, &maps.obs_jpjv, (int)base, DEXSIM_ROW_JP, full);
                 tma_load_2d(sb + OFF_OV, &maps.obs_ov, (int)base, DEXSIM_ROW_OV, full);
                 tma_load_2d(sb + OFF_OP64, &maps.op64, (int)base, 0, full);
@@ -211,29 +317,49 @@ step_tma_kernel(const DexsimState st, const DexsimParams p, const DexsimGroup* _
                     bulk_load(sb + OFF_EPST0, st.ep_stats + base, cols * 4, full);
                     bulk_load(sb + OFF_EPST1, st.ep_stats + ld + base, cols * 4, full);
                 }
+                if (load_episode) bulk_load(sb + OFF_EPISODE, st.episode + base, cols * 4, full);
+                // next tile: from the global counter (its round trip overlaps this tile's transfer), else round-robin
+                tile = sched ? (int)(atomicAdd(&sched[0], 1u) + gridDim.x) : tile + (int)gridDim.x;
             }
-            // drain: outputs of the last min(STAGES, my_tiles) tiles
-            const int first = my_tiles > STAGES ? my_tiles - STAGES : 0;
-            for (int k = first; k < my_tiles; ++k) {
-                mbar_wait(smem_u32(&bars[NFULL + k % STAGES]), (uint32_t)((k / STAGES) & 1));
-                issue_stores(k);
+            // drain: outputs of the tiles still held by the other stages, oldest first
+            for (int d = 1; d < STAGES; ++d) {
+                const int kk = k - STAGES + d;
+                if (kk < 0) continue;
+                const int s = kk % STAGES;
+                if (!((held >> s) & 1u)) continue;
+                mbar_wait(smem_u32(&bars[STAGES + s]), (uint32_t)((kk / STAGES) & 1));
+                issue_stores(s, s_tile[s]);
             }
             bulk_wait0();       // shared memory must outlive every outstanding bulk store
+            if (sched) {        // the last CTA to finish re-arms the scheduler words for the next launch
+                __threadfence();
+                if (atomicAdd(&sched[1], 1u) == gridDim.x - 1) { sched[0] = 0u; sched[1] = 0u; }
+            }
         }
     } else {
         // ===== compute warps: lane == column of the tile =====
-        const int col = tid % TMA_COMPUTE_THREADS;
-        for (int k = tid / TMA_COMPUTE_THREADS; k < my_tiles; k += GROUPS) {
+        const int col = tid;
+        const int lane = tid & 31;
+        const int wcol0 = col - lane;
+        for (int k = 0;; ++k) {
             const int s = k % STAGES;
             unsigned char* sp = stage_base + (size_t)s * STAGE_BYTES;
-            const int64_t base = ((int64_t)blockIdx.x + (int64_t)k * gridDim.x) * TILE;
+            mbar_wait(smem_u32(&bars[s]), (uint32_t)((k / STAGES) & 1));
+            const int tile = s_tile[s];
+            if (tile < 0) break;
+            const int64_t base = (int64_t)tile * TILE;
             const int64_t i = base + col;
-            mbar_wait(smem_u32(&bars[full_index<STAGES, GROUPS>(k)]), full_parity<STAGES, GROUPS>(k));
-            if (i < n) {
-                float* s_jpjv = reinterpret_cast<float*>(sp + OFF_JPJV);
+            float* s_jpjv = reinterpret_cast<float*>(sp + OFF_JPJV);
+            double* s_op = reinterpret_cast<double*>(sp + OFF_OP64);
+            float* __restrict__ obs = st.obs;
+            const bool valid = i < n;
+            bool do_reset = false, lane_reset = false;
+            bool fused_dyn = false, fused_obs = false;
+            uint32_t episode = 0u;
+            int g = 0;
+            EnvRegs e;
+            if (valid) {
                 const float* s_ov = reinterpret_cast<const float*>(sp + OFF_OV);
-                const double* s_op = reinterpret_cast<const double*>(sp + OFF_OP64);
-                EnvRegs e;
 #pragma unroll
                 for (int j = 0; j < NJ; ++j) { e.jp[j] = s_jpjv[j * TILE + col]; e.jv[j] = s_jpjv[(NJ + j) * TILE + col]; }
 #pragma unroll
@@ -256,6 +382,30 @@ step_tma_kernel(const DexsimState st, const DexsimParams p, const DexsimGroup* _
 #pragma unroll
                     for (int j = 0; j < NJ; ++j) a[j] = s_act[j * TILE + col];
                 }
+                const int64_t gid = p.env_gid0 + i;
+                if (EXTRA) {
+                    // evaluation/robustness_tests.py:180-187: a <- clip(a + N(0, sigma_dyn), -1, 1)
+                    fused_dyn = !io.dyn_noise && io.sigma_dyn != 0.0f;
+                    fused_obs = !io.obs_noise && io.noisy_obs && io.sigma_obs != 0.0f;
+                    if (fused_dyn || fused_obs) {
+                        episode = reinterpret_cast<const uint32_t*>(sp + OFF_EPISODE)[col];
+                        if (io.sigma_dyn < 0.0f || io.sigma_obs < 0.0f)
+                            g = group_of_env ? (int)group_of_env[i] : (int)((uint32_t)gid % (uint32_t)p.num_groups);
+                    }
+                    if (io.dyn_noise) {
+#pragma unroll
+                        for (int j = 0; j < NJ; ++j)
+                            a[j] = clip_f32(__fadd_rn(a[j], __ldg(io.dyn_noise + j * ld + i)), -1.0f, 1.0f);
+                    } else if (fused_dyn) {
+                        const float sigma = io.sigma_dyn > 0.0f ? io.sigma_dyn : groups[g].sigma_dyn;
+                        if (sigma > 0.0f) {
+                            float nz[NJ];
+                            normal_rows<NJ>(p.seed, (uint32_t)gid, episode, (uint32_t)e.sc, STREAM_DYN, sigma, nz);
+#pragma unroll
+                            for (int j = 0; j < NJ; ++j) a[j] = clip_f32(__fadd_rn(a[j], nz[j]), -1.0f, 1.0f);
+                        }
+                    }
+                }
                 double op_old[3]; float ov_old[3];
 #pragma unroll
                 for (int c = 0; c < 3; ++c) { op_old[c] = e.op[c]; ov_old[c] = e.ov[c]; }
@@ -268,8 +418,16 @@ step_tma_kernel(const DexsimState st, const DexsimParams p, const DexsimGroup* _
                 (sp + OFF_TERM)[col] = r.terminated ? 1 : 0;
                 (sp + OFF_TRUNC)[col] = r.truncated ? 1 : 0;
                 (sp + OFF_NC)[col] = (unsigned char)r.n_c;
+                if (EXTRA) {
+                    if (io.reward64) io.reward64[i] = r.total;
+                    if (io.reward_comps) {
+                        io.reward_comps[0 * ld + i] = (float)r.distance;
+                        io.reward_comps[1 * ld + i] = (float)r.contact;
+                        io.reward_comps[2 * ld + i] = (float)r.closure;
+                        io.reward_comps[3 * ld + i] = (float)r.stability;
+                    }
+                }
 
-                bool did_reset = false;
                 if (TRACK) {
                     double ep_return = 0.0;
                     EpStats es{0u, 0u};
@@ -281,54 +439,126 @@ step_tma_kernel(const DexsimState st, const DexsimParams p, const DexsimGroup* _
                     }
                     const bool done = r.terminated || r.truncated || (p.loop_max_steps > 0 && e.sc >= p.loop_max_steps);
                     if (p.auto_reset && done) {
-                        did_reset = true;
-                        const int64_t gid = p.env_gid0 + i;
-                        const int g = group_of_env ? (int)group_of_env[i] : (int)((uint32_t)gid % (uint32_t)p.num_groups);
-                        uint32_t episode = st.episode[i];
-                        double size, mass, friction;
+                        // episode end on the owning lane (counters, labels); the reset draws are shared by the warp below
+                        g = group_of_env ? (int)group_of_env[i] : (int)((uint32_t)gid % (uint32_t)p.num_groups);
+                        if (!(EXTRA && (fused_dyn || fused_obs))) episode = st.episode[i];
                         unsigned long long* cnt = nullptr;
                         double* rs = nullptr;
                         if (count_episodes) {
                             cnt = (staged_cnt ? sh_cnt : reinterpret_cast<unsigned long long*>(io.counters)) + (int64_t)g * DEXSIM_NCOUNTERS;
                             if (io.ret_sums) rs = (staged_cnt ? sh_rs : io.ret_sums) + 2 * g;
                         }
-                        finish_and_reset(e, p, groups[g], (uint32_t)gid, episode, ep_return, es, r.terminated, r.n_c,
-                                         cnt, rs, size, mass, friction, nullptr, /*classify=*/TRACK == 1);
+#ifndef DEXSIM_RESET_COOP
+                        // the owning lane draws all of its env's Philox blocks (reset_draws + env_reset, dexsim_core.cuh)
+                        {
+                            double size, mass, friction;
+                            finish_and_reset(e, p, groups[g], (uint32_t)gid, episode, ep_return, es, r.terminated, r.n_c,
+                                             cnt, rs, size, mass, friction, nullptr, /*classify=*/TRACK == 1);
+                            st.episode[i] = episode;
+                            st.size[i] = size; st.mass[i] = mass; st.friction[i] = friction;
+                            st.thr[i] = e.thr; st.damp[i] = e.damp;
+                            lane_reset = true;
+                        }
+#else
+                        do_reset = true;
+                        finish_episode(e, p, (uint32_t)gid, episode, ep_return, es, r.terminated, r.n_c, cnt, rs, nullptr,
+                                       /*classify=*/TRACK == 1);
+                        episode += 1u;
                         st.episode[i] = episode;
-                        st.size[i] = size; st.mass[i] = mass; st.friction[i] = friction;
-                        st.thr[i] = e.thr; st.damp[i] = e.damp;
+                        ep_return = 0.0;
+                        es.w0 = 0u; es.w1 = 0u;
+                        if (!p.respawn) {           // reused env object: position re-cast to float32 (envs/manipulation_env.py:160-161)
+#pragma unroll
+                            for (int c = 0; c < 3; ++c) s_op[c * TILE + col] = (double)(float)e.op[c];
+                        }
+#endif
                     }
                     if (TRACK == 1) {
                         reinterpret_cast<double*>(sp + OFF_EPRET)[col] = ep_return;
                         reinterpret_cast<uint32_t*>(sp + OFF_EPST0)[col] = es.w0;
                         reinterpret_cast<uint32_t*>(sp + OFF_EPST1)[col] = es.w1;
                     }
-                    (sp + OFF_FIN)[col] = did_reset ? 1 : 0;
+                    (sp + OFF_FIN)[col] = (do_reset || lane_reset) ? 1 : 0;
                 }
-                // always-changing state goes back through the stage (one bulk store per tile)
+                if (!do_reset) {
+                    // always-changing state goes back through the stage (one bulk store per tile)
 #pragma unroll
-                for (int j = 0; j < NJ; ++j) { s_jpjv[j * TILE + col] = e.jp[j]; s_jpjv[(NJ + j) * TILE + col] = e.jv[j]; }
-                reinterpret_cast<int*>(sp + OFF_SC)[col] = e.sc;
-                // rarely-changing rows: straight from registers, only when they changed
-                float* __restrict__ obs = st.obs;
+                    for (int j = 0; j < NJ; ++j) { s_jpjv[j * TILE + col] = e.jp[j]; s_jpjv[(NJ + j) * TILE + col] = e.jv[j]; }
+                    reinterpret_cast<int*>(sp + OFF_SC)[col] = e.sc;
+                    // rarely-changing rows: straight from registers, only when they changed
 #pragma unroll
-                for (int c = 0; c < 3; ++c) {
-                    if (__double_as_longlong(e.op[c]) != __double_as_longlong(op_old[c])) {
-                        st.op64[c * ld + i] = e.op[c];
-                        obs[(DEXSIM_ROW_OP + c) * ld + i] = (float)e.op[c];
+                    for (int c = 0; c < 3; ++c) {
+                        if (__double_as_longlong(e.op[c]) != __double_as_longlong(op_old[c])) {
+                            st.op64[c * ld + i] = e.op[c];
+                            obs[(DEXSIM_ROW_OP + c) * ld + i] = (float)e.op[c];
+                        }
+                        if (__float_as_uint(e.ov[c]) != __float_as_uint(ov_old[c])) obs[(DEXSIM_ROW_OV + c) * ld + i] = e.ov[c];
                     }
-                    if (__float_as_uint(e.ov[c]) != __float_as_uint(ov_old[c])) obs[(DEXSIM_ROW_OV + c) * ld + i] = e.ov[c];
-                }
-                const unsigned flip = e.cmask ^ cmask_old;
-                if (flip) {
+                    const unsigned flip = e.cmask ^ cmask_old;
+                    if (flip) {
 #pragma unroll
-                    for (int f = 0; f < NF; ++f)
-                        if ((flip >> f) & 1u) obs[(DEXSIM_ROW_CONTACT + f) * ld + i] = ((e.cmask >> f) & 1u) ? 1.0f : 0.0f;
-                    st.cmask[i] = (uint8_t)e.cmask;
+                        for (int f = 0; f < NF; ++f)
+                            if ((flip >> f) & 1u) obs[(DEXSIM_ROW_CONTACT + f) * ld + i] = ((e.cmask >> f) & 1u) ? 1.0f : 0.0f;
+                        st.cmask[i] = (uint8_t)e.cmask;
+                    }
+                }
+            }
+            if (TRACK) {
+                // warp-uniform from here: every lane of the warp takes part in its resetting lanes' draws
+                __syncwarp();
+                const unsigned rm = __ballot_sync(0xffffffffu, do_reset);
+                if (rm) {
+                    // does a resetting env's group randomise size / mass / friction?  (then Philox blocks 5 and 6 are drawn too)
+                    bool ranged = false;
+                    if (do_reset) ranged = (groups[g].size_ranged | groups[g].mass_ranged | groups[g].fric_ranged) != 0;
+                    const bool any_ranged = __any_sync(0xffffffffu, ranged);
+                    warp_reset_draws(rm, lane, wcol0, base, sp, st, p, groups, episode, g, any_ranged);
+                    __syncwarp();                       // the draws of MY env were written by other lanes
+                    if (do_reset) {
+                        // envs/manipulation_env.py:163-176: velocities zero, step count zero, contacts of the new state
+#pragma unroll
+                        for (int j = 0; j < NJ; ++j) { e.jp[j] = s_jpjv[j * TILE + col]; e.jv[j] = 0.0f; }
+#pragma unroll
+                        for (int c = 0; c < 3; ++c) { e.op[c] = s_op[c * TILE + col]; e.ov[c] = 0.0f; }
+                        e.thr = reinterpret_cast<const double*>(sp + OFF_THR)[col];
+                        e.sc = 0;
+                        int n_c; double dmin;
+                        e.cmask = update_contacts<false>(e, n_c, dmin);
+#pragma unroll
+                        for (int f = 0; f < NF; ++f) obs[(DEXSIM_ROW_CONTACT + f) * ld + i] = ((e.cmask >> f) & 1u) ? 1.0f : 0.0f;
+                        st.cmask[i] = (uint8_t)e.cmask;
+                    }
+                }
+            }
+            if (EXTRA && valid && io.noisy_obs) {
+                // evaluation/robustness_tests.py:204-205: all 45 entries of the observation AFTER the step (and after a
+                // possible auto-reset), rows written straight from registers
+                float* __restrict__ out = io.noisy_obs;
+                if (io.obs_noise) {
+                    const float* __restrict__ nz = io.obs_noise;
+#pragma unroll
+                    for (int row = 0; row < NOBS; ++row)
+                        out[row * ld + i] = __fadd_rn(obs_entry(e, row), __ldg(nz + row * ld + i));
+                } else if (fused_obs) {
+                    // the same 45 normals dexsim_fill_normal(STREAM_OBS) would produce: one Philox block = four rows
+                    const float sigma = io.sigma_obs > 0.0f ? io.sigma_obs : groups[g].sigma_obs;
+                    const int64_t gid = p.env_gid0 + i;
+#pragma unroll
+                    for (int b = 0; b < (NOBS + 3) / 4; ++b) {
+                        const U4 o = rng_block(p.seed, (uint32_t)gid, episode, (uint32_t)e.sc, STREAM_OBS, (uint32_t)b);
+                        float z[4];
+                        normal_pair(o.x, o.y, z[0], z[1]);
+                        normal_pair(o.z, o.w, z[2], z[3]);
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            const int row = 4 * b + q;
+                            if (row < NOBS) out[row * ld + i] = __fadd_rn(obs_entry(e, row), __fmul_rn(sigma, z[q]));
+                        }
+                    }
                 }
             }
             fence_async_smem();                       // generic-proxy writes -> visible to the copy engine
-            mbar_arrive(smem_u32(&bars[NFULL + s]));
+            mbar_arrive(smem_u32(&bars[STAGES + s]));
         }
     }
     if (TRACK && staged_cnt) {

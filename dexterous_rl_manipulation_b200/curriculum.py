@@ -43,6 +43,8 @@ class BatchedCurriculumDriver:
         self.max_sequential_updates = int(max_sequential_updates)
         self._last = None
         self.progressions = 0
+        self.exact_episodes = 0          # every episode fed so far / how many of them succeeded (see feed())
+        self.exact_successes = 0
         env.curriculum_config = scheduler.get_current_config()
 
     def feed(self, episodes: int, successes: int, steps: int) -> int:
@@ -51,6 +53,8 @@ class BatchedCurriculumDriver:
             return 0
         sch = self.scheduler
         episodes, successes = int(episodes), int(successes)
+        self.exact_episodes += episodes
+        self.exact_successes += successes
         base, rem = divmod(int(steps), episodes)
         progressed = 0
         k = 0
@@ -62,7 +66,10 @@ class BatchedCurriculumDriver:
                 k += 1
         if k < episodes:
             # bulk tail: no progression can happen any more (or the sequential budget is spent);
-            # the scheduler's totals stay exact, its per-episode lists get a bounded tail
+            # the scheduler's totals (total_episodes, total_steps) stay exact, its per-episode lists get a bounded
+            # tail -- so statistics the reference derives from the LISTS (get_statistics()["overall_success_rate"] =
+            # mean(episode_successes)) describe the retained tail only; exact totals are kept in
+            # `self.exact_episodes` / `self.exact_successes` for callers that report overall rates
             rest = episodes - k
             rest_steps = int(steps) - (base * k + min(k, rem))
             keep = min(rest, int(getattr(sch, "window_size", 20)))
@@ -73,9 +80,10 @@ class BatchedCurriculumDriver:
             # let the scheduler act on the new totals / window exactly as further update() calls would
             # (CurriculumScheduler: one level per call while the window rate holds; StepBasedScheduler,
             # experiments/curriculum_scheduler.py:276-335: one milestone per call)
+            # The reference progresses at most once per update() call, i.e. at most `rest` times over this tail.
             should, prog = getattr(sch, "_should_progress", None), getattr(sch, "_progress", None)
             guard = 0
-            while should is not None and prog is not None and guard < 1024 and should():
+            while should is not None and prog is not None and guard < min(rest, 1024) and should():
                 guard += 1
                 if not prog():
                     break

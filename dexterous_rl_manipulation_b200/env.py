@@ -196,6 +196,7 @@ class BatchedManipulationEnv:
         self._num_contacts = z(ld, dtype=torch.uint8)
         self._finished = z(ld, dtype=torch.uint8) if self.auto_reset else None
         self._action_dev = z(n, 15, dtype=torch.float32)
+        self._sched = z(_L.SCHED_WORDS, dtype=torch.int32)      # dynamic tile scheduler words of the pipelined step kernel
         self._noisy_obs = None
         self._obs_noise = None
         self._dyn_noise = None
@@ -256,6 +257,7 @@ class BatchedManipulationEnv:
         io.num_contacts, io.finished = self._ptr(self._num_contacts), self._ptr(self._finished)
         io.counters, io.ret_sums = self._ptr(self.counters), self._ptr(self.ret_sums)
         io.reward64 = self._ptr(self._reward64)
+        io.sched = self._ptr(self._sched)
         self._io_single = None
 
     @property
@@ -948,13 +950,41 @@ class BatchedManipulationEnv:
         return self
 
     def state_dict(self):
-        """All device state (checkpoint / resume is a torch.save away)."""
+        """Everything a resumed run needs to continue bit for bit: all device state, the host-side PCG64 generators that
+        drive later resets in rng="numpy" mode, the Philox seed, the rollout step base (history rows / t_end), the
+        first-reset flag and the per-env SimpleLearner state when enabled.  ``torch.save``-able."""
         keys = ("_obs", "_op64", "_thr", "_damp", "_step_count", "_cmask", "_size", "_mass", "_friction",
-                "_episode", "_ep_return", "_ep_stats", "counters", "ret_sums")
-        return {k: getattr(self, k).clone() for k in keys if getattr(self, k) is not None}
+                "_episode", "_ep_return", "_ep_stats", "counters", "ret_sums", "_learner_mean", "_learner_best")
+        sd = {k: getattr(self, k).clone() for k in keys if getattr(self, k, None) is not None}
+        sd["_host"] = {
+            "seed": self.seed, "rollout_steps": self._rollout_steps, "spawned": self._spawned, "did_reset": self._did_reset,
+            "np_rngs": None if self._np_rngs is None else [None if r is None else r.bit_generator.state for r in self._np_rngs],
+            "learner_hp": getattr(self, "_learner_hp", None),
+        }
+        return sd
 
     def load_state_dict(self, sd):
+        host = sd.get("_host")
         for k, v in sd.items():
+            if k == "_host":
+                continue
+            if getattr(self, k, None) is None and k in ("_learner_mean", "_learner_best"):
+                explo, lr, clip = (host or {}).get("learner_hp") or (0.3, 0.01, 0.5)
+                self.enable_learner(learning_rate=lr, exploration_noise=explo, action_clip_range=clip)
             getattr(self, k).copy_(v)
         self._did_reset = True
         self._spawned = True
+        if host is not None:
+            self.seed = int(host["seed"])
+            self._params.seed = self.seed & 0xFFFFFFFFFFFFFFFF
+            self._rollout_steps = int(host["rollout_steps"])
+            self._spawned, self._did_reset = bool(host["spawned"]), bool(host["did_reset"])
+            if host["np_rngs"] is not None:
+                self._np_rngs = []
+                for state in host["np_rngs"]:
+                    if state is None:
+                        self._np_rngs.append(None)
+                    else:
+                        r = np.random.Generator(np.random.PCG64())
+                        r.bit_generator.state = state
+                        self._np_rngs.append(r)

@@ -67,7 +67,14 @@ def _label(code, table):
     return None if int(code) == _lib.LABEL_NONE else table[int(code)]
 
 
-def _episode_dict(rec, counts, size, mass, friction):
+def _episode_dict(rec, counts, size, mass, friction, max_steps=200, success_threshold=3):
+    la, lb = int(rec["label_metrics"]), int(rec["label_taxonomy"])
+    if int(rec["var_tie"]) == 1 and counts is not None:
+        # the device met an exact variance tie without the history at hand: decide it here with np.var's own arithmetic
+        # (evaluation/metrics.py:77-80, evaluation/failure_taxonomy.py:189,219-230)
+        la, lb = _lib.classify_counts(bool(rec["success"]), int(rec["steps"]), int(rec["final_contacts"]),
+                                      int(rec["final_contacts"]), counts, max_steps=max_steps,
+                                      success_threshold=success_threshold)
     d = {
         "episode_reward": float(rec["episode_reward"]),
         "episode_steps": int(rec["steps"]),
@@ -78,8 +85,8 @@ def _episode_dict(rec, counts, size, mass, friction):
         "object_size": float(size),
         "object_mass": float(mass),
         "friction_coefficient": float(friction),
-        "failure_type": _label(rec["label_metrics"], _lib.LABELS_METRICS),
-        "failure_mode": _label(rec["label_taxonomy"], _lib.LABELS_TAXONOMY),
+        "failure_type": _label(la, _lib.LABELS_METRICS),
+        "failure_mode": _label(lb, _lib.LABELS_TAXONOMY),
     }
     return d
 
@@ -158,7 +165,7 @@ def _heldout_result(heldout_set, recs, n_eps, seeds, policy, policy_seed, reward
         obj_results = []
         for e in range(n_eps):
             rec, counts = recs[o * n_eps + e]
-            d = _episode_dict(rec, counts, size[o], mass[o], fric[o])
+            d = _episode_dict(rec, counts, size[o], mass[o], fric[o], max_episode_steps)
             d["object_idx"], d["episode"] = o, e
             # everything needed to re-run exactly this episode with full capture (replay_episode)
             d["replay"] = {"object_idx": o, "reset_seed": env_seeds[o * n_eps + e], "env_gid": int(rec["env_gid"]),
@@ -244,7 +251,8 @@ def evaluate_with_noise_batched(eval_config, policy: str = "heuristic", observat
         recs = _run_one_episode_each(env, max_episode_steps, policy, False, max_episode_steps, True, {})
         for r in range(m):
             rec, counts = recs[r]
-            d = _episode_dict(rec, counts, eval_config.object_size, eval_config.object_mass, eval_config.friction_coefficient)
+            d = _episode_dict(rec, counts, eval_config.object_size, eval_config.object_mass, eval_config.friction_coefficient,
+                                  max_episode_steps)
             local[lo + r].append({k: d[k] for k in ("success", "episode_steps", "num_contacts", "final_contacts",
                                                     "contact_history", "episode_reward", "failure_type", "failure_mode")})
     if distributed:

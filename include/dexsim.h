@@ -35,7 +35,7 @@
 extern "C" {
 #endif
 
-#define DEXSIM_ABI_VERSION 2
+#define DEXSIM_ABI_VERSION 3
 #define DEXSIM_NJ 15      /* joints            envs/manipulation_env.py:52 */
 #define DEXSIM_NF 5       /* fingers           envs/manipulation_env.py:50 */
 #define DEXSIM_OBS 45     /* observation width envs/manipulation_env.py:96-106 */
@@ -53,7 +53,7 @@ extern "C" {
 #define DEXSIM_E_NULL (-1001)        /* required pointer is NULL */
 #define DEXSIM_E_SIZE (-1002)        /* n < 0, ld < n, ld % 32 != 0, k_steps < 1 ... */
 #define DEXSIM_E_ALIGN (-1003)       /* a row base is not 16-byte aligned */
-#define DEXSIM_E_PARAM (-1004)       /* bad enum / flag value */
+#define DEXSIM_E_PARAM (-1004)       /* bad enum / flag / parameter value (e.g. tracked episodes longer than 5,242 steps) */
 #define DEXSIM_E_GROUPS (-1005)      /* num_groups out of range [1, DEXSIM_MAX_GROUPS] */
 #define DEXSIM_E_GEOMETRY (-1006)    /* unsupported num_fingers / joints_per_finger */
 
@@ -82,7 +82,8 @@ extern "C" {
 #define DEXSIM_CNT_SUM_FINAL_CONTACTS 3
 #define DEXSIM_CNT_LABEL_METRICS 4      /* +label code, 6 slots: evaluation/metrics.py:39-96 */
 #define DEXSIM_CNT_LABEL_TAXONOMY 10    /* +label code, 6 slots: evaluation/failure_taxonomy.py:156-239 */
-#define DEXSIM_CNT_VAR_TIES 16          /* episodes whose contact-count variance sat exactly on a threshold */
+#define DEXSIM_CNT_VAR_TIES 16          /* episodes whose contact-count variance sat exactly on a threshold AND whose
+                                         * history was not at hand to decide it the way np.var does (var_tie == 1) */
 #define DEXSIM_CNT_SUM_STEPS_SQ 17
 #define DEXSIM_NCOUNTERS 18
 
@@ -106,7 +107,9 @@ typedef struct DexsimState {
     double*   friction;    /* [ld]      info["curriculum"]["friction_coefficient"], :275 */
     uint32_t* episode;     /* [ld]      episodes finished by this env (Philox counter word) */
     double*   ep_return;   /* [ld]      running episode return (float64 like evaluator.py:144); NULL = not tracked */
-    uint32_t* ep_stats;    /* [2, ld]   packed contact-count history summary; NULL = not tracked */
+    uint32_t* ep_stats;    /* [2, ld]   packed contact-count history summary; NULL = not tracked.  Holds episodes of up to
+                            *           5,242 steps: calls that could run a tracked episode longer than that
+                            *           (min(loop_max_steps, max_episode_steps + 1)) return DEXSIM_E_PARAM */
 } DexsimState;
 
 /* Scalars of one DexterousManipulationEnv construction + the batched env's own switches. */
@@ -137,7 +140,9 @@ typedef struct DexsimGroup {
 
 /* Inputs / outputs of one batched step (all device pointers, SoA with the state's ld). */
 typedef struct DexsimStepIO {
-    const float* action;        /* [15, ld] (layout 0) or [n, 15] (layout 1); required for dexsim_step */
+    const float* action;        /* [15, ld] (layout 0) or [n, 15] (layout 1); required for dexsim_step.  A 16-byte aligned
+                                 * base takes the vectorised / bulk-copy paths; any other alignment (e.g. an [n,15] slice
+                                 * that starts at an odd env) is read with scalar loads by the register-resident kernel. */
     int32_t      action_layout; /* 0 = SoA [15, ld], 1 = AoS [n, 15] (the reference's per-env layout) */
     int32_t      pad_;
     const float* dyn_noise;     /* [15, ld] pre-drawn float32 N(0, sigma_dyn) or NULL (robustness_tests.py:180-187) */
@@ -162,7 +167,13 @@ typedef struct DexsimStepIO {
      * (episode, step count AFTER the step and a possible auto-reset) (:204-205); needs `noisy_obs`. */
     float        sigma_dyn;
     float        sigma_obs;
+    /* Scratch of the pipelined step kernel's dynamic tile scheduler: DEXSIM_SCHED_WORDS zero-initialised device words,
+     * or NULL = static round-robin tile assignment.  The kernel hands tiles to its CTAs from a counter kept here and
+     * leaves the words zero again; one buffer per step that can be in flight at a time (calls on the same stream may
+     * share it).  dexsim_step uses words 0-1, dexsim_step_host words 2c, 2c+1 for its chunk c. */
+    uint32_t*    sched;
 } DexsimStepIO;
+#define DEXSIM_SCHED_WORDS 64
 
 /* ---- library ---------------------------------------------------------------------------- */
 int         dexsim_version(void);            /* DEXSIM_ABI_VERSION */
@@ -222,7 +233,9 @@ typedef struct DexsimEpisodeRecord {
     uint8_t  label_taxonomy;   /* evaluation/failure_taxonomy.py label code or DEXSIM_LABEL_NONE */
     double   episode_reward;   /* "episode_reward", float64 running sum */
     uint32_t t_end;            /* step_base + index of the step that ended the episode */
-    uint32_t var_tie;          /* 1: a variance threshold was hit exactly (label resolved as in exact arithmetic) */
+    uint32_t var_tie;          /* a variance threshold was hit exactly: 2 = decided by NumPy's np.var arithmetic on the recorded
+                                * history (DexsimRolloutIO.hist), label exact; 1 = no history recorded, label resolved as in
+                                * exact arithmetic -- re-label it with dexsim_classify_summary(counts) */
 } DexsimEpisodeRecord;
 
 typedef struct DexsimRolloutIO {
@@ -294,7 +307,13 @@ typedef struct DexsimEpisodeSummary {
     int32_t max_count, sum_counts, sum_sq_counts;
     int32_t first5_sum, last5_sum;
 } DexsimEpisodeSummary;
-int dexsim_classify_summary(const DexsimEpisodeSummary* s, int32_t max_steps, int32_t success_threshold,
+/* `counts`: the hist_len per-step contact counts (host pointer) or NULL.  Both classifiers threshold
+ * np.var(contact_counts) (metrics.py:77-80, failure_taxonomy.py:189,219-230).  The summary decides every case except an
+ * exact tie with a threshold, where NumPy's pairwise float64 sum can land on either side: with `counts` the tie is
+ * decided by the same arithmetic np.var performs (*var_tie = 2, labels bit-exact); without it as in exact arithmetic
+ * (*var_tie = 1, label unconfirmed).  *var_tie = 0: no tie, the labels are exact either way. */
+int dexsim_classify_summary(const DexsimEpisodeSummary* s, const uint8_t* counts /* [hist_len] or NULL */,
+                            int32_t max_steps, int32_t success_threshold,
                             int32_t* label_metrics, int32_t* label_taxonomy, int32_t* var_tie);
 
 /* ---- host-buffer step (end-to-end path): actions in HOST memory -> device -> step ->

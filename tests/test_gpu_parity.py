@@ -110,6 +110,32 @@ def test_noise_wrapper_golden(dx, golden_dir):
         np.testing.assert_allclose(rew.cpu().numpy(), g["reward"][:, t], rtol=REWARD_RTOL, atol=REWARD_ATOL)
 
 
+def test_noise_wrapper_golden_on_the_tma_pipeline(dx, golden_dir):
+    """The same golden (CombinedNoiseWrapper with its own normal draws replayed, evaluation/robustness_tests.py:177-207)
+    served by the TMA/mbarrier step kernel: the six golden envs are tiled to 192 so that the batch is pipeline-sized,
+    and the register-resident kernel is switched off for the test."""
+    from dexterous_rl_manipulation_b200 import _lib
+    g = _load(golden_dir, "noise.npz")
+    reps = 32
+    n0, T = g["actions"].shape[:2]
+    n = n0 * reps
+    tile = lambda a: np.concatenate([a] * reps, axis=0)
+    env = _make_env(dx, n, True, int(g["max_steps"]))
+    obs0, _ = env.reset_from_draws(tile(g["jp0"]), tile(g["size"]), tile(g["mass"]), tile(g["friction"]), tile(g["pos"]))
+    _lib.set_step_impl("tma")
+    try:
+        for t in range(T):
+            obs, rew, te, tr, info = env.step(torch.from_numpy(tile(g["actions"][:, t])).cuda(),
+                                              dyn_noise=tile(g["dyn_noise"][:, t]), obs_noise=tile(g["obs_noise"][:, t + 1]))
+            assert np.array_equal(obs.cpu().numpy(), tile(g["obs"][:, t + 1])), t
+            assert np.array_equal(te.cpu().numpy(), tile(g["terminated"][:, t]))
+            assert np.array_equal(tr.cpu().numpy(), tile(g["truncated"][:, t]))
+            assert np.array_equal(info["num_contacts"].cpu().numpy(), tile(g["num_contacts"][:, t]))
+            np.testing.assert_allclose(rew.cpu().numpy(), tile(g["reward"][:, t]), rtol=REWARD_RTOL, atol=REWARD_ATOL)
+    finally:
+        _lib.set_step_impl("auto")
+
+
 def _random_draws(rng, n, ragged=True):
     jp0 = rng.uniform(-0.1, 0.1, (n, 15)).astype(np.float32)
     size = rng.uniform(0.02, 0.12, n)
@@ -122,17 +148,33 @@ def _random_draws(rng, n, ragged=True):
     return jp0, size, mass, fric, pos
 
 
-@pytest.mark.parametrize("n,dense,comps", [(1, True, True), (33, False, True), (1000, True, True), (4096, True, True),
-                                           (1000, True, False), (4096, False, False), (20000, True, False)])
-def test_step_matches_oracle(dx, n, dense, comps):
-    """Ragged batch sizes (1, 33, 1000 are not multiples of the warp / CTA size) vs the oracle."""
+@pytest.fixture
+def step_impl():
+    """Pin dexsim_step to one of its two kernels for a test (the auto choice goes by batch size: small batches take
+    the register-resident kernel, large ones the TMA pipeline); restored afterwards."""
+    from dexterous_rl_manipulation_b200 import _lib
+
+    def choose(impl):
+        _lib.set_step_impl(impl)
+    yield choose
+    _lib.set_step_impl("auto")
+
+
+@pytest.mark.parametrize("n,dense,comps,impl", [(1, True, True, "auto"), (33, False, True, "auto"), (1000, True, True, "register"),
+                                                (1000, True, True, "tma"), (4096, True, True, "tma"), (1000, True, False, "tma"),
+                                                (4096, False, False, "tma"), (4096, False, False, "register"),
+                                                (20000, True, False, "tma"), (20000, True, False, "auto")])
+def test_step_matches_oracle(dx, n, dense, comps, impl, step_impl):
+    """Ragged batch sizes (1, 33, 1000 are not multiples of the warp / CTA size) vs the oracle, through both step
+    kernels (with and without the reward-component outputs)."""
     from oracle import oracle
+    step_impl(impl)
     rng = np.random.default_rng(n)
     jp0, size, mass, fric, pos = _random_draws(rng, n)
     ob = oracle.OracleBatch(n, dense=dense, max_episode_steps=60)
     o0 = ob.reset_predrawn(jp0, size, mass, fric, pos)
     env = None
-    if n > 1:       # comps=False keeps the call eligible for the TMA pipeline kernel (n >= 128)
+    if n > 1:
         env = dx.BatchedManipulationEnv(n, "cuda", max_episode_steps=60, reward_type="dense" if dense else "sparse",
                                         reward_components=comps)
     if n == 1:
@@ -201,8 +243,10 @@ def test_fused_rollout_matches_oracle(dx, policy, dense, respawn, n):
     np.testing.assert_allclose(env._ep_return[:n].cpu().numpy(), ob.env["ep_return"], rtol=1e-12, atol=1e-12)
 
 
-def test_step_autoreset_equals_fused_rollout(dx):
+@pytest.mark.parametrize("impl", ["register", "tma"])
+def test_step_autoreset_equals_fused_rollout(dx, impl, step_impl):
     """Stepping with the exposed Philox actions + in-kernel auto-reset == the fused rollout kernel."""
+    step_impl(impl)
     from dexterous_rl_manipulation_b200 import _lib
     import ctypes as C
     CC = dx.CurriculumConfig
@@ -224,9 +268,11 @@ def test_step_autoreset_equals_fused_rollout(dx):
     torch.testing.assert_close(a.ret_sums, b.ret_sums, rtol=1e-9, atol=0)
 
 
-def test_noisy_step_equals_noisy_fused_rollout(dx):
+@pytest.mark.parametrize("impl", ["register", "tma"])
+def test_noisy_step_equals_noisy_fused_rollout(dx, impl, step_impl):
     """Dynamics-noise cells (per-group sigma): API stepping with in-kernel noise == the fused rollout kernel's noise --
     two independent code paths drawing from the same Philox stream keyed by (env, episode, step)."""
+    step_impl(impl)
     from dexterous_rl_manipulation_b200 import _lib
     import ctypes as C
     CC = dx.CurriculumConfig
@@ -458,10 +504,60 @@ def test_tma_pipeline_equals_register_kernel(dx, n, track, dense):
         _lib.set_step_impl("auto")
 
 
+@pytest.mark.parametrize("n,track,ranged,respawn,predrawn", [(4096 + 77, False, False, True, False), (1000, True, False, True, False),
+                                                            (70_000, "counts", True, True, False), (5000, True, True, False, False),
+                                                            (3000, "counts", False, True, True)])
+def test_tma_pipeline_noise_and_components_equal_register_kernel(dx, n, track, ranged, respawn, predrawn):
+    """Noise (Philox in-kernel or pre-drawn), reward components and the float64 reward on the TMA pipeline
+    (EXTRA instantiations) against the register-resident kernel: every output and every state array bit for bit,
+    across auto-resets in both spawn modes and with ranged size / mass / friction groups (Philox blocks 5-6 of the
+    warp-cooperative reset)."""
+    from dexterous_rl_manipulation_b200 import _lib
+    CC = dx.CurriculumConfig
+    g1 = CC(object_size_range=(0.03, 0.09), object_mass_range=(0.05, 0.3), friction_range=(0.2, 0.9)) if ranged else CC.hard()
+    kw = dict(max_episode_steps=20, reward_type="dense", seed=11, groups=[CC.easy(), g1], reward_components=True)
+    if not predrawn:
+        kw.update(observation_noise_std=0.05, dynamics_noise_std=0.1)
+    if track:
+        kw.update(auto_reset=True, respawn=respawn, loop_max_steps=20, track_episodes=track != "counts")
+    envs = {}
+    try:
+        for impl in ("register", "tma"):
+            env = dx.BatchedManipulationEnv(n, "cuda", **kw)
+            env.reset(seed=11)
+            envs[impl] = env
+        gen = torch.Generator(device="cuda").manual_seed(8)
+        for t in range(50):
+            a = torch.rand(n, 15, device="cuda", generator=gen) * 2.6 - 1.3
+            extra = {}
+            if predrawn:
+                extra = dict(dyn_noise=torch.randn(n, 15, device="cuda", generator=gen) * 0.1,
+                             obs_noise=torch.randn(n, 45, device="cuda", generator=gen) * 0.05)
+            outs = {}
+            for impl, env in envs.items():
+                _lib.set_step_impl(impl)
+                o = env.step(a, **extra)
+                rc = o[4]["reward_components"]
+                outs[impl] = [x.clone() for x in o[:4]] + [o[4]["num_contacts"].clone()] + [rc[k].clone() for k in ("distance", "contact", "closure", "stability")]
+            for x, y in zip(outs["register"], outs["tma"]):
+                assert torch.equal(x, y), t
+        a, b = envs["register"], envs["tma"]
+        for name in ("_obs", "_op64", "_thr", "_damp", "_step_count", "_cmask", "_size", "_mass", "_friction", "_episode", "_noisy_obs"):
+            assert torch.equal(getattr(a, name), getattr(b, name)), name
+        if track:
+            assert torch.equal(a.counters, b.counters) and int(a.counters[:, 0].sum()) > n
+        if track is True:
+            assert torch.equal(a._ep_stats, b._ep_stats) and torch.equal(a._ep_return, b._ep_return)
+    finally:
+        _lib.set_step_impl("auto")
+
+
 @pytest.mark.parametrize("n,track", [(1000, False), (4096 + 5, True)])
-def test_in_kernel_noise_equals_separate_noise_kernels(dx, n, track):
+@pytest.mark.parametrize("impl", ["register", "tma"])
+def test_in_kernel_noise_equals_separate_noise_kernels(dx, n, track, impl, step_impl):
     """DexsimStepIO.sigma_dyn / sigma_obs (Philox normals drawn inside the step kernel) give exactly what the
     separate dexsim_fill_normal launches + add give: same streams, same counters, also across auto-resets."""
+    step_impl(impl)
     CC = dx.CurriculumConfig
     kw = dict(max_episode_steps=20, reward_type="dense", seed=9, curriculum_config=CC.easy(),
               observation_noise_std=0.05, dynamics_noise_std=0.1)
@@ -486,9 +582,11 @@ def test_in_kernel_noise_equals_separate_noise_kernels(dx, n, track):
         assert torch.equal(a.counters, b.counters) and int(a.counters[:, 0].sum()) > n
 
 
-def test_group_noise_cells_in_step(dx):
+@pytest.mark.parametrize("impl", ["register", "tma"])
+def test_group_noise_cells_in_step(dx, impl, step_impl):
     """Noise cells as groups of one batch (group_sigma_*), stepped through the API with external actions: every
     env behaves like the same env of a batch whose env-level noise is its group's value."""
+    step_impl(impl)
     CC = dx.CurriculumConfig
     n, cfg = 2048, CC.medium()
     kw = dict(max_episode_steps=30, reward_type="dense", seed=4)
@@ -1321,3 +1419,118 @@ def test_custom_python_reward_object_on_the_single_env_path(dx):
     assert r_new.calls == r_ref.calls > 10 and r_new.resets == r_ref.resets == 2
     with pytest.raises(NotImplementedError):
         dx.BatchedManipulationEnv(8, "cuda", reward_shaping=ShapedByHeight())
+
+
+def test_variance_ties_through_a_real_rollout(dx):
+    """Exact variance ties (np.var(contact_counts) == 2.0 in exact arithmetic, where NumPy's pairwise float sum lands
+    on either side) forced through a fused rollout with external actions: with the contact threshold raised to 5 and
+    per-finger action biases the contact count wanders over 0..5 and a few in a thousand episodes hit the tie.  With the
+    history recorded the device decides them with np.var's own arithmetic (var_tie == 2); every label must equal the
+    oracle's (full-history np.var emulation, pinned to the reference) and -- when present -- the UNMODIFIED reference
+    classifiers'; without the history the same episodes are only flagged (var_tie == 1, DEXSIM_CNT_VAR_TIES) and the
+    evaluation front-end's host re-labelling gives the exact labels."""
+    from oracle import oracle, ref_harness
+    from dexterous_rl_manipulation_b200 import _lib
+    from dexterous_rl_manipulation_b200.evaluation import _episode_dict, count_rows
+    n, T, thr = 16384, 80, 5
+    rng = np.random.default_rng(7)
+    bias = rng.uniform(-1, 1, (1, n, 5, 1)).astype(np.float32)
+    acts = np.clip(np.repeat(bias, 3, axis=3).reshape(1, n, 15) + rng.normal(0, 0.3, (T, n, 15)).astype(np.float32), -1.5, 1.5)
+    acts = torch.from_numpy(acts.astype(np.float32))
+    logs = {}
+    for with_hist in (True, False):
+        env = dx.BatchedManipulationEnv(n, "cuda", max_episode_steps=T, reward_type="dense", track_episodes=True,
+                                        curriculum_config=dx.CurriculumConfig.easy(), seed=7)
+        env._params.success_threshold = thr
+        env.reset(seed=7)
+        env.enable_episode_log(n)
+        if with_hist:
+            env.enable_history(T)
+        env.rollout(T, policy="external", actions=acts, success_is_terminated=False, one_episode=True, loop_max_steps=T,
+                    zero_counters=True)
+        log = env.read_episode_log()
+        assert len(log) == n
+        logs[with_hist] = (log, env._hist[:, :n].cpu().numpy() if with_hist else None, env.counters.cpu().numpy().copy())
+    log, hist, cnt = logs[True]
+    log0, _, cnt0 = logs[False]
+    assert np.array_equal(log["env_gid"], log0["env_gid"]) and np.array_equal(log["steps"], log0["steps"])
+    ties = np.nonzero(log["var_tie"] == 2)[0]
+    assert len(ties) >= 5, len(ties)
+    assert np.array_equal(log0["var_tie"] == 1, log["var_tie"] == 2) and not np.any(log["var_tie"] == 1)
+    assert int(cnt[:, _lib.CNT_VAR_TIES].sum()) == 0 and int(cnt0[:, _lib.CNT_VAR_TIES].sum()) == len(ties)
+    R = ref_harness.load() if ref_harness.available() else None
+    changed = 0
+    for q in range(n):
+        r = log[q]
+        i = int(r["env_gid"])
+        counts = hist[:int(r["steps"]), i]
+        ea, eb, _ = oracle.classify(False, int(r["steps"]), int(r["final_contacts"]), int(r["final_contacts"]), counts,
+                                    max_steps=T, threshold=thr)
+        ea, eb = (255 if ea < 0 else ea), (255 if eb < 0 else eb)
+        assert (int(r["label_metrics"]), int(r["label_taxonomy"])) == (ea, eb), (q, counts.tolist())
+        if r["var_tie"] == 2:
+            # host re-labelling (evaluation front-ends) of the record the device could only flag
+            d = _episode_dict(log0[q], counts, 0.08, 0.05, 0.8, max_steps=T, success_threshold=thr)
+            assert d["failure_type"] == dx.LABELS_METRICS[ea] and d["failure_mode"] == dx.LABELS_TAXONOMY[eb]
+            la, lb = _lib.classify_counts(False, int(r["steps"]), int(r["final_contacts"]), int(r["final_contacts"]), counts,
+                                          max_steps=T, success_threshold=thr)
+            assert (la, lb) == (ea, eb)
+            changed += (int(log0[q]["label_metrics"]), int(log0[q]["label_taxonomy"])) != (ea, eb)
+            if R is not None:
+                ep = {"success": False, "episode_steps": int(r["steps"]), "num_contacts": int(r["final_contacts"]),
+                      "final_contacts": int(r["final_contacts"]), "contact_history": count_rows(counts)}
+                ra = R.metrics.EvaluationMetrics(thr).classify_failure(dict(ep), max_steps=T)
+                rb, _conf = R.failure_taxonomy.FailureClassifier(thr).classify(dict(ep), max_steps=T)
+                assert ra.value == dx.LABELS_METRICS[ea] and rb.value == dx.LABELS_TAXONOMY[eb]
+    # the label counters follow the corrected labels
+    for code in range(6):
+        assert int(cnt[:, _lib.CNT_LABEL_METRICS + code].sum()) == int((log["label_metrics"] == code).sum())
+        assert int(cnt[:, _lib.CNT_LABEL_TAXONOMY + code].sum()) == int((log["label_taxonomy"] == code).sum())
+
+
+def test_misaligned_aos_action_pointer(dx, step_impl):
+    """An [n,15] action slice that starts at an odd env (60-byte stride => base not 16-byte aligned) handed straight to
+    the C ABI: the register-resident kernel reads it with scalar loads, results identical to an aligned copy."""
+    import ctypes as C
+    from dexterous_rl_manipulation_b200 import _lib
+    n = 1000
+    kw = dict(max_episode_steps=50, reward_type="dense", seed=2)
+    a, b = dx.BatchedManipulationEnv(n, "cuda", **kw), dx.BatchedManipulationEnv(n, "cuda", **kw)
+    a.reset(seed=2); b.reset(seed=2)
+    big = torch.rand(n + 3, 15, device="cuda") * 2.4 - 1.2
+    for off in (1, 2, 3):
+        view = big[off:off + n]
+        assert view.data_ptr() % 16 != 0
+        io = a._io
+        io.action, io.action_layout = view.data_ptr(), 1
+        _lib.check(a._lib.dexsim_step(a._state_ref, a._params_ref, a._groups_ptr, a._goe_ptr, a._io_ref, a._stream()), "dexsim_step")
+        step_impl("register")
+        b.step(view.clone())
+        step_impl("auto")
+        assert torch.equal(a._obs, b._obs) and torch.equal(a._reward, b._reward) and torch.equal(a._op64, b._op64)
+
+
+def test_state_dict_resumes_bit_for_bit(dx):
+    """state_dict() / load_state_dict(): a resumed run continues exactly like the uninterrupted one -- device state,
+    the host PCG64 generators of rng="numpy" resets, Philox seed, rollout step base and the per-env learners."""
+    CC = dx.CurriculumConfig
+    def make():
+        env = dx.BatchedManipulationEnv(64, "cuda", max_episode_steps=15, reward_type="dense", track_episodes=True,
+                                        rng="numpy", curriculum_config=CC(object_size_range=(0.03, 0.08)), seed=5)
+        env.enable_learner()
+        env.reset(seed=5)
+        return env
+    a = make()
+    a.rollout(20, policy="learner", respawn=False)
+    a.reset()                                              # draws from the host generators
+    sd = a.state_dict()
+    b = make()
+    b.load_state_dict(sd)
+    for env in (a, b):
+        env.rollout(20, policy="learner", respawn=False)
+        env.reset()                                        # the next host draws must agree as well
+        env.rollout(7, policy="random")
+    for name in ("_obs", "_op64", "_size", "_mass", "_friction", "_episode", "_step_count", "_learner_mean", "_learner_best",
+                 "counters", "_ep_return", "_ep_stats"):
+        assert torch.equal(getattr(a, name), getattr(b, name)), name
+    assert a._rollout_steps == b._rollout_steps and a.seed == b.seed
