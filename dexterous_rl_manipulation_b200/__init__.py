@@ -25,12 +25,13 @@ from . import distributed  # noqa: E402
 from .curriculum import BatchedCurriculumDriver, CurriculumScheduler  # noqa: E402
 from . import evaluation  # noqa: E402
 from . import training  # noqa: E402
+from .training import run_episodes_batched  # noqa: E402
 
 DexterousManipulationEnv = BatchedManipulationEnv   # the reference's class name, for drop-in imports
 
 __all__ = [
     "BatchedManipulationEnv", "DexterousManipulationEnv", "Box", "CurriculumConfig", "group_from_config",
-    "group_table", "classify_summary", "classify_counts", "evaluation", "training", "BatchedCurriculumDriver", "CurriculumScheduler", "DexsimError", "distributed", "LABELS_METRICS", "LABELS_TAXONOMY",
+    "group_table", "classify_summary", "classify_counts", "run_episodes_batched", "evaluation", "training", "BatchedCurriculumDriver", "CurriculumScheduler", "DexsimError", "distributed", "LABELS_METRICS", "LABELS_TAXONOMY",
     "LABEL_NONE", "NCOUNTERS", "CNT_EPISODES", "CNT_SUCCESSES", "CNT_SUM_STEPS", "CNT_SUM_FINAL_CONTACTS",
     "CNT_LABEL_METRICS", "CNT_LABEL_TAXONOMY", "CNT_VAR_TIES", "CNT_SUM_STEPS_SQ",
 ]

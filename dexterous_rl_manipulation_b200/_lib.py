@@ -24,7 +24,7 @@ RNG_STREAM_DYN, RNG_STREAM_OBS = 2, 3
 EPISODE_RECORD_DTYPE = _np.dtype([("env_gid", "u4"), ("episode", "u4"), ("steps", "i4"), ("success", "u1"),
                                   ("final_contacts", "u1"), ("label_metrics", "u1"), ("label_taxonomy", "u1"),
                                   ("episode_reward", "f8"), ("t_end", "u4"), ("var_tie", "u4")])
-HOST_SKIP_QUAT = 1
+HOST_SKIP_QUAT, HOST_ASYNC, HOST_PACKED_CONTACTS = 1, 2, 4
 SCHED_WORDS = 64
 ROLLOUT_NO_DYN_NOISE = 1
 
@@ -144,7 +144,7 @@ def lib():
     L.dexsim_classify_summary.argtypes = [C.POINTER(DexsimEpisodeSummary), vp, i32, i32, C.POINTER(i32),
                                           C.POINTER(i32), C.POINTER(i32)]
     L.dexsim_step_host.argtypes = [C.POINTER(DexsimState), C.POINTER(DexsimParams), vp, vp, C.POINTER(DexsimStepIO),
-                                   vp, vp, vp, vp, vp, vp, i32, i32, vp]
+                                   vp, vp, vp, vp, vp, vp, vp, i32, i32, vp]
     for name in EXPORTS:
         fn = getattr(L, name)          # raises AttributeError if a declared symbol is not exported
         if name not in ("dexsim_error_string",):

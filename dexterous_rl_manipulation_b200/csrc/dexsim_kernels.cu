@@ -1148,16 +1148,20 @@ int dexsim_classify_summary(const DexsimEpisodeSummary* s, const uint8_t* counts
 //      overlap (separate copy engines per direction).  Internal streams/events are created once per
 //      device and fork from / join into the caller's stream, so the call stays stream-ordered. ----------
 namespace {
-constexpr int HOST_STREAMS = 3;
+constexpr int HOST_STREAMS = 3;        // chunk c: upload, kernel and observation download on stream c % 3
+constexpr int HOST_MAX_CHUNKS = 32;
 struct HostPipe {
     bool ready = false;
     cudaStream_t streams[HOST_STREAMS];
+    cudaStream_t small;                // per-env vectors (reward, flags) of the WHOLE batch: a few large copies instead of
+                                       // one small copy per vector per chunk
     cudaEvent_t fork_ev;
-    cudaEvent_t join_ev[HOST_STREAMS];
+    cudaEvent_t join_ev[HOST_STREAMS + 1];
+    cudaEvent_t kdone[HOST_MAX_CHUNKS];
 };
 HostPipe g_pipes[64];
 std::mutex g_pipes_mutex;      // first use from several host threads at once
-std::mutex g_enqueue_mutex;    // the fork / join events of a device's pipe are reused by every call
+std::mutex g_enqueue_mutex[64];   // per device: the fork / join events of a device's pipe are reused by every call on it
 
 int get_pipe(HostPipe** out) {
     int dev = 0;
@@ -1170,7 +1174,15 @@ int get_pipe(HostPipe** out) {
         for (int k = 0; k < HOST_STREAMS; ++k) {
             err = cudaStreamCreateWithFlags(&hp.streams[k], cudaStreamNonBlocking);
             if (err != cudaSuccess) return -(int)err;
+        }
+        err = cudaStreamCreateWithFlags(&hp.small, cudaStreamNonBlocking);
+        if (err != cudaSuccess) return -(int)err;
+        for (int k = 0; k < HOST_STREAMS + 1; ++k) {
             err = cudaEventCreateWithFlags(&hp.join_ev[k], cudaEventDisableTiming);
+            if (err != cudaSuccess) return -(int)err;
+        }
+        for (int k = 0; k < HOST_MAX_CHUNKS; ++k) {
+            err = cudaEventCreateWithFlags(&hp.kdone[k], cudaEventDisableTiming);
             if (err != cudaSuccess) return -(int)err;
         }
         err = cudaEventCreateWithFlags(&hp.fork_ev, cudaEventDisableTiming);
@@ -1185,10 +1197,11 @@ int get_pipe(HostPipe** out) {
 int dexsim_step_host(const DexsimState* st, const DexsimParams* p, const DexsimGroup* groups,
                      const uint16_t* group_of_env, const DexsimStepIO* io, const float* h_action, float* h_obs,
                      float* h_reward, uint8_t* h_terminated, uint8_t* h_truncated, uint8_t* h_num_contacts,
-                     int32_t chunks, int32_t flags, void* stream) {
+                     uint8_t* h_contact_mask, int32_t chunks, int32_t flags, void* stream) {
     int rc = check_state(st);
     if (rc) return rc;
     if (!p || !io || !io->action || !h_action || !h_reward || !h_terminated || !h_truncated) return DEXSIM_E_NULL;
+    if ((flags & DEXSIM_HOST_PACKED_CONTACTS) && !h_contact_mask) return DEXSIM_E_NULL;
     if (io->dyn_noise || io->obs_noise || io->noisy_obs || io->sigma_dyn != 0.0f || io->sigma_obs != 0.0f)
         return DEXSIM_E_PARAM;   // noise: use dexsim_step
     cudaStream_t user = (cudaStream_t)stream;
@@ -1196,24 +1209,49 @@ int dexsim_step_host(const DexsimState* st, const DexsimParams* p, const DexsimG
     if (n == 0) return 0;
     const bool aos = io->action_layout == 1;
     // chunk boundaries are multiples of 1024 envs (tile- and alignment-friendly)
+    if (chunks > HOST_MAX_CHUNKS) chunks = HOST_MAX_CHUNKS;
     int64_t per = ((n + (chunks > 0 ? chunks : 1) - 1) / (chunks > 0 ? chunks : 1) + 1023) / 1024 * 1024;
     const int nchunks = (int)((n + per - 1) / per);
     HostPipe* hp = nullptr;
-    // The device's internal streams and events are shared by every caller: enqueue one step at a time.
-    std::unique_lock<std::mutex> enqueue_lock(g_enqueue_mutex, std::defer_lock);
+    int dev = 0;
+    // A device's internal streams and events are shared by every caller on that device: enqueue one step at a time
+    // per device (callers driving different GPUs from different host threads do not wait for each other).
+    std::unique_lock<std::mutex> enqueue_lock;
     if (nchunks > 1) {
         rc = get_pipe(&hp);
         if (rc) return rc;
-        enqueue_lock.lock();
-        cudaError_t err = cudaEventRecord(hp->fork_ev, user);
+        cudaError_t err = cudaGetDevice(&dev);
+        if (err != cudaSuccess) return -(int)err;
+        enqueue_lock = std::unique_lock<std::mutex>(g_enqueue_mutex[dev & 63]);
+        err = cudaEventRecord(hp->fork_ev, user);
         if (err != cudaSuccess) return -(int)err;
         for (int k = 0; k < HOST_STREAMS && k < nchunks; ++k) {
             err = cudaStreamWaitEvent(hp->streams[k], hp->fork_ev, 0);
             if (err != cudaSuccess) return -(int)err;
         }
     }
+    // observation rows that travel: all 45, or without the constant quaternion rows 33-36 (SKIP_QUAT), and without the
+    // five 0/1 contact rows 40-44 when the 1-byte contact mask is sent instead (PACKED_CONTACTS)
+    const int rows_hi = (flags & DEXSIM_HOST_PACKED_CONTACTS) ? DEXSIM_ROW_CONTACT : DEXSIM_OBS;
     // Whatever happens while enqueueing, the caller's stream is joined with the internal ones before returning,
     // so that no copy is still in flight on a stream the caller cannot see.
+    auto copy_vectors = [&](cudaStream_t s, int64_t lo, int64_t m) -> int {
+        cudaError_t err = cudaMemcpyAsync(h_reward + lo, io->reward + lo, (size_t)m * sizeof(float), cudaMemcpyDeviceToHost, s);
+        if (err != cudaSuccess) return -(int)err;
+        err = cudaMemcpyAsync(h_terminated + lo, io->terminated + lo, (size_t)m, cudaMemcpyDeviceToHost, s);
+        if (err != cudaSuccess) return -(int)err;
+        err = cudaMemcpyAsync(h_truncated + lo, io->truncated + lo, (size_t)m, cudaMemcpyDeviceToHost, s);
+        if (err != cudaSuccess) return -(int)err;
+        if (h_num_contacts) {
+            err = cudaMemcpyAsync(h_num_contacts + lo, io->num_contacts + lo, (size_t)m, cudaMemcpyDeviceToHost, s);
+            if (err != cudaSuccess) return -(int)err;
+        }
+        if (flags & DEXSIM_HOST_PACKED_CONTACTS) {
+            err = cudaMemcpyAsync(h_contact_mask + lo, st->cmask + lo, (size_t)m, cudaMemcpyDeviceToHost, s);
+            if (err != cudaSuccess) return -(int)err;
+        }
+        return 0;
+    };
     auto enqueue_chunks = [&]() -> int {
     for (int c = 0; c < nchunks; ++c) {
         const int64_t lo = (int64_t)c * per, hi = (lo + per < n) ? lo + per : n, m = hi - lo;
@@ -1240,6 +1278,10 @@ int dexsim_step_host(const DexsimState* st, const DexsimParams* p, const DexsimG
         if (err != cudaSuccess) return -(int)err;
         rc = launch_step(&sub, &sp, groups, group_of_env ? group_of_env + lo : nullptr, &sio, s);
         if (rc) return rc;
+        if (nchunks > 1) {
+            err = cudaEventRecord(hp->kdone[c], s);      // this chunk's kernel has run: its per-env vectors are final
+            if (err != cudaSuccess) return -(int)err;
+        }
         if (h_obs) {
             if (flags & DEXSIM_HOST_SKIP_QUAT) {     // rows 33-36 are the constant (1,0,0,0): caller keeps them
                 err = cudaMemcpy2DAsync(h_obs + lo, (size_t)ld * 4, st->obs + lo, (size_t)ld * 4, (size_t)m * 4,
@@ -1247,23 +1289,28 @@ int dexsim_step_host(const DexsimState* st, const DexsimParams* p, const DexsimG
                 if (err != cudaSuccess) return -(int)err;
                 err = cudaMemcpy2DAsync(h_obs + (size_t)DEXSIM_ROW_OV * ld + lo, (size_t)ld * 4,
                                         st->obs + (size_t)DEXSIM_ROW_OV * ld + lo, (size_t)ld * 4, (size_t)m * 4,
-                                        DEXSIM_OBS - DEXSIM_ROW_OV, cudaMemcpyDeviceToHost, s);
+                                        rows_hi - DEXSIM_ROW_OV, cudaMemcpyDeviceToHost, s);
             } else {
-                err = cudaMemcpy2DAsync(h_obs + lo, (size_t)ld * 4, st->obs + lo, (size_t)ld * 4, (size_t)m * 4, DEXSIM_OBS,
+                err = cudaMemcpy2DAsync(h_obs + lo, (size_t)ld * 4, st->obs + lo, (size_t)ld * 4, (size_t)m * 4, rows_hi,
                                         cudaMemcpyDeviceToHost, s);
             }
             if (err != cudaSuccess) return -(int)err;
         }
-        err = cudaMemcpyAsync(h_reward + lo, io->reward + lo, (size_t)m * sizeof(float), cudaMemcpyDeviceToHost, s);
-        if (err != cudaSuccess) return -(int)err;
-        err = cudaMemcpyAsync(h_terminated + lo, io->terminated + lo, (size_t)m, cudaMemcpyDeviceToHost, s);
-        if (err != cudaSuccess) return -(int)err;
-        err = cudaMemcpyAsync(h_truncated + lo, io->truncated + lo, (size_t)m, cudaMemcpyDeviceToHost, s);
-        if (err != cudaSuccess) return -(int)err;
-        if (h_num_contacts) {
-            err = cudaMemcpyAsync(h_num_contacts + lo, io->num_contacts + lo, (size_t)m, cudaMemcpyDeviceToHost, s);
+        if (nchunks == 1) {
+            rc = copy_vectors(s, 0, n);
+            if (rc) return rc;
+        }
+    }
+    if (nchunks > 1) {
+        // reward / flags of the whole batch in one copy per vector (5 copies instead of 5 per chunk: every copy costs
+        // the DMA engine a few microseconds whatever its size), on their own stream once every chunk's kernel has run --
+        // the kernels finish long before the observation downloads do, so these ride along with them
+        for (int c = 0; c < nchunks; ++c) {
+            cudaError_t err = cudaStreamWaitEvent(hp->small, hp->kdone[c], 0);
             if (err != cudaSuccess) return -(int)err;
         }
+        rc = copy_vectors(hp->small, 0, n);
+        if (rc) return rc;
     }
     return 0;
     };
@@ -1274,8 +1321,14 @@ int dexsim_step_host(const DexsimState* st, const DexsimParams* p, const DexsimG
             if (err == cudaSuccess) err = cudaStreamWaitEvent(user, hp->join_ev[k], 0);
             if (err != cudaSuccess && rc == 0) rc = -(int)err;
         }
+        {
+            cudaError_t err = cudaEventRecord(hp->join_ev[HOST_STREAMS], hp->small);
+            if (err == cudaSuccess) err = cudaStreamWaitEvent(user, hp->join_ev[HOST_STREAMS], 0);
+            if (err != cudaSuccess && rc == 0) rc = -(int)err;
+        }
         enqueue_lock.unlock();
     }
+    if ((flags & DEXSIM_HOST_ASYNC) && rc == 0) return 0;          // the caller synchronizes `stream` before reading
     const int sync_rc = cuda_rc(cudaStreamSynchronize(user));
     return rc ? rc : sync_rc;
 }

@@ -230,6 +230,31 @@ class BatchedManipulationEnv:
             self._step_out = (self._obs_view, self._reward[:n], self._terminated[:n].view(torch.bool),
                               self._truncated[:n].view(torch.bool), self._make_info())
 
+    @classmethod
+    def from_experiment_config(cls, cfg, num_envs: int = 1, device="cuda", curriculum_config=None, **kw):
+        """Build the env from the reference's ``ExperimentConfig`` (experiments/experiment_config.py:236-300) or from the
+        dict / JSON it serialises to (``config_default.json`` ...): ``training.max_episode_steps``, ``training.reward_type``,
+        ``training.num_fingers`` / ``joints_per_finger`` and ``training.seed`` are taken from it exactly as the reference's
+        drivers pass them to ``DexterousManipulationEnv`` (evaluation/component_ablation.py:132-140); the curriculum starts
+        at ``curriculum_config`` or, when the config carries a ``curriculum_scheduler`` section, at that scheduler's
+        initial preset.  Other keywords go to the constructor (``auto_reset=...``, ``track_episodes=...``)."""
+        if isinstance(cfg, str):
+            import json
+            with open(cfg) as fh:
+                cfg = json.load(fh)
+        get = (lambda o, k, d=None: o.get(k, d)) if isinstance(cfg, dict) else (lambda o, k, d=None: getattr(o, k, d))
+        tr = get(cfg, "training", {}) or {}
+        tget = (lambda k, d: tr.get(k, d)) if isinstance(tr, dict) else (lambda k, d: getattr(tr, k, d))
+        if curriculum_config is None:
+            sch = get(cfg, "curriculum_scheduler", None)
+            name = None if sch is None else (sch.get("initial_config") if isinstance(sch, dict) else getattr(sch, "initial_config", None))
+            if isinstance(name, str) and hasattr(CurriculumConfig, name):
+                curriculum_config = getattr(CurriculumConfig, name)()
+        kw.setdefault("seed", int(tget("seed", 0)))
+        return cls(num_envs, device, num_fingers=int(tget("num_fingers", 5)), joints_per_finger=int(tget("joints_per_finger", 3)),
+                   max_episode_steps=int(tget("max_episode_steps", 200)), reward_type=tget("reward_type", "dense"),
+                   curriculum_config=curriculum_config, **kw)
+
     # ------------------------------------------------------------------ plumbing
     @staticmethod
     def _ptr(t):
@@ -792,27 +817,46 @@ class BatchedManipulationEnv:
         return self._info
 
     # ------------------------------------------------------------------ host-buffer step (end to end)
-    def step_host(self, action_host, chunks=None):
+    def _host_buffers(self, slot):
+        bufs = getattr(self, "_h_slots", None)
+        if bufs is None:
+            bufs = self._h_slots = {}
+        if slot not in bufs:
+            n, ld = self.num_envs, self.ld
+            pin = lambda *shape, dtype: torch.zeros(*shape, dtype=dtype).pin_memory()
+            b = {"obs": pin(45, ld, dtype=torch.float32), "reward": pin(ld, dtype=torch.float32),
+                 "term": pin(ld, dtype=torch.uint8), "trunc": pin(ld, dtype=torch.uint8), "nc": pin(ld, dtype=torch.uint8),
+                 "cmask": pin(ld, dtype=torch.uint8)}
+            b["obs"][_L.ROW_QUAT].fill_(1.0)          # constant quaternion rows are never re-copied
+            b["info"] = {"num_contacts": b["nc"][:n], "contact_mask": b["cmask"][:n]}
+            b["out"] = (b["obs"][:, :n].t(), b["reward"][:n], b["term"][:n].view(torch.bool), b["trunc"][:n].view(torch.bool),
+                        b["info"])
+            bufs[slot] = b
+        return bufs[slot]
+
+    def step_host(self, action_host, chunks=None, sync=True, packed_contacts=False, slot=0):
         """One step with HOST buffers: ``action_host`` is a float32 [num_envs, 15] NumPy array or CPU
         tensor (pinned memory makes the copies true DMA); returns CPU tensors
         ``(obs [num_envs,45], reward, terminated, truncated, info)`` living in pinned buffers that
-        the next call overwrites.  One C-ABI call (dexsim_step_host): H2D copy of the actions, the
-        step kernel, D2H copies of observation / reward / flags, stream synchronize.  Large batches are
+        the next call with the same ``slot`` overwrites.  One C-ABI call (dexsim_step_host): H2D copy of the actions,
+        the step kernel, D2H copies of observation / reward / flags, stream synchronize.  Large batches are
         split into ``chunks`` ranges (default: one per 65,536 envs, at most 8) so that the upload of one
-        range overlaps the kernel and the download of the others."""
+        range overlaps the kernel and the download of the others.
+
+        ``sync=False``: return as soon as everything is enqueued; call ``host_sync()`` (or synchronize the current
+        stream) before reading the returned tensors.  With two result ``slot`` s a caller can overlap the upload of the
+        next step (or of another env group) with this step's download.
+        ``packed_contacts=True``: the five 0/1 contact columns of the observation (obs[:, 40:45]) are NOT downloaded;
+        ``info["contact_mask"]`` (uint8, bit f = finger f) carries the same information in one byte per env
+        (-11 % download bytes).  ``expand_contacts_host(slot)`` fills the columns in on the host when needed."""
         if not self._did_reset:
             raise RuntimeError("call reset() before step_host()")
-        n, ld = self.num_envs, self.ld
-        if getattr(self, "_h_obs", None) is None:
-            pin = lambda *shape, dtype: torch.zeros(*shape, dtype=dtype).pin_memory()
-            self._h_obs = pin(45, ld, dtype=torch.float32)
-            self._h_obs[_L.ROW_QUAT].fill_(1.0)          # constant quaternion rows are never re-copied
-            self._h_reward = pin(ld, dtype=torch.float32)
-            self._h_term, self._h_trunc, self._h_nc = (pin(ld, dtype=torch.uint8) for _ in range(3))
-            self._h_info = {"num_contacts": self._h_nc[:n]}
+        n = self.num_envs
+        b = self._host_buffers(slot)
         a = action_host if isinstance(action_host, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(action_host, np.float32))
         if a.dtype != torch.float32 or not a.is_contiguous() or a.numel() != n * 15:
             a = a.to(torch.float32).reshape(n, 15).contiguous()
+        flags = _L.HOST_SKIP_QUAT | (0 if sync else _L.HOST_ASYNC) | (_L.HOST_PACKED_CONTACTS if packed_contacts else 0)
         with torch.cuda.device(self.device):
             self._sync_groups()
             io = self._io
@@ -821,12 +865,25 @@ class BatchedManipulationEnv:
             io.sigma_dyn = io.sigma_obs = 0.0
             _lib.check(self._lib.dexsim_step_host(
                 C.byref(self._state), C.byref(self._params), self._ptr(self._groups_dev), self._ptr(self._goe),
-                C.byref(io), a.data_ptr(), self._h_obs.data_ptr(), self._h_reward.data_ptr(), self._h_term.data_ptr(),
-                self._h_trunc.data_ptr(), self._h_nc.data_ptr(),
-                int(chunks) if chunks is not None else max(1, min(8, n // 65536)), _L.HOST_SKIP_QUAT,
-                self._stream()), "dexsim_step_host")
-        return (self._h_obs[:, :n].t(), self._h_reward[:n], self._h_term[:n].view(torch.bool),
-                self._h_trunc[:n].view(torch.bool), self._h_info)
+                C.byref(io), a.data_ptr(), b["obs"].data_ptr(), b["reward"].data_ptr(), b["term"].data_ptr(),
+                b["trunc"].data_ptr(), b["nc"].data_ptr(), b["cmask"].data_ptr(),
+                int(chunks) if chunks is not None else max(1, min(8, n // 65536)), flags, self._stream()), "dexsim_step_host")
+        if not sync:
+            self._host_keepalive = a                   # the upload may still be reading it
+        return b["out"]
+
+    def host_sync(self):
+        """Wait for every ``step_host(sync=False)`` issued on the current stream: their host tensors are valid afterwards."""
+        torch.cuda.current_stream(self.device).synchronize()
+
+    def expand_contacts_host(self, slot=0):
+        """Fill obs[:, 40:45] of a ``packed_contacts`` result in from its contact mask (host-side, vectorised)."""
+        b = self._host_buffers(slot)
+        n = self.num_envs
+        m = b["cmask"][:n]
+        for f in range(5):
+            b["obs"][_L.ROW_CONTACT + f, :n] = ((m >> f) & 1).to(torch.float32)
+        return b["out"][0]
 
     # ------------------------------------------------------------------ fused rollout
     def enable_episode_log(self, capacity):

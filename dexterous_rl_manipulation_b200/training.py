@@ -7,11 +7,39 @@ Here every env of the batch is one such independent training run (its own Simple
 reused env object): ``num_runs`` runs x ``num_episodes`` episodes execute as fused rollouts with the
 learner in-kernel, and the per-episode records come back from the device log.
 """
-from typing import Dict
+from typing import Dict, Optional, Tuple
 
 import numpy as np
 
 from .env import BatchedManipulationEnv
+
+
+def run_episodes_batched(env: BatchedManipulationEnv, policy: str = "random", max_steps: Optional[int] = None,
+                         actions=None, reset: bool = True, seed=None) -> Tuple[np.ndarray, np.ndarray, np.ndarray]:
+    """``run_episode`` (training/episode_utils.py:13-55) for every env of the batch at once: one episode per env in ONE
+    fused launch, returning the reference's triple as arrays ``(success [n] bool, steps [n] int32, total_reward [n]
+    float64)`` indexed by env.
+
+    ``policy``: "random" | "heuristic" | "learner" (generated in-kernel, Philox) or "external" with ``actions`` of shape
+    [max_steps, n, 15].  Semantics are the reference loop's: ``env.reset()`` first (``reset=False`` continues from the
+    current state), at most ``max_steps or env.max_episode_steps`` steps, stop at ``terminated or truncated``, the env is
+    left un-reset; ``success`` is ``info.get("success", False)`` -- always False unless the env was built with
+    ``info_success=True`` (the reference env never sets the key).  Needs ``track_episodes=True``."""
+    n = env.num_envs
+    k = int(max_steps or env.max_episode_steps)
+    if reset:
+        env.reset(seed=seed)
+    env.enable_episode_log(capacity=n)
+    env._rollout_steps = 0
+    kw = {"actions": actions} if policy == "external" else {}
+    env.rollout(k, policy=policy, loop_max_steps=k, success_is_terminated=bool(env.info_success), one_episode=True, **kw)
+    log = env.read_episode_log(sort=False)
+    success, steps, total = np.zeros(n, bool), np.full(n, k, np.int32), np.zeros(n)
+    i = log["env_gid"].astype(np.int64) - env.env_gid0
+    success[i], steps[i], total[i] = log["success"].astype(bool), log["steps"], log["episode_reward"]
+    if len(log) != n:
+        raise RuntimeError(f"{n - len(log)} envs did not finish an episode within {k} steps")
+    return success, steps, total
 
 
 def train_learners_batched(num_runs: int, num_episodes: int, curriculum_config=None, reward_type: str = "dense",

@@ -16,8 +16,8 @@
  *     asynchronous on that stream unless stated; no allocation and no per-call global state
  *     (the only process-wide switches are dexsim_set_step_impl / dexsim_set_rollout_impl, for tests
  *     and profiling) => thread-safe per (device, stream).  dexsim_step_host forks onto a few internal
- *     streams per device, joins them into `stream` and synchronizes it before returning; concurrent
- *     callers are serialised while they enqueue.
+ *     streams per device, joins them into `stream` and (unless DEXSIM_HOST_ASYNC) synchronizes it before
+ *     returning; concurrent callers on the SAME device are serialised while they enqueue.
  *   - Return value: 0 = ok; negative cudaError_t (-e) for CUDA failures; DEXSIM_E_* for
  *     argument errors.  No exceptions cross the boundary.  dexsim_error_string() explains.
  *   - Per-env arrays are structure-of-arrays with leading dimension `ld` (>= n, multiple of
@@ -317,18 +317,27 @@ int dexsim_classify_summary(const DexsimEpisodeSummary* s, const uint8_t* counts
                             int32_t* label_metrics, int32_t* label_taxonomy, int32_t* var_tie);
 
 /* ---- host-buffer step (end-to-end path): actions in HOST memory -> device -> step ->
- *      obs / reward / flags back to HOST memory, synchronous on return.  Pinned buffers make the
- *      copies asynchronous DMA; pageable buffers work but stage through the driver.  With chunks > 1
+ *      obs / reward / flags back to HOST memory, synchronous on return unless DEXSIM_HOST_ASYNC.  Pinned buffers make
+ *      the copies asynchronous DMA; pageable buffers work but stage through the driver.  With chunks > 1
  *      the envs are split into that many ranges whose H2D copy, kernel and D2H copies overlap on
  *      internal streams (created once per device, forked from / joined into `stream`).
  *      This is what a caller that keeps NumPy-side policies uses in place of
  *      `obs, r, term, trunc, info = env.step(action)` (envs/manipulation_env.py:184). ------------------ */
-#define DEXSIM_HOST_SKIP_QUAT 1   /* do not copy obs rows 33-36 (constant quaternion, already in h_obs) */
+#define DEXSIM_HOST_SKIP_QUAT 1        /* do not copy obs rows 33-36 (constant quaternion, already in h_obs) */
+#define DEXSIM_HOST_ASYNC 2            /* return without synchronizing: every copy is ordered before later work on `stream`;
+                                        * the host buffers are valid once the caller has synchronized that stream (or an
+                                        * event recorded on it).  Lets the upload of the next step (or of another env
+                                        * group) overlap this step's download. */
+#define DEXSIM_HOST_PACKED_CONTACTS 4  /* lossless narrower download: obs rows 40-44 (five 0/1 floats per env) stay on
+                                        * the device and the 1-byte contact mask (bit f = finger f, DexsimState.cmask) is
+                                        * copied to h_contact_mask instead (-19 bytes of 171 per env); the caller expands
+                                        * the rows on the host if and when it needs them */
 int dexsim_step_host(const DexsimState* st, const DexsimParams* p, const DexsimGroup* groups,
                      const uint16_t* group_of_env, const DexsimStepIO* io /* device scratch */,
                      const float* h_action /* host [n, 15] (layout 1) or [15, ld] (layout 0) */,
                      float* h_obs /* host [45, ld] or NULL */, float* h_reward /* host [ld] */,
                      uint8_t* h_terminated, uint8_t* h_truncated, uint8_t* h_num_contacts /* host [ld] or NULL */,
+                     uint8_t* h_contact_mask /* host [ld]; required with DEXSIM_HOST_PACKED_CONTACTS, else may be NULL */,
                      int32_t chunks, int32_t flags, void* stream);
 
 #ifdef __cplusplus

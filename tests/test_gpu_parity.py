@@ -710,6 +710,25 @@ def test_step_host_matches_device_step(dx, n, chunks, track):
     assert torch.equal(a_env._episode, b_env._episode)
     if track:
         assert torch.equal(a_env.counters, b_env.counters) and int(a_env.counters[:, 0].sum()) > 0
+    # asynchronous, double-buffered and with the contacts packed into their 1-byte mask: same results
+    pins = [torch.empty(n, 15).pin_memory() for _ in range(2)]
+    pending = None
+    for t in range(12):
+        act = rng.uniform(-1.2, 1.2, (n, 15)).astype(np.float32)
+        o1, r1, te1, tr1, i1 = a_env.step(torch.from_numpy(act).cuda())
+        expect = (o1.cpu().clone(), r1.cpu().clone(), te1.cpu().clone(), tr1.cpu().clone(), i1["num_contacts"].cpu().clone())
+        pins[t % 2].copy_(torch.from_numpy(act))
+        out = b_env.step_host(pins[t % 2], chunks=chunks, sync=False, packed_contacts=True, slot=t % 2)
+        if pending is not None:                     # the previous step's results (other slot) are still intact
+            po, pe = pending
+            assert torch.equal(po[1], pe[1]) and torch.equal(po[2], pe[2])
+        b_env.host_sync()
+        o2 = b_env.expand_contacts_host(slot=t % 2)
+        assert torch.equal(o2, expect[0]) and torch.equal(out[1], expect[1]), t
+        assert torch.equal(out[2], expect[2]) and torch.equal(out[3], expect[3]) and torch.equal(out[4]["num_contacts"], expect[4])
+        assert torch.equal(out[4]["contact_mask"], a_env._cmask[:n].cpu())
+        pending = (out, expect)
+    assert torch.equal(a_env._obs, b_env._obs)
 
 
 class _PatternPolicy:
@@ -1534,3 +1553,52 @@ def test_state_dict_resumes_bit_for_bit(dx):
                  "counters", "_ep_return", "_ep_stats"):
         assert torch.equal(getattr(a, name), getattr(b, name)), name
     assert a._rollout_steps == b._rollout_steps and a.seed == b.seed
+
+
+def test_run_episodes_batched_returns_the_reference_triple(dx):
+    """run_episodes_batched == `run_episode` (training/episode_utils.py:13-55) for every env: (success, steps, total
+    reward) against the oracle stepped with the same actions, float64 return summed in the reference's order."""
+    from oracle import oracle
+    n, T = 300, 40
+    rng = np.random.default_rng(12)
+    jp0, size, mass, fric, pos = _random_draws(rng, n, ragged=False)
+    acts = rng.uniform(-1.0, 1.0, (T, n, 15)).astype(np.float32)
+    acts[:, :, :] -= 0.4 * (np.arange(n) % 3 == 0)[None, :, None]        # a third of the envs close their fingers faster
+    for info_success in (False, True):
+        env = dx.BatchedManipulationEnv(n, "cuda", max_episode_steps=30, reward_type="dense", track_episodes=True,
+                                        info_success=info_success)
+        env.reset_from_draws(jp0, size, mass, fric, pos)
+        success, steps, total = dx.run_episodes_batched(env, policy="external", actions=acts, max_steps=T, reset=False)
+        ob = oracle.OracleBatch(n, dense=True, max_episode_steps=30)
+        ob.reset_predrawn(jp0, size, mass, fric, pos)
+        e_steps, e_total, e_succ, live = np.zeros(n, np.int32), np.zeros(n), np.zeros(n, bool), np.ones(n, bool)
+        for t in range(T):
+            _, r, _, te, tr, _ = ob.step(acts[t])
+            e_total[live] += r[live]
+            e_steps[live] += 1
+            ended = live & (te | tr)
+            e_succ[ended] = te[ended] if info_success else False
+            live &= ~ended
+        assert np.array_equal(steps, e_steps) and np.array_equal(success, e_succ)
+        np.testing.assert_allclose(total, e_total, rtol=1e-12, atol=0)
+        assert success.any() == info_success and (steps < T).any()
+
+
+def test_from_experiment_config(dx, tmp_path):
+    """BatchedManipulationEnv.from_experiment_config: the reference's ExperimentConfig object, its dict and its JSON file."""
+    import json
+    cfg = {"experiment_name": "t", "training": {"max_episode_steps": 37, "reward_type": "sparse", "seed": 9, "num_fingers": 5,
+                                                "joints_per_finger": 3}, "curriculum_scheduler": {"initial_config": "easy", "target_config": "hard"}}
+    path = tmp_path / "cfg.json"
+    path.write_text(json.dumps(cfg))
+    for src in (cfg, str(path)):
+        env = dx.BatchedManipulationEnv.from_experiment_config(src, num_envs=8, auto_reset=True)
+        assert (env.max_episode_steps, env.reward_type, env.seed, env.num_envs, env.auto_reset) == (37, "sparse", 9, 8, True)
+        assert env.curriculum_config.object_size == dx.CurriculumConfig.easy().object_size
+    from oracle import ref_harness
+    if ref_harness.available():
+        R = ref_harness.load()
+        import importlib
+        ec = importlib.import_module("experiments.experiment_config").ExperimentConfig.quick_test()
+        env = dx.BatchedManipulationEnv.from_experiment_config(ec, num_envs=4)
+        assert env.max_episode_steps == ec.training.max_episode_steps and env.reward_type == ec.training.reward_type

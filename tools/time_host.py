@@ -13,7 +13,7 @@ env = dx.BatchedManipulationEnv(n, "cuda", max_episode_steps=200, reward_type="d
                                 loop_max_steps=200, track_episodes=False, curriculum_config=dx.CurriculumConfig.easy())
 env.reset(seed=1)
 pool = [torch.rand(n, 15).mul_(2).sub_(1).pin_memory() for _ in range(2)]
-for chunks in (1, 4, 8, 16, 32, 64):
+for chunks in (1, 4, 6, 8, 12, 16, 24, 32):
     for t in range(3):
         env.step_host(pool[t % 2], chunks=chunks)
     t0 = time.perf_counter()
@@ -21,3 +21,14 @@ for chunks in (1, 4, 8, 16, 32, 64):
         env.step_host(pool[t % 2], chunks=chunks)
     dt = (time.perf_counter() - t0) / 20
     print(f"chunks {chunks:3d}: {dt * 1e3:6.3f} ms/step  {n / dt / 1e6:7.1f} M env-steps/s  D2H {(41 * 4 + 7) * n / dt / 1e9:5.1f} GB/s", flush=True)
+
+for chunks in (8, 16):
+    for t in range(3):
+        env.step_host(pool[t % 2], chunks=chunks, sync=False, slot=t % 2)
+    env.host_sync()
+    t0 = time.perf_counter()
+    for t in range(20):
+        env.step_host(pool[t % 2], chunks=chunks, sync=False, slot=t % 2)
+    env.host_sync()
+    dt = (time.perf_counter() - t0) / 20
+    print(f"async chunks {chunks:3d}: {dt * 1e3:6.3f} ms/step  {n / dt / 1e6:7.1f} M env-steps/s", flush=True)
