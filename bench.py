@@ -526,8 +526,8 @@ def run_b200(args):
     d2h_bytes = (env.ld * 41 * 4 + E * (4 + 3)) * n_gpus
     e2e = {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": E * 15 * 4 * n_gpus,
            "d2h_bytes_per_step": d2h_bytes, "steps": args.e2e_steps,
-           "note": "synchronous step_host(): obs rows 33-36 (constant quaternion) are not re-copied; 8 chunks, H2D / kernel / D2H overlapped",
-           "api": "BatchedManipulationEnv.step_host -> dexsim_step_host", "gpu_launches": args.e2e_steps * 8,
+           "note": "synchronous step_host(): obs rows 33-36 (constant quaternion) are not re-copied; 16 chunks, H2D / kernel / D2H overlapped",
+           "api": "BatchedManipulationEnv.step_host -> dexsim_step_host", "gpu_launches": args.e2e_steps * max(1, min(16, E // 65536)),
            "numa_bound": bool(numa_bound),
            "copy_ceiling": ceiling,
            "frac_of_copy_ceiling": (e2e_value / ceiling["value"]) if ceiling and ceiling.get("value") else None,

@@ -22,6 +22,9 @@ namespace dexsim {
 #define DEXSIM_STEP_MIN_BLOCKS 2
 #endif
 constexpr int STEP_THREADS = 256;
+#ifndef DEXSIM_PDL_DEFAULT
+#define DEXSIM_PDL_DEFAULT(n) 1      // measured on B200 (tools/time_small.py): 14.3 -> 12.1 us at 131,072 envs, 70.0 -> 67.7 us at 1 Mi
+#endif
 
 constexpr int SMEM_GROUPS_MAX = 64;     // group table + block counters are staged in smem up to this many groups
 
@@ -787,6 +790,17 @@ static void launch_step_variant(bool extras, int grid, cudaStream_t s, const Dex
     else        step_kernel<DENSE, AOS, false><<<grid, STEP_THREADS, 0, s>>>(st, p, groups, goe, io);
 }
 
+// Programmatic dependent launch of the pipelined step kernel: DEXSIM_PDL=0 never, =1 always, unset = default policy.
+static int pdl_choice(int64_t n) {
+    static int forced = -2;
+    if (forced == -2) {
+        const char* e = getenv("DEXSIM_PDL");
+        forced = e ? atoi(e) : -1;
+    }
+    if (forced >= 0) return forced ? 1 : 0;
+    return DEXSIM_PDL_DEFAULT(n);
+}
+
 template <bool DENSE, bool AOS, int TRACK, bool EXTRA, int STAGES>
 static int launch_tma_variant(int sm_count, cudaStream_t s, const DexsimState& st, const DexsimParams& p,
                               const DexsimGroup* groups, const uint16_t* goe, const DexsimStepIO& io,
@@ -810,7 +824,21 @@ static int launch_tma_variant(int sm_count, cudaStream_t s, const DexsimState& s
     }
     int grid = sm_count * ctas_per_sm;
     if (grid > num_tiles) grid = num_tiles;
-    kern<<<grid, TMA_THREADS, smem, s>>>(st, p, groups, goe, io, maps, num_tiles);
+    // Programmatic dependent launch for back-to-back steps of batches whose step is launch-latency bound: this grid may
+    // start (barrier init, counter staging) while the previous step's grid drains and blocks in griddepcontrol.wait
+    // until that grid has completed -- stream order is preserved for every access.  All CTAs of a launch are resident
+    // at once (grid <= SMs x CTAs per SM), so a waiting grid can never keep its predecessor's CTAs off the SMs.
+    const int pdl = pdl_choice(st.n);
+    if (pdl) {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3(TMA_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = s;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = attr; cfg.numAttrs = 1;
+        return cuda_rc(cudaLaunchKernelEx(&cfg, kern, st, p, groups, goe, io, maps, num_tiles, pdl));
+    }
+    kern<<<grid, TMA_THREADS, smem, s>>>(st, p, groups, goe, io, maps, num_tiles, 0);
     return cuda_rc(cudaGetLastError());
 }
 
@@ -827,19 +855,21 @@ static int step_impl_choice() {
 }
 
 // Smallest batch the auto choice sends down the TMA pipeline (DEXSIM_TMA_MIN_ENVS overrides it for experiments).
-// Measured on B200 (tools/time_small.py, us per step, register-resident vs pipeline, hard curriculum):
-//   plain:   65,536 envs 6.2 vs 9.0;  98,304 9.6 vs 10.3;  131,072 10.3 vs 10.4;  196,608 14.4 vs 12.3;  262,144 18.5 vs 15.3
-//   counts:  65,536 10.2 vs 11.4;  98,304 13.7 vs 12.6;  131,072 15.1 vs 14.0;  196,608 20.2 vs 16.7
-//   tracked: 65,536 11.1 vs 12.6;  98,304 15.5 vs 13.6;  131,072 16.7 vs 16.1;  196,608 22.6 vs 19.1
-// Below the crossover the batch is L2-resident and a step is a launch plus one load-compute-store round trip, which
-// the register-resident kernel (more warps in flight, no ring to fill and drain) finishes sooner.
+// Measured on B200 (tools/time_small.py, us per step, register-resident kernel vs pipeline, hard curriculum, 400 steps):
+//   without programmatic dependent launch the register-resident kernel won below ~80k envs (65,536 envs, counts:
+//   10.2 vs 11.4) -- with it (the default, see pdl_choice) the pipeline's prologue overlaps the previous step's tail:
+//   counts:  4,096 envs 7.6 vs 6.3;  16,384 8.4 vs 7.0;  65,536 10.2 vs 9.3;  131,072 15.1 vs 12.0;  196,608 20.2 vs 14.4
+//   tracked: 4,096 8.7 vs 7.1;  65,536 11.1 vs 10.7;  131,072 16.8 vs 14.2;  196,608 22.5 vs 17.2
+//   plain:   16,384 6.2 vs 4.9;  65,536 6.2 vs 7.0 (both at the ~5 us host issue rate);  131,072 10.3 vs 9.0
+// so every batch of at least one tile takes the pipeline.
 static int64_t tma_min_envs(int track, bool extra) {
+    (void)track; (void)extra;
     static int64_t forced = -2;
     if (forced == -2) {
         const char* e = getenv("DEXSIM_TMA_MIN_ENVS");
         forced = e ? atoll(e) : -1;
     }
-    int64_t v = forced >= 0 ? forced : ((track == 0 && !extra) ? 163840 : 81920);
+    const int64_t v = forced >= 0 ? forced : TILE;
     return v < TILE ? TILE : v;
 }
 
@@ -918,8 +948,6 @@ static int launch_step(const DexsimState* st, const DexsimParams* p, const Dexsi
                         !(reinterpret_cast<uintptr_t>(io->num_contacts) & 15u) && !(reinterpret_cast<uintptr_t>(st->episode) & 15u) &&
                         (track != 1 || (!(reinterpret_cast<uintptr_t>(st->ep_return) & 15u) && !(reinterpret_cast<uintptr_t>(st->ep_stats) & 15u))) &&
                         !(reinterpret_cast<uintptr_t>(io->finished) & 15u);
-    // auto: below the crossover the batch is L2-resident and one step is a launch plus one load-compute-store round trip;
-    // the register-resident kernel has the shorter round trip there (measured on B200)
     if (impl != 1 && tma_ok && (impl == 2 || st->n >= tma_min_envs(track, extra_io))) {
         rc = launch_step_tma(st, p, groups, goe, io, s, track, extra_io, di.sm_count);
         if (rc <= 0) return rc;                      // launched (0) or CUDA error (< 0); 1 = not available

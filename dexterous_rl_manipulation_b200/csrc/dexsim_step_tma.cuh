@@ -223,7 +223,7 @@ template <bool DENSE, bool AOS, int TRACK, bool EXTRA, int STAGES>
 __global__ void __launch_bounds__(TMA_THREADS, (STAGES == 2) ? (TILE <= 96 ? 4 : 3) : 2)
 step_tma_kernel(const DexsimState st, const DexsimParams p, const DexsimGroup* __restrict__ groups,
                 const uint16_t* __restrict__ group_of_env, const DexsimStepIO io,
-                const __grid_constant__ StepMaps maps, const int num_tiles) {
+                const __grid_constant__ StepMaps maps, const int num_tiles, const int pdl) {
     extern __shared__ __align__(1024) unsigned char smem[];
     unsigned char* stage_base = smem;
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);      // full[S], out_ready[S]
@@ -250,9 +250,15 @@ step_tma_kernel(const DexsimState st, const DexsimParams p, const DexsimGroup* _
     }
     __syncthreads();
 
+    // Programmatic dependent launch (only when the host launched this grid with the attribute, see launch_tma_variant):
+    // the next step's grid may begin its prologue while this one drains ...
+    if (pdl) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     if (tid >= PRODUCER_TID) {
         // ===== producer warp: one lane issues every bulk copy of this CTA =====
         if (tid == PRODUCER_TID) {
+            // ... and this grid touches global memory only after the previous grid has completed and flushed
+            // (every access of the compute warps is ordered behind the producer's first loads by the stage barriers)
+            if (pdl) asm volatile("griddepcontrol.wait;" ::: "memory");
             unsigned int* sched = io.sched;
             auto issue_stores = [&](int s, int tile) {
                 const int64_t base = (int64_t)tile * TILE;

@@ -840,7 +840,7 @@ class BatchedManipulationEnv:
         ``(obs [num_envs,45], reward, terminated, truncated, info)`` living in pinned buffers that
         the next call with the same ``slot`` overwrites.  One C-ABI call (dexsim_step_host): H2D copy of the actions,
         the step kernel, D2H copies of observation / reward / flags, stream synchronize.  Large batches are
-        split into ``chunks`` ranges (default: one per 65,536 envs, at most 8) so that the upload of one
+        split into ``chunks`` ranges (default: one per 65,536 envs, at most 16) so that the upload of one
         range overlaps the kernel and the download of the others.
 
         ``sync=False``: return as soon as everything is enqueued; call ``host_sync()`` (or synchronize the current
@@ -867,7 +867,7 @@ class BatchedManipulationEnv:
                 C.byref(self._state), C.byref(self._params), self._ptr(self._groups_dev), self._ptr(self._goe),
                 C.byref(io), a.data_ptr(), b["obs"].data_ptr(), b["reward"].data_ptr(), b["term"].data_ptr(),
                 b["trunc"].data_ptr(), b["nc"].data_ptr(), b["cmask"].data_ptr(),
-                int(chunks) if chunks is not None else max(1, min(8, n // 65536)), flags, self._stream()), "dexsim_step_host")
+                int(chunks) if chunks is not None else max(1, min(16, n // 65536)), flags, self._stream()), "dexsim_step_host")
         if not sync:
             self._host_keepalive = a                   # the upload may still be reading it
         return b["out"]
