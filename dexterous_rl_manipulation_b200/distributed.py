@@ -95,3 +95,26 @@ def summarize_counters(counters: torch.Tensor, ret_sums: torch.Tensor = None, ma
             m["std_reward"] = float(max(r[g, 1] / n - mean_r * mean_r, 0.0) ** 0.5)
         out.append(m)
     return out
+
+
+def share_best_candidate(best_value: float, best_gid: int, payload: torch.Tensor, group=None):
+    """Cross-rank arg-max with payload: every rank proposes ``(best_value, best_gid, payload)``; all ranks return the
+    proposal with the highest value (ties: lowest global id), identical on every rank.
+
+    This is the one exchange of a SHARED SimpleLearner (BASELINE.json north_star: "NCCL ... and, if training is batched,
+    the simple_learner update"; policies/simple_learner.py:73-95 keeps whatever adjustment improved the best reward):
+    the winning rank's mean action [15] replaces everybody's.  One all-gather of 17 float64 per rank -- latency-bound,
+    issued once per shared update, never per env-step.  Works with ``nccl`` (CUDA payloads) and ``gloo`` (CPU)."""
+    payload = payload.detach().reshape(-1)
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return float(best_value), int(best_gid), payload.clone()
+    mine = torch.cat([torch.tensor([float(best_value), float(best_gid)], dtype=torch.float64, device=payload.device),
+                      payload.to(torch.float64)])
+    world = dist.get_world_size(group)
+    table = torch.empty(world, mine.numel(), dtype=torch.float64, device=payload.device)
+    dist.all_gather_into_tensor(table, mine, group=group) if payload.is_cuda else \
+        dist.all_gather(list(table.unbind(0)), mine, group=group)
+    rows = table.cpu()
+    order = sorted(range(world), key=lambda r: (-float(rows[r, 0]), float(rows[r, 1])))
+    w = order[0]
+    return float(rows[w, 0]), int(rows[w, 1]), table[w, 2:].to(payload.dtype)

@@ -79,3 +79,45 @@ def train_learners_batched(num_runs: int, num_episodes: int, curriculum_config=N
     k = int(num_runs)
     return {"episode_rewards": rewards[:k], "episode_steps": steps[:k], "successes": succ[:k],
             "mean_action": env.learner_mean[:k].cpu().numpy(), "env": env}
+
+
+def train_shared_learner_batched(num_envs: int, num_episodes: int, curriculum_config=None, reward_type: str = "dense",
+                                 max_episode_steps: int = 200, learning_rate: float = 0.01, exploration_noise: float = 0.3,
+                                 action_clip_range: float = 0.5, seed: int = 42, device="cuda", num_envs_global: Optional[int] = None,
+                                 group=None) -> Dict:
+    """ONE SimpleLearner trained on a whole batch of rollouts (and on every GPU of the job): each episode all envs start
+    from the shared mean action, explore and hill-climb independently inside the fused rollout exactly like
+    policies/simple_learner.py:60-95, and after the episode the mean of the env with the highest episode return --
+    over all envs of all ranks -- becomes the shared mean (``distributed.share_best_candidate``: one 17-double
+    all-gather per episode; the only collective besides the counter all-reduce).  With ``torch.distributed`` initialised
+    the ``num_envs_global`` envs (default ``num_envs`` x world size) are sharded by global id; every rank returns the same
+    history.  Unlike ``train_learners_batched`` (independent runs, the reference's semantics run many times) this is a
+    population search, so its trajectories have no reference counterpart -- only its per-env arithmetic does.
+
+    Returns {"best_return" [num_episodes], "winner_gid" [num_episodes], "mean_action" [15], "env"}."""
+    import torch
+    import torch.distributed as dist
+    from .distributed import shard_range, share_best_candidate
+    world = dist.get_world_size(group) if (dist.is_available() and dist.is_initialized()) else 1
+    rank = dist.get_rank(group) if world > 1 else 0
+    total = int(num_envs_global) if num_envs_global is not None else int(num_envs) * world
+    lo, hi = shard_range(total, rank, world)
+    n = max(hi - lo, 2)
+    env = BatchedManipulationEnv(n, device, max_episode_steps=max_episode_steps, reward_type=reward_type,
+                                 curriculum_config=curriculum_config, track_episodes=True, seed=seed, env_gid0=lo)
+    env.enable_learner(learning_rate, exploration_noise, action_clip_range)
+    env.enable_episode_log(capacity=n)
+    best_hist, gid_hist = np.zeros(num_episodes), np.zeros(num_episodes, np.int64)
+    for ep in range(int(num_episodes)):
+        env.reset(seed=seed if ep == 0 else None)
+        env._ep_log_count.zero_()
+        env.rollout(max_episode_steps, policy="learner", respawn=False, loop_max_steps=max_episode_steps, one_episode=True)
+        log = env.read_episode_log(sort=False)
+        log = log[log["env_gid"] < hi] if hi - lo < n else log          # padding env of a 1-env shard never wins
+        k = int(np.lexsort((log["env_gid"], -log["episode_reward"]))[0])
+        gid = int(log["env_gid"][k])
+        mean = env._learner_mean[:, gid - lo].clone()
+        best, wgid, wmean = share_best_candidate(float(log["episode_reward"][k]), gid, mean, group=group)
+        env._learner_mean[:, :] = wmean.to(env._learner_mean.dtype).reshape(15, 1)      # every env continues from the winner
+        best_hist[ep], gid_hist[ep] = best, wgid
+    return {"best_return": best_hist, "winner_gid": gid_hist, "mean_action": env.learner_mean[0].cpu().numpy(), "env": env}

@@ -145,6 +145,7 @@ def config5_learner_seeds(runs_per_cell=4096, episodes=20,
         gathered = [None] * WORLD
         torch.distributed.all_gather_object(gathered, out)
     merged = {k: v for g in gathered for k, v in g.items()}
+    merged = {k: merged[k] for k in sorted(merged)}          # cell order independent of the rank count (float sums below)
     total_steps = sum(v[2] for v in merged.values())
     summary = {rt: {"final_mean_return": float(np.mean([v[0] for k, v in merged.items() if k.startswith(rt)])),
                     "final_success_rate": float(np.mean([v[1] for k, v in merged.items() if k.startswith(rt)])),

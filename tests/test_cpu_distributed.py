@@ -136,3 +136,32 @@ def test_two_rank_heldout_front_end_gathers_the_single_process_result(tmp_path):
         with open(tmp_path / f"res{rank}.pkl", "rb") as fh:
             got = pickle.load(fh)
         assert got == single, rank
+
+
+def _share_worker(rank, world, port, out_dir):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    # rank 1 holds the better candidate in round 0; round 1 is a tie on the value, decided by the lower global id
+    rounds = [((1.5, 7, torch.full((15,), 0.25)), (2.5, 900, torch.arange(15, dtype=torch.float32))),
+              ((3.0, 40, torch.full((15,), -1.0)), (3.0, 12, torch.full((15,), 2.0)))]
+    got = []
+    for cand in rounds:
+        v, g, payload = cand[rank]
+        got.append(dx.distributed.share_best_candidate(v, g, payload))
+    torch.save(got, os.path.join(out_dir, f"share_{rank}.pt"))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_shared_learner_exchange_two_ranks(tmp_path):
+    """distributed.share_best_candidate (the shared SimpleLearner's one collective): both ranks end up with the same
+    winner -- highest value, ties to the lowest global env id -- and its payload."""
+    mp.spawn(_share_worker, args=(2, _free_port(), str(tmp_path)), nprocs=2, join=True)
+    a, b = torch.load(tmp_path / "share_0.pt"), torch.load(tmp_path / "share_1.pt")
+    for (va, ga, pa), (vb, gb, pb) in zip(a, b):
+        assert (va, ga) == (vb, gb) and torch.equal(pa, pb)
+    assert (a[0][0], a[0][1]) == (2.5, 900) and torch.equal(a[0][2], torch.arange(15, dtype=torch.float32))
+    assert (a[1][0], a[1][1]) == (3.0, 12) and torch.equal(a[1][2], torch.full((15,), 2.0))
+    # without a process group the call is the identity
+    v, g, p = dx.distributed.share_best_candidate(1.0, 3, torch.ones(15))
+    assert (v, g) == (1.0, 3) and torch.equal(p, torch.ones(15))

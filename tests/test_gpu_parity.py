@@ -1602,3 +1602,23 @@ def test_from_experiment_config(dx, tmp_path):
         ec = importlib.import_module("experiments.experiment_config").ExperimentConfig.quick_test()
         env = dx.BatchedManipulationEnv.from_experiment_config(ec, num_envs=4)
         assert env.max_episode_steps == ec.training.max_episode_steps and env.reward_type == ec.training.reward_type
+
+
+def test_shared_learner_population_update(dx):
+    """training.train_shared_learner_batched: after every episode all envs continue from the mean action of the env with
+    the highest episode return (lowest global id on ties); sharding the population by global id -- what several GPUs do,
+    with distributed.share_best_candidate picking the winner across ranks -- is covered on CPU with gloo; here the
+    single-process history must be reproducible and the winner must really be the arg-max of the logged returns."""
+    kw = dict(num_envs=512, num_episodes=4, curriculum_config=dx.CurriculumConfig.easy(), reward_type="dense",
+              max_episode_steps=25, seed=3)
+    a = dx.training.train_shared_learner_batched(**kw)
+    b = dx.training.train_shared_learner_batched(**kw)
+    assert np.array_equal(a["best_return"], b["best_return"]) and np.array_equal(a["winner_gid"], b["winner_gid"])
+    assert np.array_equal(a["mean_action"], b["mean_action"])
+    env = a["env"]
+    m = env.learner_mean
+    assert torch.equal(m, m[0:1].expand_as(m))                       # one shared mean
+    log = env.read_episode_log(sort=False)                           # the last episode's records
+    k = np.lexsort((log["env_gid"], -log["episode_reward"]))[0]
+    assert a["winner_gid"][-1] == log["env_gid"][k] and a["best_return"][-1] == log["episode_reward"][k]
+    assert np.all(np.abs(a["mean_action"]) <= 0.5 + 1e-7)

@@ -3,7 +3,8 @@
     python tools/profile_step.py [num_envs] [variant]
 
 variant: api (step kernel, plain), api_counts (auto-reset + counters, the bench path), api_track (auto-reset +
-full episode tracking), fused (rollout kernel).  8 warm-up launches, then 6 profiled-range launches.
+full episode tracking), api_noisy (sigma_obs 0.05 + sigma_dyn 0.1 drawn in-kernel), fused (rollout kernel).
+8 warm-up launches, then 6 profiled-range launches.
 """
 import os
 import sys
@@ -20,6 +21,8 @@ CC = dx.CurriculumConfig
 kw = dict(max_episode_steps=200, reward_type="dense", curriculum_config=CC.hard(), seed=42)
 if variant == "api":
     env = dx.BatchedManipulationEnv(n, "cuda", **kw)
+elif variant == "api_noisy":
+    env = dx.BatchedManipulationEnv(n, "cuda", observation_noise_std=0.05, dynamics_noise_std=0.1, **kw)
 elif variant in ("api_track", "api_counts"):
     env = dx.BatchedManipulationEnv(n, "cuda", auto_reset=True, respawn=True, loop_max_steps=200,
                                     track_episodes=variant == "api_track", **kw)
