@@ -489,8 +489,11 @@ reset_philox_kernel(const DexsimState st, const DexsimParams p, const DexsimGrou
 #ifndef DEXSIM_ROLLOUT_MIN_BLOCKS
 #define DEXSIM_ROLLOUT_MIN_BLOCKS 2
 #endif
+#ifndef DEXSIM_ROLLOUT_THREADS
+#define DEXSIM_ROLLOUT_THREADS 256      // CTA shape of the fused rollout for large batches (x MIN_BLOCKS resident CTAs per SM)
+#endif
 template <bool DENSE, bool LEARNER>
-__global__ void __launch_bounds__(STEP_THREADS, DEXSIM_ROLLOUT_MIN_BLOCKS)
+__global__ void __launch_bounds__(DEXSIM_ROLLOUT_THREADS, DEXSIM_ROLLOUT_MIN_BLOCKS)
 rollout_kernel(const DexsimState st, const DexsimParams p, const DexsimGroup* __restrict__ groups,
                const uint16_t* __restrict__ group_of_env, const int k_steps, const int policy_kind,
                const DexsimRolloutIO rio) {
@@ -723,7 +726,7 @@ static int query_device(DeviceInfo& d) {
     if (err != cudaSuccess) return -(int)err;
     err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&d.step_ctas, step_kernel<true, false, false>, STEP_THREADS, 0);
     if (err != cudaSuccess) return -(int)err;
-    err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&d.rollout_ctas, rollout_kernel<true, false>, STEP_THREADS, 0);
+    err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&d.rollout_ctas, rollout_kernel<true, false>, DEXSIM_ROLLOUT_THREADS, 0);
     if (err != cudaSuccess) return -(int)err;
     d.valid = true;
     return 0;
@@ -801,6 +804,19 @@ static int pdl_choice(int64_t n) {
     return DEXSIM_PDL_DEFAULT(n);
 }
 
+// The programmatic edge is kept inside captured graphs as well (DEXSIM_PDL_GRAPH=0 drops it, for experiments): measured on
+// B200 with capture_step(steps=8), us per step with / without: 65,536 envs 9.4 / 10.6, 131,072 12.6 / 13.6, 1 Mi 69.2 / 70.0.
+// Eager stepping with PDL (9.3 / 12.1 / 67.1) is as fast as a graph replay once the GPU, not the host, is the bound
+// (>= 65,536 envs); at 4,096 envs the replay wins (6.5 vs 7.5, the eager loop runs at the host's issue rate).
+static bool pdl_in_graphs() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("DEXSIM_PDL_GRAPH");
+        v = (e && !atoi(e)) ? 0 : 1;
+    }
+    return v == 1;
+}
+
 template <bool DENSE, bool AOS, int TRACK, bool EXTRA, int STAGES>
 static int launch_tma_variant(int sm_count, cudaStream_t s, const DexsimState& st, const DexsimParams& p,
                               const DexsimGroup* groups, const uint16_t* goe, const DexsimStepIO& io,
@@ -828,7 +844,12 @@ static int launch_tma_variant(int sm_count, cudaStream_t s, const DexsimState& s
     // start (barrier init, counter staging) while the previous step's grid drains and blocks in griddepcontrol.wait
     // until that grid has completed -- stream order is preserved for every access.  All CTAs of a launch are resident
     // at once (grid <= SMs x CTAs per SM), so a waiting grid can never keep its predecessor's CTAs off the SMs.
-    const int pdl = pdl_choice(st.n);
+    int pdl = pdl_choice(st.n);
+    if (pdl && !pdl_in_graphs()) {
+        // inside a stream capture the kernel nodes of consecutive steps already launch back to back
+        cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+        if (cudaStreamIsCapturing(s, &cap) == cudaSuccess && cap != cudaStreamCaptureStatusNone) pdl = 0;
+    }
     if (pdl) {
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3(TMA_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = s;
@@ -1080,8 +1101,8 @@ int dexsim_rollout(const DexsimState* st, const DexsimParams* p, const DexsimGro
     // Small batches are latency-bound: spread warps over as many SM sub-partitions as possible
     // (4 per SM) by shrinking the CTA; large batches use full 256-thread CTAs.
     const int64_t warps = (st->n + 31) / 32;
-    int threads = STEP_THREADS;
-    while (threads > 32 && warps * 32 / threads < (int64_t)di.sm_count * 4) threads >>= 1;
+    int threads = DEXSIM_ROLLOUT_THREADS;
+    while (threads > 32 && warps * 32 / threads < (int64_t)di.sm_count * 4) threads = (threads / 2 + 31) / 32 * 32;
     const int64_t blocks = (st->n + threads - 1) / threads;
     if (blocks > 0x7FFFFFFFll) return DEXSIM_E_SIZE;
     const int G = p->num_groups;

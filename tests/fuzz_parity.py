@@ -1,6 +1,8 @@
-"""Randomised differential test, CUDA fused rollout vs the oracle's rollout (experiments / soak; the fixed-seed
-versions of these checks live in tests/test_gpu_parity.py).  Runs random configurations until the time budget is
-spent and stops at the first mismatch.
+"""Randomised differential test (experiments / soak; the fixed-seed versions of these checks live in
+tests/test_gpu_parity.py): CUDA fused rollout vs the oracle's rollout, dexsim_step (either step kernel, with and without
+pre-drawn noise) vs the oracle's step on hostile actions, and API-mode auto-reset stepping with the exposed Philox
+actions vs the oracle's rollout (the pipelined kernel's dynamic tile scheduler and reset path at multi-tile sizes).
+Runs random configurations until the time budget is spent and stops at the first mismatch.
 
     python tests/fuzz_parity.py [seconds] [first_seed]
 """
@@ -13,6 +15,7 @@ import torch
 
 sys.path.insert(0, os.path.abspath(os.path.join(os.path.dirname(__file__), "..")))
 import dexterous_rl_manipulation_b200 as dx  # noqa: E402
+from dexterous_rl_manipulation_b200 import _lib  # noqa: E402
 from oracle import oracle  # noqa: E402
 
 budget = float(sys.argv[1]) if len(sys.argv) > 1 else 60.0
@@ -23,11 +26,13 @@ done = episodes = 0
 def fuzz_api_steps(case):
     """dexsim_step (TMA pipeline or register kernel, AoS actions) vs the oracle's step on hostile actions."""
     rng = np.random.default_rng(10_000_000 + case)
-    n = int(rng.choice([2, 33, 128, 129, 1000, 4096, 9999]))
+    n = int(rng.choice([2, 33, 128, 129, 1000, 4096, 9999, 70001, 131072]))
     dense = bool(rng.integers(2))
-    comps = bool(rng.integers(2))                       # False keeps n >= 128 on the TMA pipeline
+    comps = bool(rng.integers(2))
+    noisy = bool(rng.integers(3) == 0)                  # pre-drawn dynamics + observation noise (EXTRA instantiations)
+    impl = ["auto", "register", "tma"][int(rng.integers(3))] if n >= 128 else "auto"
     max_steps = int(rng.choice([1, 5, 60, 200]))
-    T = int(rng.integers(1, 120))
+    T = int(rng.integers(1, 120 if n < 50000 else 10))
     w = tuple(float(x) for x in rng.uniform(0.0, 3.0, 4)) if dense and rng.integers(2) else None
     jp0 = rng.uniform(-1.0, 1.0, (n, 15)).astype(np.float32) if rng.integers(2) else rng.uniform(-0.1, 0.1, (n, 15)).astype(np.float32)
     size, mass, fric = rng.uniform(0.005, 0.4, n), rng.uniform(0.01, 3.0, n), rng.uniform(0.0, 2.0, n)
@@ -41,16 +46,20 @@ def fuzz_api_steps(case):
                                     reward_components=comps, **kw)
     ob = oracle.OracleBatch(n, dense=dense, max_episode_steps=max_steps, **({"weights": w} if w is not None else {}))
     g0, _ = env.reset_from_draws(jp0, size, mass, fric, pos)
-    desc = dict(case=case, mode="api", n=n, dense=dense, comps=comps, max_steps=max_steps, T=T, weights=w)
+    desc = dict(case=case, mode="api", n=n, dense=dense, comps=comps, max_steps=max_steps, T=T, weights=w, noisy=noisy, impl=impl)
     assert np.array_equal(g0.cpu().numpy(), ob.reset_predrawn(jp0, size, mass, fric, pos)), ("reset", desc)
+    _lib.set_step_impl(impl)
     for t in range(T):
         kind = int(rng.integers(5))
         a = (rng.uniform(-1.5, 1.5, (n, 15)) if kind < 2 else rng.normal(0, [0.3, 3.0, 1e3][kind - 2], (n, 15))).astype(np.float32)
         if rng.integers(4) == 0:
             idx = rng.integers(0, n, 3), rng.integers(0, 15, 3)
             a[idx] = [np.nan, np.inf, -np.inf]
-        oo, orr, oc, ote, otr, onc = ob.step(a)
-        obs, rew, te, tr, info = env.step(torch.from_numpy(a).cuda())
+        nz = {}
+        if noisy:
+            nz = dict(dyn_noise=rng.normal(0, 0.1, (n, 15)).astype(np.float32), obs_noise=rng.normal(0, 0.05, (n, 45)).astype(np.float32))
+        oo, orr, oc, ote, otr, onc = ob.step(a, threads=8, **nz)
+        obs, rew, te, tr, info = env.step(torch.from_numpy(a).cuda(), **nz)
         ok = (np.array_equal(obs.cpu().numpy(), oo, equal_nan=True) and np.array_equal(te.cpu().numpy(), ote)
               and np.array_equal(tr.cpu().numpy(), otr) and np.array_equal(info["num_contacts"].cpu().numpy(), onc)
               and np.allclose(rew.cpu().numpy(), orr, rtol=1e-6, atol=1e-7, equal_nan=True)
@@ -58,13 +67,69 @@ def fuzz_api_steps(case):
         if not ok:
             print("MISMATCH", desc, "step", t, flush=True)
             sys.exit(1)
+    _lib.set_step_impl("auto")
     return T * n
+
+
+def fuzz_api_autoreset(case):
+    """API-mode stepping with in-kernel auto-reset and counters (either step kernel, counts-only or full tracking, multi-tile
+    sizes that exercise the dynamic tile scheduler) fed with the exposed Philox policy actions, vs the oracle's rollout."""
+    import ctypes as C
+    rng = np.random.default_rng(20_000_000 + case)
+    n = int(rng.choice([129, 1000, 4097, 60001, 131072]))
+    dense, respawn = bool(rng.integers(2)), bool(rng.integers(2))
+    policy_kind = int(rng.integers(1, 3))
+    full = bool(rng.integers(2))
+    impl = ["auto", "register", "tma"][int(rng.integers(3))]
+    max_steps = int(rng.choice([2, 7, 40]))
+    loop_max = int(rng.choice([2 * max_steps, max_steps, max(1, max_steps // 2)]))
+    K = int(rng.integers(3, 70 if n < 50000 else 14))
+    seed = int(rng.integers(0, 2 ** 63))
+    gid0 = int(rng.choice([0, 5, 2 ** 32 - 30_000]))
+    cfgs = [CC.easy(), CC(object_size=0.06, object_size_range=(0.03, 0.09), friction_range=(0.1, 0.9))][:int(rng.integers(1, 3))]
+    env = dx.BatchedManipulationEnv(n, "cuda", max_episode_steps=max_steps, reward_type="dense" if dense else "sparse",
+                                    auto_reset=True, respawn=respawn, loop_max_steps=loop_max, track_episodes=full, groups=cfgs,
+                                    seed=seed, env_gid0=gid0)
+    env.reset(seed=seed)
+    ob = oracle.OracleBatch(n, dense=dense, max_episode_steps=max_steps)
+    groups = np.concatenate([oracle.make_group(c) for c in cfgs])
+    G = len(cfgs)
+    ob.reset_predrawn(env._obs[:15, :n].t().cpu().numpy(), env._size[:n].cpu().numpy(), env._mass[:n].cpu().numpy(),
+                      env._friction[:n].cpu().numpy(), env._obs[30:33, :n].t().cpu().numpy())
+    desc = dict(case=case, mode="api_autoreset", n=n, dense=dense, respawn=respawn, policy=policy_kind, full=full, impl=impl,
+                max_steps=max_steps, loop_max=loop_max, K=K, gid0=gid0, groups=G)
+    _lib.set_step_impl(impl)
+    act = torch.zeros(15, env.ld, device="cuda")
+    for _ in range(K):
+        _lib.check(env._lib.dexsim_fill_policy_actions(C.byref(env._state), C.byref(env._params), policy_kind, act.data_ptr(),
+                                                       env._stream()), "fill")
+        env.step(act[:, :n].t().contiguous())
+    _lib.set_step_impl("auto")
+    cnt_o, _ = ob.rollout(groups, K, seed, policy_kind=policy_kind, respawn=respawn, env_gid0=gid0, loop_max_steps=loop_max, threads=8)
+    cnt = env.counters.cpu().numpy()
+    cols = list(range(16)) + [17] if full else [0, 1, 2, 3, 17]
+    ok = (np.array_equal(cnt[:, cols], cnt_o[:, cols])
+          and np.array_equal(env._obs[:, :n].t().cpu().numpy(), ob.observation(), equal_nan=True)
+          and np.array_equal(env._op64[:, :n].t().cpu().numpy(), ob.env["op"])
+          and np.array_equal(env._step_count[:n].cpu().numpy(), ob.env["step_count"])
+          and np.array_equal(env._episode[:n].cpu().numpy().astype(np.uint32), ob.env["episode"]))
+    if not ok:
+        print("MISMATCH", desc, flush=True)
+        sys.exit(1)
+    return K * n, int(cnt[:, 0].sum())
 
 
 api_steps = 0
 while time.time() < t_end:
-    if case % 2:
+    if case % 3 == 1:
         api_steps += fuzz_api_steps(case)
+        done += 1
+        case += 1
+        continue
+    if case % 3 == 2:
+        k, e = fuzz_api_autoreset(case)
+        api_steps += k
+        episodes += e
         done += 1
         case += 1
         continue

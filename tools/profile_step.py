@@ -23,15 +23,17 @@ if variant == "api":
     env = dx.BatchedManipulationEnv(n, "cuda", **kw)
 elif variant == "api_noisy":
     env = dx.BatchedManipulationEnv(n, "cuda", observation_noise_std=0.05, dynamics_noise_std=0.1, **kw)
-elif variant in ("api_track", "api_counts"):
+elif variant in ("api_track", "api_counts", "api_counts_easy", "api_track_easy"):
+    if variant.endswith("_easy"):        # 15-step episodes: ~6.7 % of the envs reset every step
+        kw["curriculum_config"] = CC.easy()
     env = dx.BatchedManipulationEnv(n, "cuda", auto_reset=True, respawn=True, loop_max_steps=200,
-                                    track_episodes=variant == "api_track", **kw)
+                                    track_episodes=variant.startswith("api_track"), **kw)
 else:
     env = dx.BatchedManipulationEnv(n, "cuda", track_episodes=True, **kw)
 env.reset(seed=42)
 g = torch.Generator(device="cuda").manual_seed(0)
 pool = [torch.rand(n, 15, device="cuda", generator=g) * 2 - 1 for _ in range(4)]
-for t in range(14):
+for t in range(14 if not variant.endswith('_easy') else 44):
     if variant == "fused":
         env.rollout(20, policy="random")
     else:

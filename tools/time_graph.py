@@ -1,7 +1,6 @@
-"""CUDA-graph replay timing for small batches (experiments only)."""
+"""API step replayed from a CUDA graph (capture_step, 8 steps per replay) vs eager stepping at mid sizes (experiments)."""
 import os
 import sys
-import time
 
 import torch
 
@@ -9,41 +8,31 @@ sys.path.insert(0, os.path.abspath(os.path.join(os.path.dirname(__file__), "..")
 import dexterous_rl_manipulation_b200 as dx  # noqa: E402
 
 CC = dx.CurriculumConfig
-from dexterous_rl_manipulation_b200 import _lib  # noqa: E402
-for n in (4096, 16384, 65536):
-  for impl in ("register", "tma"):
-    _lib.set_step_impl(impl)
-    for steps in (1, 8):
-        env = dx.BatchedManipulationEnv(n, "cuda", max_episode_steps=200, reward_type="dense", curriculum_config=CC.hard(),
-                                        auto_reset=True, respawn=True, loop_max_steps=200, track_episodes=True, seed=42)
-        env.reset(seed=42)
-        buf = torch.rand(steps, n, 15, device="cuda") * 2 - 1
-        replay = env.capture_step(buf, steps=steps)
-        for _ in range(20):
-            replay()
-        torch.cuda.synchronize()
-        reps = 300
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        t0 = time.perf_counter()
-        e0.record()
-        for _ in range(reps):
-            replay()
-        e1.record()
-        host = time.perf_counter() - t0
-        torch.cuda.synchronize()
-        ms = e0.elapsed_time(e1) / (reps * steps)
-        print(f"{impl:8s} n={n:6d} graph of {steps} step(s): gpu {ms * 1e3:6.2f} us/step, host {host / (reps * steps) * 1e6:6.2f} us/step, "
-              f"{n / ms / 1e6:6.2f} G env-steps/s")
-        # correctness: graph replay == eager stepping
-        a = dx.BatchedManipulationEnv(n, "cuda", max_episode_steps=200, reward_type="dense", curriculum_config=CC.hard(),
-                                      auto_reset=True, respawn=True, loop_max_steps=200, track_episodes=True, seed=7)
-        b = dx.BatchedManipulationEnv(n, "cuda", max_episode_steps=200, reward_type="dense", curriculum_config=CC.hard(),
-                                      auto_reset=True, respawn=True, loop_max_steps=200, track_episodes=True, seed=7)
-        a.reset(seed=7); b.reset(seed=7)
-        rb = b.capture_step(buf, steps=steps)
-        for _ in range(5):
-            for k in range(steps):
-                a.step(buf[k])
-            rb()
-        assert torch.equal(a._obs, b._obs) and torch.equal(a._step_count, b._step_count) and torch.equal(a.counters, b.counters)
-print("graph replay == eager: ok")
+for n in (int(a) for a in (sys.argv[1:] or ["4096", "65536", "131072", "262144", "1048576"])):
+    env = dx.BatchedManipulationEnv(n, "cuda", max_episode_steps=200, reward_type="dense", curriculum_config=CC.hard(),
+                                    auto_reset=True, respawn=True, loop_max_steps=200, track_episodes=False, seed=42)
+    env.reset(seed=42)
+    g = torch.Generator(device="cuda").manual_seed(0)
+    pool = [torch.rand(n, 15, device="cuda", generator=g) * 2 - 1 for _ in range(8)]
+    for t in range(40):
+        env.step(pool[t % 8])
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for t in range(400):
+        env.step(pool[t % 8])
+    e1.record()
+    torch.cuda.synchronize()
+    eager = e0.elapsed_time(e1) / 400 * 1e3
+    replay = env.capture_step(torch.stack(pool), steps=8)
+    for _ in range(10):
+        replay()
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(50):
+        replay()
+    e1.record()
+    torch.cuda.synchronize()
+    graph = e0.elapsed_time(e1) / 400 * 1e3
+    print(f"{os.environ.get('DEXSIM_PDL_GRAPH', '0')} n={n:8d} eager {eager:7.2f} us/step  graph replay {graph:7.2f} us/step", flush=True)
+    del env, replay
