@@ -26,6 +26,7 @@ EPISODE_RECORD_DTYPE = _np.dtype([("env_gid", "u4"), ("episode", "u4"), ("steps"
                                   ("episode_reward", "f8"), ("t_end", "u4"), ("var_tie", "u4")])
 HOST_SKIP_QUAT, HOST_ASYNC, HOST_PACKED_CONTACTS = 1, 2, 4
 SCHED_WORDS = 64
+STEP_REVERSE_TILES = 1
 ROLLOUT_NO_DYN_NOISE = 1
 
 # value strings of FailureType (evaluation/metrics.py:15-22) / FailureMode
@@ -61,7 +62,7 @@ class DexsimGroup(C.Structure):
 
 
 class DexsimStepIO(C.Structure):
-    _fields_ = [("action", C.c_void_p), ("action_layout", C.c_int32), ("pad_", C.c_int32),
+    _fields_ = [("action", C.c_void_p), ("action_layout", C.c_int32), ("flags", C.c_int32),
                 ("dyn_noise", C.c_void_p), ("obs_noise", C.c_void_p), ("noisy_obs", C.c_void_p),
                 ("reward", C.c_void_p), ("reward_comps", C.c_void_p), ("terminated", C.c_void_p),
                 ("truncated", C.c_void_p), ("num_contacts", C.c_void_p), ("finished", C.c_void_p),

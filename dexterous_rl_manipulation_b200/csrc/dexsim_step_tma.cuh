@@ -279,6 +279,9 @@ step_tma_kernel(const DexsimState st, const DexsimParams p, const DexsimGroup* _
                 bulk_commit();
             };
             unsigned held = 0u;                        // bit s: stage s still holds the outputs of tile s_tile[s]
+            // `tile` counts work items 0 .. num_tiles-1 in hand-out order; with DEXSIM_STEP_REVERSE_TILES item t is tile
+            // num_tiles-1-t, so that a step starts where the previous one ended (what is still in L2)
+            const bool reverse = (io.flags & DEXSIM_STEP_REVERSE_TILES) != 0;
             int tile = (int)blockIdx.x;                // first tile: static
             int k = 0;
             for (;; ++k) {
@@ -298,9 +301,10 @@ step_tma_kernel(const DexsimState st, const DexsimParams p, const DexsimGroup* _
                     mbar_arrive(full);
                     break;
                 }
-                s_tile[s] = tile;
+                const int tile_id = reverse ? num_tiles - 1 - tile : tile;
+                s_tile[s] = tile_id;
                 held |= 1u << s;
-                const int64_t base = (int64_t)tile * TILE;
+                const int64_t base = (int64_t)tile_id * TILE;
                 const uint32_t cols = tile_cols(n, base);
                 const bool full_tile = (n - base) >= TILE;
                 uint32_t tx = (30 + 3) * TILE * 4 + 3 * TILE * 8 + cols * (8 + 4 + 4 + 1);
@@ -312,6 +316,7 @@ step_tma_kernel(const DexsimState st, const DexsimParams p, const DexsimGroup* _
                 tma_load_2d(sb + OFF_JPJV, &maps.obs_jpjv, (int)base, DEXSIM_ROW_JP, full);
                 tma_load_2d(sb + OFF_OV, &maps.obs_ov, (int)base, DEXSIM_ROW_OV, full);
                 tma_load_2d(sb + OFF_OP64, &maps.op64, (int)base, 0, full);
+                // (an L2 evict-first hint on these streaming loads and on the per-env output stores was measured: no effect)
                 if (AOS) { if (full_tile) bulk_load(sb + OFF_ACT, io.action + base * NJ, NJ * TILE * 4, full); }
                 else tma_load_2d(sb + OFF_ACT, &maps.act_soa, (int)base, 0, full);
                 bulk_load(sb + OFF_THR, st.thr + base, cols * 8, full);

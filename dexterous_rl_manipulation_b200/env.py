@@ -223,6 +223,7 @@ class BatchedManipulationEnv:
         # (same numbers, kept for cross-checking)
         self.fused_noise = True
         self._io_has_noise = False
+        self._alternate_tiles = _L.STEP_REVERSE_TILES    # 0 switches the alternation off (experiments)
         self._state_ref, self._params_ref, self._io_ref = C.byref(self._state), C.byref(self._params), C.byref(self._io)
         self._goe_ptr = self._ptr(self._goe)
         self._step_out = None
@@ -568,6 +569,7 @@ class BatchedManipulationEnv:
             # hot path: one ctypes call, persistent output views, no allocation
             io = self._io
             io.action, io.action_layout = action.data_ptr(), 1
+            io.flags ^= self._alternate_tiles          # walk the batch back and forth: a step starts on what is still in L2
             if self._io_has_noise:
                 io.dyn_noise = io.obs_noise = io.noisy_obs = None
                 io.sigma_dyn = io.sigma_obs = 0.0
@@ -613,6 +615,7 @@ class BatchedManipulationEnv:
         io = self._io
         a = self._ingest_action(action)
         io.action, io.action_layout = a.data_ptr(), 1
+        io.flags ^= self._alternate_tiles
         keep = [a]
         group_obs, group_dyn = self._group_noise
         want_dyn = dyn_noise is not None or self.dynamics_noise_std > 0.0 or group_dyn

@@ -138,13 +138,19 @@ typedef struct DexsimGroup {
     float   sigma_obs, sigma_dyn;
 } DexsimGroup;
 
+/* DexsimStepIO.flags: walk the batch from its last tile to its first.  A caller that steps the same state repeatedly
+ * alternates this bit from call to call (the Python face does): what the previous step touched last is what is still in
+ * the 126 MB L2 -- reads of those tiles hit, and their stores overwrite lines that are still dirty instead of costing a
+ * write-back.  Results do not depend on it. */
+#define DEXSIM_STEP_REVERSE_TILES 1
+
 /* Inputs / outputs of one batched step (all device pointers, SoA with the state's ld). */
 typedef struct DexsimStepIO {
     const float* action;        /* [15, ld] (layout 0) or [n, 15] (layout 1); required for dexsim_step.  A 16-byte aligned
                                  * base takes the vectorised / bulk-copy paths; any other alignment (e.g. an [n,15] slice
                                  * that starts at an odd env) is read with scalar loads by the register-resident kernel. */
     int32_t      action_layout; /* 0 = SoA [15, ld], 1 = AoS [n, 15] (the reference's per-env layout) */
-    int32_t      pad_;
+    int32_t      flags;         /* DEXSIM_STEP_* bits */
     const float* dyn_noise;     /* [15, ld] pre-drawn float32 N(0, sigma_dyn) or NULL (robustness_tests.py:180-187) */
     const float* obs_noise;     /* [45, ld] pre-drawn float32 N(0, sigma_obs) or NULL (:204-205) */
     float*       noisy_obs;     /* [45, ld] out: obs + noise; required iff obs noise is on */

@@ -30,6 +30,8 @@ elif variant in ("api_track", "api_counts", "api_counts_easy", "api_track_easy")
                                     track_episodes=variant.startswith("api_track"), **kw)
 else:
     env = dx.BatchedManipulationEnv(n, "cuda", track_episodes=True, **kw)
+if os.environ.get("DEXSIM_ALTERNATE", "1") == "0":      # walk the batch in the same direction every step (A/B of the L2 reuse)
+    env._alternate_tiles = 0
 env.reset(seed=42)
 g = torch.Generator(device="cuda").manual_seed(0)
 pool = [torch.rand(n, 15, device="cuda", generator=g) * 2 - 1 for _ in range(4)]

@@ -18,7 +18,7 @@ g = torch.Generator(device="cuda").manual_seed(0)
 pool = [torch.rand(n, 15, device="cuda", generator=g) * 2 - 1 for _ in range(4)]
 for cfg_name in ("hard", "easy"):
     for variant in ("api", "api_counts", "api_track"):
-        for sched in ("static", "dynamic"):
+        for sched in ("static", "dynamic", "dyn+alt"):
             kw = dict(max_episode_steps=200, reward_type="dense", curriculum_config=getattr(CC, cfg_name)(), seed=42)
             if variant != "api":
                 kw.update(auto_reset=True, respawn=True, loop_max_steps=200, track_episodes=variant == "api_track")
@@ -27,6 +27,8 @@ for cfg_name in ("hard", "easy"):
             env = dx.BatchedManipulationEnv(n, "cuda", **kw)
             if sched == "static":
                 env._io.sched = None
+            if sched != "dyn+alt":          # "dyn+alt": dynamic tiles + the walk direction alternating from step to step (the default)
+                env._alternate_tiles = 0
             env.reset(seed=42)
             for t in range(20):
                 env.step(pool[t % 4])
