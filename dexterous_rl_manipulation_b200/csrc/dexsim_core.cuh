@@ -77,6 +77,26 @@ DEXSIM_D double clip_f64(double x, double lo, double hi) {
 // relative width 2^-49, the "contact branch" -- is the square root evaluated; the decision is
 // bit-identical to the reference's everywhere.  Likewise min_i RN(sqrt(sq_i)) == RN(sqrt(min_i sq_i)),
 // so the dense reward needs one square root, not five.
+// One finger of the test below (shared by update_contacts and the warp-cooperative reset): returns the contact bit,
+// sq = squared fingertip-object distance.
+DEXSIM_D bool finger_contact(const float j0, const float j1, const float j2, const double op0, const double op1, const double op2,
+                             const double thr, const double lo2, const double hi2, const bool thr_pos, double& sq) {
+    // :301-302 float32 sequential sum of 3 joints, "* 0.1" stays float32, then widened (:300)
+    const float s = __fadd_rn(__fadd_rn(j0, j1), j2);
+    const double tip = (double)__fmul_rn(s, 0.1f);
+    // :309 np.linalg.norm(axis=1) in float64, left to right
+    const double dx = __dsub_rn(tip, op0);
+    const double dy = __dsub_rn(tip, op1);
+    const double dz = __dsub_rn(tip, op2);
+    sq = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
+    // two compares and a select for all but the tie band: lanes of a warp differ in their contact state all the
+    // time, so an if / else-if chain here diverges (ncu: 26 of 32 lanes active on these lines); the band does not
+    const bool below = sq < lo2, above = sq > hi2;
+    bool c = below;
+    if (!(below || above)) c = __dsqrt_rn(sq) < thr;           // tie band (and NaN): exact test, :310
+    return c && thr_pos;
+}
+
 template <bool NEED_DMIN>
 DEXSIM_D unsigned update_contacts(const EnvRegs& e, int& n_c, double& dmin) {
     unsigned mask = 0u;
@@ -87,20 +107,9 @@ DEXSIM_D unsigned update_contacts(const EnvRegs& e, int& n_c, double& dmin) {
     double sqmin = 0.0;
 #pragma unroll
     for (int f = 0; f < NF; ++f) {
-        // :301-302 float32 sequential sum of 3 joints, "* 0.1" stays float32, then widened (:300)
-        const float s = __fadd_rn(__fadd_rn(e.jp[3 * f], e.jp[3 * f + 1]), e.jp[3 * f + 2]);
-        const double tip = (double)__fmul_rn(s, 0.1f);
-        // :309 np.linalg.norm(axis=1) in float64, left to right
-        const double dx = __dsub_rn(tip, e.op[0]);
-        const double dy = __dsub_rn(tip, e.op[1]);
-        const double dz = __dsub_rn(tip, e.op[2]);
-        const double sq = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
-        // two compares and a select for all but the tie band: lanes of a warp differ in their contact state all the
-        // time, so an if / else-if chain here diverges (ncu: 26 of 32 lanes active on these lines); the band does not
-        const bool below = sq < lo2, above = sq > hi2;
-        bool c = below;
-        if (!(below || above)) c = __dsqrt_rn(sq) < e.thr;         // tie band (and NaN): exact test, :310
-        c = c && thr_pos;
+        double sq;
+        const bool c = finger_contact(e.jp[3 * f], e.jp[3 * f + 1], e.jp[3 * f + 2], e.op[0], e.op[1], e.op[2], e.thr, lo2, hi2,
+                                      thr_pos, sq);
         mask |= (c ? 1u : 0u) << f;
         n_c += c ? 1 : 0;
         if (NEED_DMIN) sqmin = (f == 0) ? sq : ((sq < sqmin || sq != sq) ? sq : sqmin);   // np.min propagates NaN

@@ -51,7 +51,12 @@ constexpr int OFF_EPST0 = OFF_EPRET + TILE * 8;     // [128] u32, in/out (tracki
 constexpr int OFF_EPST1 = OFF_EPST0 + TILE * 4;     // [128] u32, in/out (tracking)
 constexpr int OFF_FIN = OFF_EPST1 + TILE * 4;       // [128] u8, out (auto-reset)
 constexpr int OFF_EPISODE = OFF_FIN + TILE;         // [128] u32, in (in-kernel noise: Philox counter word)
+#ifdef DEXSIM_RESET_COOP
+constexpr int OFF_WSLOT = OFF_EPISODE + TILE * 4;   // [128] u64 scratch: one slot per resetting env of a warp (experiment build only)
+constexpr int STAGE_BYTES = (OFF_WSLOT + TILE * 8 + 127) / 128 * 128;
+#else
 constexpr int STAGE_BYTES = (OFF_EPISODE + TILE * 4 + 127) / 128 * 128;      // every stage starts 128-byte aligned
+#endif
 static_assert(OFF_OV % 128 == 0 && OFF_OP64 % 128 == 0 && OFF_ACT % 128 == 0, "tensor-map box destinations");
 static_assert(OFF_THR % 16 == 0 && OFF_DAMP % 16 == 0 && OFF_SC % 16 == 0 && OFF_REWARD % 16 == 0 && OFF_CMASK % 16 == 0 &&
               OFF_TERM % 16 == 0 && OFF_TRUNC % 16 == 0 && OFF_NC % 16 == 0 && OFF_EPRET % 16 == 0 && OFF_EPST0 % 16 == 0 &&
@@ -123,30 +128,40 @@ __device__ __forceinline__ uint32_t tile_cols(int64_t n, int64_t base) {
 // 0.45 % resets per env-step 69.4 vs 70.6 (counts) and 77.4 vs 79.9 (full tracking); 6.8 % resets per env-step 99.2 vs
 // 104.1 and 119.7 vs 131.9 -- the shuffles, the rank search and the read-back of the new state through shared memory
 // cost more than the serialised Philox blocks they save.  The product therefore resets on the owning lane.
-//   rm: ballot of resetting lanes; episode / g: each lane's NEW episode index and group (read by shuffle).
+//   rm: ballot of resetting lanes; episode / g: each lane's NEW episode index and group.  A resetting lane publishes
+//   (lane, group, episode) in a per-warp slot indexed by its rank among the resetting lanes; work items read their env from there.
 //   keep-position mode (p.respawn == 0): the owner has stored (double)(float)position into the stage before the call.
-__device__ __forceinline__ void warp_reset_draws(const unsigned rm, const int lane, const int wcol0, const int64_t base,
-                                                 unsigned char* sp, const DexsimState& st, const DexsimParams& p,
-                                                 const DexsimGroup* __restrict__ groups, const uint32_t episode,
-                                                 const int g, const bool any_ranged) {
+//   Phase A: (env, Philox block) items -> joints into the stage, position / parameters to their rows.
+//   Phase B: (env, finger) items -> contact bits (finger_contact), contact rows, the mask assembled with one ballot.
+#ifdef DEXSIM_RESET_COOP
+__device__ __forceinline__ void warp_reset_draws(const unsigned rm, const bool do_reset, const int lane, const int wcol0,
+                                                 const int64_t base, unsigned char* sp, const DexsimState& st,
+                                                 const DexsimParams& p, const DexsimGroup* __restrict__ groups,
+                                                 const uint32_t episode, const int g, const bool any_ranged) {
     float* s_jpjv = reinterpret_cast<float*>(sp + OFF_JPJV);
     double* s_op = reinterpret_cast<double*>(sp + OFF_OP64);
     double* s_thr = reinterpret_cast<double*>(sp + OFF_THR);
     int* s_sc = reinterpret_cast<int*>(sp + OFF_SC);
+    uint8_t* s_cmask = reinterpret_cast<uint8_t*>(sp + OFF_CMASK);
+    unsigned long long* wslot = reinterpret_cast<unsigned long long*>(sp + OFF_WSLOT) + wcol0;
     float* __restrict__ obs = st.obs;
     const int64_t ld = st.ld;
+    const int m = __popc(rm);
+    if (do_reset)
+        wslot[__popc(rm & ((1u << lane) - 1u))] = (unsigned long long)episode | ((unsigned long long)(unsigned)g << 32) |
+                                                  ((unsigned long long)(unsigned)lane << 48);
+    __syncwarp();
     const int nb = any_ranged ? 7 : 5;
-    const int items = __popc(rm) * nb;
+    const int items = m * nb;
     for (int t0 = 0; t0 < items; t0 += 32) {
         const int t = t0 + lane;
-        const bool act = t < items;
-        const int r = act ? (any_ranged ? t / 7 : t / 5) : 0;
+        if (t >= items) continue;
+        const int r = any_ranged ? t / 7 : t / 5;
         const int b = t - r * nb;
-        const int src = (int)__fns(rm, 0u, r + 1);                    // lane of the r-th resetting env
-        const uint32_t ep = __shfl_sync(0xffffffffu, episode, src);
-        const int gi = __shfl_sync(0xffffffffu, g, src);
-        if (!act) continue;
-        const int c = wcol0 + src;
+        const unsigned long long slot = wslot[r];
+        const uint32_t ep = (uint32_t)slot;
+        const int gi = (int)((slot >> 32) & 0xFFFFu);
+        const int c = wcol0 + (int)(slot >> 48);
         const int64_t i = base + c;
         const uint32_t gid = (uint32_t)(p.env_gid0 + i);
         const DexsimGroup& grp = groups[gi];
@@ -207,7 +222,35 @@ __device__ __forceinline__ void warp_reset_draws(const unsigned rm, const int la
             st.damp[i] = (float)__dsub_rn(1.0, __dmul_rn(__dmul_rn(friction, 0.1), 0.01));
         }
     }
+    __syncwarp();                                                     // joints / position / threshold of every resetting env are in the stage
+    // Phase B: six envs per round, lane = 5 * (env of the round) + finger
+    const int el = lane / 5, f = lane - 5 * el;
+    for (int r0 = 0; r0 < m; r0 += 6) {
+        const int r = r0 + el;
+        const bool act = lane < 30 && r < m;
+        bool cbit = false;
+        int c = 0;
+        int64_t i = 0;
+        if (act) {
+            c = wcol0 + (int)(wslot[r] >> 48);
+            i = base + c;
+            const double thr = s_thr[c];
+            const double thr2 = __dmul_rn(thr, thr);
+            double sq;
+            cbit = finger_contact(s_jpjv[(3 * f) * TILE + c], s_jpjv[(3 * f + 1) * TILE + c], s_jpjv[(3 * f + 2) * TILE + c],
+                                  s_op[c], s_op[TILE + c], s_op[2 * TILE + c], thr, __dmul_rn(thr2, 1.0 - 0x1p-50),
+                                  __dmul_rn(thr2, 1.0 + 0x1p-50), thr > 0.0, sq);
+            obs[(DEXSIM_ROW_CONTACT + f) * ld + i] = cbit ? 1.0f : 0.0f;
+        }
+        const unsigned bits = __ballot_sync(0xffffffffu, cbit);
+        if (act && f == 0) {
+            const uint8_t cm = (uint8_t)((bits >> (5 * el)) & 31u);
+            st.cmask[i] = cm;
+            s_cmask[c] = cm;                                          // for the owner (EXTRA instantiations rebuild the observation)
+        }
+    }
 }
+#endif
 
 // DENSE: reward type.  AOS: action layout [n,15].  TRACK: 0 = plain step; 1 = episode tracking (return + history
 // summary per env -> failure labels), auto-reset, counters; 2 = auto-reset and counters only (what a curriculum
@@ -236,8 +279,12 @@ step_tma_kernel(const DexsimState st, const DexsimParams p, const DexsimGroup* _
     const int64_t n = st.n, ld = st.ld;
     const bool count_episodes = TRACK && p.auto_reset && io.counters != nullptr;
     const bool staged_cnt = count_episodes && p.num_groups <= TMA_GROUPS_MAX;
-    // in-kernel noise reads each env's episode counter (Philox counter word) every step: it rides the stage ring
-    const bool load_episode = EXTRA && ((!io.dyn_noise && io.sigma_dyn != 0.0f) || (!io.obs_noise && io.noisy_obs && io.sigma_obs != 0.0f));
+    // The episode counter (Philox counter word) rides the stage ring whenever the kernel may need it: in-kernel noise reads
+    // it every step, and an auto-reset needs it before it can draw anything -- as a dependent load from HBM inside the
+    // compute phase it cost every warp with a finishing lane about a microsecond (ncu, 6.7 % resets per env-step:
+    // long_scoreboard the top stall of the reset path); 4 B/env-step of extra traffic buy that latency back.
+    const bool load_episode = (EXTRA && ((!io.dyn_noise && io.sigma_dyn != 0.0f) || (!io.obs_noise && io.noisy_obs && io.sigma_obs != 0.0f))) ||
+                              (TRACK && p.auto_reset);
 
     if (tid == 0) {
         for (int b = 0; b < STAGES; ++b) mbar_init(smem_u32(&bars[b]), 1);
@@ -352,6 +399,7 @@ step_tma_kernel(const DexsimState st, const DexsimParams p, const DexsimGroup* _
         const int col = tid;
         const int lane = tid & 31;
         const int wcol0 = col - lane;
+        (void)wcol0; (void)lane;        // used by the -DDEXSIM_RESET_COOP experiment build only
         for (int k = 0;; ++k) {
             const int s = k % STAGES;
             unsigned char* sp = stage_base + (size_t)s * STAGE_BYTES;
@@ -452,7 +500,7 @@ step_tma_kernel(const DexsimState st, const DexsimParams p, const DexsimGroup* _
                     if (p.auto_reset && done) {
                         // episode end on the owning lane (counters, labels); the reset draws are shared by the warp below
                         g = group_of_env ? (int)group_of_env[i] : (int)((uint32_t)gid % (uint32_t)p.num_groups);
-                        if (!(EXTRA && (fused_dyn || fused_obs))) episode = st.episode[i];
+                        episode = reinterpret_cast<const uint32_t*>(sp + OFF_EPISODE)[col];     // load_episode is on with auto-reset
                         unsigned long long* cnt = nullptr;
                         double* rs = nullptr;
                         if (count_episodes) {
@@ -514,6 +562,7 @@ step_tma_kernel(const DexsimState st, const DexsimParams p, const DexsimGroup* _
                     }
                 }
             }
+#ifdef DEXSIM_RESET_COOP
             if (TRACK) {
                 // warp-uniform from here: every lane of the warp takes part in its resetting lanes' draws
                 __syncwarp();
@@ -523,24 +572,21 @@ step_tma_kernel(const DexsimState st, const DexsimParams p, const DexsimGroup* _
                     bool ranged = false;
                     if (do_reset) ranged = (groups[g].size_ranged | groups[g].mass_ranged | groups[g].fric_ranged) != 0;
                     const bool any_ranged = __any_sync(0xffffffffu, ranged);
-                    warp_reset_draws(rm, lane, wcol0, base, sp, st, p, groups, episode, g, any_ranged);
-                    __syncwarp();                       // the draws of MY env were written by other lanes
-                    if (do_reset) {
-                        // envs/manipulation_env.py:163-176: velocities zero, step count zero, contacts of the new state
+                    warp_reset_draws(rm, do_reset, lane, wcol0, base, sp, st, p, groups, episode, g, any_ranged);
+                    if (EXTRA) {
+                        __syncwarp();                   // the new state of MY env was written by other lanes
+                        if (do_reset) {                 // rebuild the registers the noisy observation is made from
 #pragma unroll
-                        for (int j = 0; j < NJ; ++j) { e.jp[j] = s_jpjv[j * TILE + col]; e.jv[j] = 0.0f; }
+                            for (int j = 0; j < NJ; ++j) { e.jp[j] = s_jpjv[j * TILE + col]; e.jv[j] = 0.0f; }
 #pragma unroll
-                        for (int c = 0; c < 3; ++c) { e.op[c] = s_op[c * TILE + col]; e.ov[c] = 0.0f; }
-                        e.thr = reinterpret_cast<const double*>(sp + OFF_THR)[col];
-                        e.sc = 0;
-                        int n_c; double dmin;
-                        e.cmask = update_contacts<false>(e, n_c, dmin);
-#pragma unroll
-                        for (int f = 0; f < NF; ++f) obs[(DEXSIM_ROW_CONTACT + f) * ld + i] = ((e.cmask >> f) & 1u) ? 1.0f : 0.0f;
-                        st.cmask[i] = (uint8_t)e.cmask;
+                            for (int c = 0; c < 3; ++c) { e.op[c] = s_op[c * TILE + col]; e.ov[c] = 0.0f; }
+                            e.sc = 0;
+                            e.cmask = (sp + OFF_CMASK)[col];
+                        }
                     }
                 }
             }
+#endif
             if (EXTRA && valid && io.noisy_obs) {
                 // evaluation/robustness_tests.py:204-205: all 45 entries of the observation AFTER the step (and after a
                 // possible auto-reset), rows written straight from registers
