@@ -263,7 +263,7 @@ __device__ __forceinline__ void warp_reset_draws(const unsigned rm, const bool d
 // round 2: 125k .. 152k active cycles per SM under the static round-robin, the launch lasting as long as the slowest),
 // and tiles with episode resets take longer than others; with the counter every SM works until the batch is done.
 template <bool DENSE, bool AOS, int TRACK, bool EXTRA, int STAGES>
-__global__ void __launch_bounds__(TMA_THREADS, (STAGES == 2) ? (TILE <= 96 ? 4 : 3) : 2)
+__global__ void __launch_bounds__(TMA_THREADS, (STAGES == 2) ? (TILE <= 96 ? 4 : 3) : (STAGES == 1 ? 4 : 2))
 step_tma_kernel(const DexsimState st, const DexsimParams p, const DexsimGroup* __restrict__ groups,
                 const uint16_t* __restrict__ group_of_env, const DexsimStepIO io,
                 const __grid_constant__ StepMaps maps, const int num_tiles, const int pdl) {

@@ -1622,3 +1622,30 @@ def test_shared_learner_population_update(dx):
     k = np.lexsort((log["env_gid"], -log["episode_reward"]))[0]
     assert a["winner_gid"][-1] == log["env_gid"][k] and a["best_return"][-1] == log["episode_reward"][k]
     assert np.all(np.abs(a["mean_action"]) <= 0.5 + 1e-7)
+
+
+@pytest.mark.parametrize("n,track", [(70_001, "counts"), (150_000, True)])
+def test_walk_direction_and_tile_schedule_do_not_change_results(dx, n, track, step_impl):
+    """The pipelined step kernel hands tiles out dynamically (DexsimStepIO.sched) and walks the batch in alternating
+    directions from step to step (DEXSIM_STEP_REVERSE_TILES, for L2 reuse): neither may change a bit -- against the same
+    env stepped with static round-robin tiles in one direction, at sizes with several tiles per CTA."""
+    step_impl("tma")
+    CC = dx.CurriculumConfig
+    kw = dict(max_episode_steps=12, reward_type="dense", seed=21, groups=[CC.easy(), CC(object_size_range=(0.03, 0.09))],
+              auto_reset=True, respawn=True, loop_max_steps=12, track_episodes=track is True)
+    a, b = dx.BatchedManipulationEnv(n, "cuda", **kw), dx.BatchedManipulationEnv(n, "cuda", **kw)
+    b._alternate_tiles = 0
+    b._io.sched = None
+    a.reset(seed=21); b.reset(seed=21)
+    gen = torch.Generator(device="cuda").manual_seed(4)
+    for t in range(40):
+        act = torch.rand(n, 15, device="cuda", generator=gen) * 2.4 - 1.2
+        ra, rb = a.step(act), b.step(act)
+        for x, y in zip(ra[:4], rb[:4]):
+            assert torch.equal(x, y), t
+        assert torch.equal(ra[4]["finished"], rb[4]["finished"])
+    assert a._io.flags in (0, 1) and b._io.flags == 0
+    for name in ("_obs", "_op64", "_thr", "_damp", "_step_count", "_cmask", "_size", "_mass", "_friction", "_episode"):
+        assert torch.equal(getattr(a, name), getattr(b, name)), name
+    assert torch.equal(a.counters, b.counters) and int(a.counters[:, 0].sum()) > n
+    assert int(a._sched.abs().sum()) == 0                       # the scheduler words are re-armed after every launch
