@@ -24,7 +24,7 @@ RNG_STREAM_DYN, RNG_STREAM_OBS = 2, 3
 EPISODE_RECORD_DTYPE = _np.dtype([("env_gid", "u4"), ("episode", "u4"), ("steps", "i4"), ("success", "u1"),
                                   ("final_contacts", "u1"), ("label_metrics", "u1"), ("label_taxonomy", "u1"),
                                   ("episode_reward", "f8"), ("t_end", "u4"), ("var_tie", "u4")])
-HOST_SKIP_QUAT, HOST_ASYNC, HOST_PACKED_CONTACTS = 1, 2, 4
+HOST_SKIP_QUAT, HOST_ASYNC, HOST_PACKED_CONTACTS, HOST_EXPAND_CONTACTS = 1, 2, 4, 8
 SCHED_WORDS = 64
 STEP_REVERSE_TILES = 1
 ROLLOUT_NO_DYN_NOISE = 1

@@ -1243,6 +1243,20 @@ int get_pipe(HostPipe** out) {
 }
 }  // namespace
 
+// obs rows 40-44 (envs/manipulation_env.py:262: contacts as 0/1 float32) of envs [0, n) from their contact bit masks
+static void expand_contact_rows_range(float* h_obs, const uint8_t* mask, int64_t lo, int64_t hi, int64_t ld) {
+    float* r0 = h_obs + (size_t)(DEXSIM_ROW_CONTACT + 0) * ld;
+    float* r1 = h_obs + (size_t)(DEXSIM_ROW_CONTACT + 1) * ld;
+    float* r2 = h_obs + (size_t)(DEXSIM_ROW_CONTACT + 2) * ld;
+    float* r3 = h_obs + (size_t)(DEXSIM_ROW_CONTACT + 3) * ld;
+    float* r4 = h_obs + (size_t)(DEXSIM_ROW_CONTACT + 4) * ld;
+    for (int64_t i = lo; i < hi; ++i) {
+        const unsigned b = mask[i];
+        r0[i] = (float)(b & 1u); r1[i] = (float)((b >> 1) & 1u); r2[i] = (float)((b >> 2) & 1u);
+        r3[i] = (float)((b >> 3) & 1u); r4[i] = (float)((b >> 4) & 1u);
+    }
+}
+
 int dexsim_step_host(const DexsimState* st, const DexsimParams* p, const DexsimGroup* groups,
                      const uint16_t* group_of_env, const DexsimStepIO* io, const float* h_action, float* h_obs,
                      float* h_reward, uint8_t* h_terminated, uint8_t* h_truncated, uint8_t* h_num_contacts,
@@ -1282,6 +1296,8 @@ int dexsim_step_host(const DexsimState* st, const DexsimParams* p, const DexsimG
     // observation rows that travel: all 45, or without the constant quaternion rows 33-36 (SKIP_QUAT), and without the
     // five 0/1 contact rows 40-44 when the 1-byte contact mask is sent instead (PACKED_CONTACTS)
     const int rows_hi = (flags & DEXSIM_HOST_PACKED_CONTACTS) ? DEXSIM_ROW_CONTACT : DEXSIM_OBS;
+    const bool expand_on_host = (flags & DEXSIM_HOST_EXPAND_CONTACTS) && (flags & DEXSIM_HOST_PACKED_CONTACTS) &&
+                                !(flags & DEXSIM_HOST_ASYNC) && h_obs != nullptr;
     // Whatever happens while enqueueing, the caller's stream is joined with the internal ones before returning,
     // so that no copy is still in flight on a stream the caller cannot see.
     auto copy_vectors = [&](cudaStream_t s, int64_t lo, int64_t m) -> int {
@@ -1295,7 +1311,7 @@ int dexsim_step_host(const DexsimState* st, const DexsimParams* p, const DexsimG
             err = cudaMemcpyAsync(h_num_contacts + lo, io->num_contacts + lo, (size_t)m, cudaMemcpyDeviceToHost, s);
             if (err != cudaSuccess) return -(int)err;
         }
-        if (flags & DEXSIM_HOST_PACKED_CONTACTS) {
+        if ((flags & DEXSIM_HOST_PACKED_CONTACTS) && !(expand_on_host && nchunks > 1)) {
             err = cudaMemcpyAsync(h_contact_mask + lo, st->cmask + lo, (size_t)m, cudaMemcpyDeviceToHost, s);
             if (err != cudaSuccess) return -(int)err;
         }
@@ -1328,6 +1344,10 @@ int dexsim_step_host(const DexsimState* st, const DexsimParams* p, const DexsimG
         rc = launch_step(&sub, &sp, groups, group_of_env ? group_of_env + lo : nullptr, &sio, s);
         if (rc) return rc;
         if (nchunks > 1) {
+            if (expand_on_host) {                        // the chunk's contact masks first: the host expands them while its rows travel
+                err = cudaMemcpyAsync(h_contact_mask + lo, st->cmask + lo, (size_t)m, cudaMemcpyDeviceToHost, s);
+                if (err != cudaSuccess) return -(int)err;
+            }
             err = cudaEventRecord(hp->kdone[c], s);      // this chunk's kernel has run: its per-env vectors are final
             if (err != cudaSuccess) return -(int)err;
         }
@@ -1378,6 +1398,17 @@ int dexsim_step_host(const DexsimState* st, const DexsimParams* p, const DexsimG
         enqueue_lock.unlock();
     }
     if ((flags & DEXSIM_HOST_ASYNC) && rc == 0) return 0;          // the caller synchronizes `stream` before reading
+    if (rc == 0 && expand_on_host) {
+        // A chunk's 1-byte contact masks reach the host right after its kernel, before its observation rows: this thread
+        // writes the five 0/1 contact rows chunk by chunk while the DMA engine is still downloading the other 36 rows --
+        // 20 of 171 bytes per env never cross PCIe and the observation is complete on return.
+        for (int c = 0; c < nchunks && rc == 0; ++c) {
+            const int64_t lo = (int64_t)c * per, hi = (lo + per < n) ? lo + per : n;
+            const cudaError_t err = nchunks > 1 ? cudaEventSynchronize(hp->kdone[c]) : cudaStreamSynchronize(user);
+            if (err == cudaSuccess) expand_contact_rows_range(h_obs, h_contact_mask, lo, hi, ld);
+            else rc = -(int)err;
+        }
+    }
     const int sync_rc = cuda_rc(cudaStreamSynchronize(user));
     return rc ? rc : sync_rc;
 }

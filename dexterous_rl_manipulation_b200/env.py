@@ -224,6 +224,7 @@ class BatchedManipulationEnv:
         self.fused_noise = True
         self._io_has_noise = False
         self._alternate_tiles = _L.STEP_REVERSE_TILES    # 0 switches the alternation off (experiments)
+        self.host_expand_contacts = True                 # step_host(): contact columns travel packed, expanded on the host
         self._state_ref, self._params_ref, self._io_ref = C.byref(self._state), C.byref(self._params), C.byref(self._io)
         self._goe_ptr = self._ptr(self._goe)
         self._step_out = None
@@ -860,6 +861,11 @@ class BatchedManipulationEnv:
         if a.dtype != torch.float32 or not a.is_contiguous() or a.numel() != n * 15:
             a = a.to(torch.float32).reshape(n, 15).contiguous()
         flags = _L.HOST_SKIP_QUAT | (0 if sync else _L.HOST_ASYNC) | (_L.HOST_PACKED_CONTACTS if packed_contacts else 0)
+        if sync and not packed_contacts and self.host_expand_contacts:
+            # default transport of a synchronous call: the contact columns travel as their 1-byte mask and the calling
+            # thread expands them into the pinned observation while the other rows are still being downloaded --
+            # the returned observation is complete, 20 of 171 bytes per env never cross PCIe
+            flags |= _L.HOST_PACKED_CONTACTS | _L.HOST_EXPAND_CONTACTS
         with torch.cuda.device(self.device):
             self._sync_groups()
             io = self._io

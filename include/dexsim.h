@@ -338,6 +338,9 @@ int dexsim_classify_summary(const DexsimEpisodeSummary* s, const uint8_t* counts
                                         * the device and the 1-byte contact mask (bit f = finger f, DexsimState.cmask) is
                                         * copied to h_contact_mask instead (-19 bytes of 171 per env); the caller expands
                                         * the rows on the host if and when it needs them */
+#define DEXSIM_HOST_EXPAND_CONTACTS 8  /* with PACKED_CONTACTS (and not ASYNC): the calling thread writes obs rows 40-44 of h_obs
+                                        * from the masks while the other rows are still being downloaded, so h_obs is complete
+                                        * on return although the five rows never crossed PCIe */
 int dexsim_step_host(const DexsimState* st, const DexsimParams* p, const DexsimGroup* groups,
                      const uint16_t* group_of_env, const DexsimStepIO* io /* device scratch */,
                      const float* h_action /* host [n, 15] (layout 1) or [15, ld] (layout 0) */,

@@ -1356,11 +1356,16 @@ def test_bench_b200_arm_prints_one_contract_line():
     assert d["metric"] == "env_steps_per_sec" and d["n_gpus"] == 1 and d["steps"] == 20 and d["warmup"] == 3
     assert d["gpu_launches"] == 20 and d["scaling"] == "weak" and d["vs_baseline"] is None and d["data"] == "synthetic"
     r = d["roofline"]
-    assert r["bound"] == "hbm" and r["unit"] == "GB/s" and 0.0 < r["frac"] < 1.0
+    # `achieved` counts ALGORITHMIC bytes: with consecutive steps walking the batch in opposite directions a fifth of them
+    # is served by L2 (and a 262,144-env batch is almost L2-resident), so the fraction may exceed 1 -- but not by much
+    assert r["bound"] == "hbm" and r["unit"] == "GB/s" and 0.0 < r["frac"] < 2.0
     assert abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9
+    assert r["sustained_steps"] >= 400 and 0.0 < r["frac_sustained"] < 2.0 and "traffic_steady_state" in r
     assert abs(d["value"] - 262144 * 20 / (d["ms_per_step"] * 20e-3)) / d["value"] < 1e-6
     e = d["e2e"]
-    assert e["value"] > 0 and e["h2d_bytes_per_step"] == 262144 * 60 and e["d2h_bytes_per_step"] > 262144 * 164
+    # 36 observation rows + reward + 3 flag bytes + the contact mask cross PCIe; the 5 contact rows are expanded on the host
+    assert e["value"] > 0 and e["h2d_bytes_per_step"] == 262144 * 60 and e["d2h_bytes_per_step"] == 262144 * (36 * 4 + 8)
+    assert e["all_rows_d2h_bytes_per_step"] == 262144 * (41 * 4 + 7) and e["copy_ceiling"]["value"] > e["value"] * 0.8
     assert e["value"] < d["value"]                       # host buffers cross PCIe: never faster than the device-resident loop
 
 

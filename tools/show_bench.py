@@ -8,7 +8,7 @@ for path in sys.argv[1:]:
     print(f"== {path}: n_gpus {d.get('n_gpus')} steps {d.get('steps')}")
     print(f"  value {d['value']:.4g}  ms/step {d['ms_per_step']:.5f}  frac {r.get('frac', 0):.3f}  frac_sustained {r.get('frac_sustained', 0):.3f} "
           f"({r.get('kernel_ms_sustained', 0) * 1e3:.2f} us)  traffic {r.get('traffic')}")
-    print(f"  e2e {e.get('value', 0):.4g}  of ceiling {e.get('frac_of_copy_ceiling')}  async {e.get('async_value', 0):.4g}  packed {e.get('packed_contacts_value', 0):.4g}  "
+    print(f"  e2e {e.get('value', 0):.4g}  of ceiling {e.get('frac_of_copy_ceiling')}  async {e.get('async_value', 0):.4g}  packed {e.get('packed_contacts_value', 0):.4g}  all_rows {e.get('all_rows_value', 0):.4g}  "
           f"ceiling {((e.get('copy_ceiling') or {}).get('value') or 0):.4g}")
     t, nz, f = d.get("tracking_full") or {}, d.get("noisy_api") or {}, d.get("fused_rollout") or {}
     print(f"  tracking_full frac {t.get('roofline_frac', 0):.3f} ({t.get('ms_per_step', 0) * 1e3:.2f} us)  noisy {nz.get('us_per_step', 0):.1f} us  fused {f.get('value', 0):.4g}")
