@@ -99,6 +99,7 @@ EXPORTS = (
     "dexsim_device_info", "dexsim_set_step_impl", "dexsim_set_rollout_impl", "dexsim_reset_predrawn",
     "dexsim_reset_philox", "dexsim_step", "dexsim_rollout", "dexsim_fill_policy_actions",
     "dexsim_fill_normal", "dexsim_classify_summary", "dexsim_step_host", "dexsim_pack_env", "dexsim_pack_env_tagged", "dexsim_step_single",
+    "dexsim_expand_contact_rows",
 )
 
 _lib = None
@@ -146,6 +147,7 @@ def lib():
                                           C.POINTER(i32), C.POINTER(i32)]
     L.dexsim_step_host.argtypes = [C.POINTER(DexsimState), C.POINTER(DexsimParams), vp, vp, C.POINTER(DexsimStepIO),
                                    vp, vp, vp, vp, vp, vp, vp, i32, i32, vp]
+    L.dexsim_expand_contact_rows.argtypes = [vp, vp, i64, i64]
     for name in EXPORTS:
         fn = getattr(L, name)          # raises AttributeError if a declared symbol is not exported
         if name not in ("dexsim_error_string",):

@@ -14,7 +14,8 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 SRC = os.path.join(HERE, "csrc", "dexsim_kernels.cu")
-DEPS = [SRC] + [os.path.join(HERE, "csrc", h) for h in ("dexsim_core.cuh", "dexsim_step_tma.cuh", "dexsim_rollout_split.cuh")] \
+HOST_SRC = os.path.join(HERE, "csrc", "dexsim_host_expand.cpp")     # plain C++ (host compiler): AVX2 expansion of packed contact rows
+DEPS = [SRC, HOST_SRC] + [os.path.join(HERE, "csrc", h) for h in ("dexsim_core.cuh", "dexsim_step_tma.cuh", "dexsim_rollout_split.cuh")] \
     + [os.path.join(HERE, "..", "include", "dexsim.h")]
 OUT = os.path.join(HERE, "libdexsim_b200.so")
 INFO = os.path.join(HERE, "BUILD_INFO.json")       # written next to the library: source hash + the nvcc command line
@@ -74,7 +75,7 @@ def build(force=False, verbose=False, out=None, defines=()):
     if out is None and not force and not needs_build():
         return OUT
     out = out or OUT
-    cmd = [nvcc_path()] + NVCC_FLAGS + [f"-D{d}" for d in defines] + (["-Xptxas", "-v"] if verbose else []) + ["-o", out, SRC]
+    cmd = [nvcc_path()] + NVCC_FLAGS + [f"-D{d}" for d in defines] + (["-Xptxas", "-v"] if verbose else []) + ["-o", out, SRC, HOST_SRC]
     proc = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if verbose or proc.returncode != 0:
         sys.stderr.write(proc.stdout)
@@ -82,7 +83,7 @@ def build(force=False, verbose=False, out=None, defines=()):
         raise RuntimeError("nvcc failed building libdexsim_b200.so")
     if out == OUT:
         with open(INFO, "w") as fh:
-            json.dump({"sources_sha256": sources_sha256(), "nvcc": " ".join(cmd[:1] + [c for c in cmd[1:] if c != out and c != SRC]),
+            json.dump({"sources_sha256": sources_sha256(), "nvcc": " ".join(cmd[:1] + [c for c in cmd[1:] if c not in (out, SRC, HOST_SRC)]),
                        "flags": NVCC_FLAGS, "defines": list(defines)}, fh, indent=1)
     return out
 

@@ -985,6 +985,11 @@ static int launch_step(const DexsimState* st, const DexsimParams* p, const Dexsi
 
 }  // namespace dexsim
 
+namespace dexsim {
+// csrc/dexsim_host_expand.cpp: observation rows 40-44 of envs [lo, hi) from their 1-byte contact masks (host code)
+void expand_contact_rows_range(float* h_obs, const uint8_t* mask, int64_t lo, int64_t hi, int64_t ld);
+}  // namespace dexsim
+
 using namespace dexsim;
 
 extern "C" {
@@ -1243,18 +1248,11 @@ int get_pipe(HostPipe** out) {
 }
 }  // namespace
 
-// obs rows 40-44 (envs/manipulation_env.py:262: contacts as 0/1 float32) of envs [0, n) from their contact bit masks
-static void expand_contact_rows_range(float* h_obs, const uint8_t* mask, int64_t lo, int64_t hi, int64_t ld) {
-    float* r0 = h_obs + (size_t)(DEXSIM_ROW_CONTACT + 0) * ld;
-    float* r1 = h_obs + (size_t)(DEXSIM_ROW_CONTACT + 1) * ld;
-    float* r2 = h_obs + (size_t)(DEXSIM_ROW_CONTACT + 2) * ld;
-    float* r3 = h_obs + (size_t)(DEXSIM_ROW_CONTACT + 3) * ld;
-    float* r4 = h_obs + (size_t)(DEXSIM_ROW_CONTACT + 4) * ld;
-    for (int64_t i = lo; i < hi; ++i) {
-        const unsigned b = mask[i];
-        r0[i] = (float)(b & 1u); r1[i] = (float)((b >> 1) & 1u); r2[i] = (float)((b >> 2) & 1u);
-        r3[i] = (float)((b >> 3) & 1u); r4[i] = (float)((b >> 4) & 1u);
-    }
+int dexsim_expand_contact_rows(float* h_obs, const uint8_t* h_contact_mask, int64_t n, int64_t ld) {
+    if (!h_obs || !h_contact_mask) return DEXSIM_E_NULL;
+    if (n < 0 || ld < n) return DEXSIM_E_SIZE;
+    expand_contact_rows_range(h_obs, h_contact_mask, 0, n, ld);
+    return 0;
 }
 
 int dexsim_step_host(const DexsimState* st, const DexsimParams* p, const DexsimGroup* groups,

@@ -888,10 +888,8 @@ class BatchedManipulationEnv:
     def expand_contacts_host(self, slot=0):
         """Fill obs[:, 40:45] of a ``packed_contacts`` result in from its contact mask (host-side, vectorised)."""
         b = self._host_buffers(slot)
-        n = self.num_envs
-        m = b["cmask"][:n]
-        for f in range(5):
-            b["obs"][_L.ROW_CONTACT + f, :n] = ((m >> f) & 1).to(torch.float32)
+        _lib.check(self._lib.dexsim_expand_contact_rows(b["obs"].data_ptr(), b["cmask"].data_ptr(), self.num_envs, self.ld),
+                   "dexsim_expand_contact_rows")
         return b["out"][0]
 
     # ------------------------------------------------------------------ fused rollout

@@ -349,6 +349,12 @@ int dexsim_step_host(const DexsimState* st, const DexsimParams* p, const DexsimG
                      uint8_t* h_contact_mask /* host [ld]; required with DEXSIM_HOST_PACKED_CONTACTS, else may be NULL */,
                      int32_t chunks, int32_t flags, void* stream);
 
+/* HOST function: observation rows 40-44 (the five 0/1 contact floats, envs/manipulation_env.py:262) of envs [0, n) of a
+ * host [45, ld] observation buffer from their 1-byte contact masks -- what DEXSIM_HOST_EXPAND_CONTACTS does chunk by chunk
+ * during the download, for callers that took DEXSIM_HOST_PACKED_CONTACTS and expand on demand.  AVX2 when available. */
+int dexsim_expand_contact_rows(float* h_obs /* host [45, ld] */, const uint8_t* h_contact_mask /* host [ld] */,
+                               int64_t n, int64_t ld);
+
 #ifdef __cplusplus
 }
 #endif

@@ -434,3 +434,23 @@ def test_curriculum_driver_tail_progresses_at_most_once_per_episode():
         assert got == (6 if hasattr(sched, "_should_progress") else 4), type(sched)
         assert sched.total_episodes == 10 and sched.total_steps == 100
         assert (drv.exact_episodes, drv.exact_successes) == (10, 10)
+
+
+def test_host_contact_row_expansion():
+    """dexsim_expand_contact_rows (host code, AVX2 or scalar): rows 40-44 of a [45, ld] observation from 1-byte contact
+    masks, for aligned and unaligned buffers and ragged sizes; nothing outside those rows / beyond n is touched."""
+    import ctypes as C
+    from dexterous_rl_manipulation_b200 import _lib
+    L = _lib.lib()
+    rng = np.random.default_rng(3)
+    for n, ld, offset in ((1, 32, 0), (37, 64, 0), (1000, 1024, 0), (1000, 1024, 1), (65536 + 5, 65568, 0)):
+        raw = np.full(45 * ld + 16, -7.0, np.float32)
+        obs = raw[offset:offset + 45 * ld].reshape(45, ld)             # offset 1: base not 32-byte aligned -> scalar path
+        mask = rng.integers(0, 32, ld).astype(np.uint8)
+        rc = L.dexsim_expand_contact_rows(obs.ctypes.data, mask.ctypes.data, n, ld)
+        assert rc == 0
+        for f in range(5):
+            assert np.array_equal(obs[40 + f, :n], ((mask[:n] >> f) & 1).astype(np.float32)), (n, f)
+            assert np.all(obs[40 + f, n:] == -7.0)
+        assert np.all(obs[:40] == -7.0)
+    assert L.dexsim_expand_contact_rows(None, None, 1, 32) == -1001
