@@ -391,8 +391,9 @@ def run_b200(args):
         from dexterous_rl_manipulation_b200.build import build_info
         with open(os.path.join(ROOT, "profiles", "step_kernel_traffic.json")) as fh:
             tr = json.load(fh)
-        cur = build_info().get("sources_sha256")
-        if int(tr.get("envs", 0)) == E and tr.get("sources_sha256") and tr.get("sources_sha256") == cur:
+        bi = build_info()
+        cur = bi.get("step_kernel_sha256") if bi.get("fresh") else None      # device code of the step kernel the library was built from
+        if int(tr.get("envs", 0)) == E and tr.get("step_kernel_sha256") and tr.get("step_kernel_sha256") == cur:
             traffic = tr["dram_bytes_per_launch"]
             traffic_steady = tr.get("steady_state")
             traffic_note = (f"ncu dram__bytes_read+write.sum of one isolated launch (caches flushed), {tr.get('report', 'profiles/')}, "
@@ -402,7 +403,7 @@ def run_b200(args):
                             f"exceed the DRAM copy peak")
         else:
             traffic_note = (f"not quoted: profiles/step_kernel_traffic.json was measured on kernel sources "
-                            f"{str(tr.get('sources_sha256'))[:16]}, this library is built from {str(cur)[:16]}")
+                            f"{str(tr.get('step_kernel_sha256'))[:16]}, this library is built from {str(cur)[:16]}")
     except (OSError, ValueError, KeyError, ImportError):
         traffic_note = "profiles/step_kernel_traffic.json not readable"
     roofline = {"bound": "hbm", "kernel": "dexsim::step_tma_kernel<dense, AoS action, auto-reset + counters, 2 stages, dynamic tiles, alternating walk>",

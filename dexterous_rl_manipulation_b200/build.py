@@ -47,6 +47,20 @@ def sources_sha256():
     return h.hexdigest()
 
 
+STEP_KERNEL_FILES = ("dexsim_step_tma.cuh", "dexsim_core.cuh")      # the device code of the pipelined step kernel
+
+
+def step_kernel_sha256():
+    """Hash of the step kernel's device code only (profiles/step_kernel_traffic.json is keyed by it: an ncu traffic figure
+    stays quotable across edits of host-side code, and goes stale with any edit of the kernel itself)."""
+    h = hashlib.sha256()
+    for name in STEP_KERNEL_FILES:
+        h.update(name.encode() + b"\0")
+        with open(os.path.join(HERE, "csrc", name), "rb") as fh:
+            h.update(fh.read())
+    return h.hexdigest()
+
+
 def build_info():
     """What the library next to this file was built from, and whether that is the tree's current source."""
     info = {}
@@ -83,7 +97,7 @@ def build(force=False, verbose=False, out=None, defines=()):
         raise RuntimeError("nvcc failed building libdexsim_b200.so")
     if out == OUT:
         with open(INFO, "w") as fh:
-            json.dump({"sources_sha256": sources_sha256(), "nvcc": " ".join(cmd[:1] + [c for c in cmd[1:] if c not in (out, SRC, HOST_SRC)]),
+            json.dump({"sources_sha256": sources_sha256(), "step_kernel_sha256": step_kernel_sha256(), "nvcc": " ".join(cmd[:1] + [c for c in cmd[1:] if c not in (out, SRC, HOST_SRC)]),
                        "flags": NVCC_FLAGS, "defines": list(defines)}, fh, indent=1)
     return out
 

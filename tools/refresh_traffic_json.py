@@ -47,7 +47,8 @@ doc = {
                "profiles/r02_counts_steady_state_noalt.csv holds the same with one direction"},
     "kernel": "step_tma_kernel<dense, AoS, counts-only, 2 stages> (the bench's main loop)",
     "report": "profiles/r02_step_tma_kernel_ncu.txt (launch 9 of tools/profile_step.py 1048576 api_counts)",
-    "sources_sha256": bi["sources_sha256"],
+    "step_kernel_sha256": bi["step_kernel_sha256"],
+    "step_kernel_files": ["csrc/dexsim_step_tma.cuh", "csrc/dexsim_core.cuh"],
 }
 json.dump(doc, open(os.path.join(ROOT, "profiles", "step_kernel_traffic.json"), "w"), indent=1)
 for f in ("r02_counts_steady_state.csv", "r02_counts_steady_state_noalt.csv"):
