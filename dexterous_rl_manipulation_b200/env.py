@@ -878,7 +878,10 @@ class BatchedManipulationEnv:
                 b["trunc"].data_ptr(), b["nc"].data_ptr(), b["cmask"].data_ptr(),
                 int(chunks) if chunks is not None else max(1, min(16, n // 65536)), flags, self._stream()), "dexsim_step_host")
         if not sync:
-            self._host_keepalive = a                   # the upload may still be reading it
+            # the upload may still be reading the action buffer: keep it alive until this slot is used again
+            if getattr(self, "_host_keepalive", None) is None:
+                self._host_keepalive = {}
+            self._host_keepalive[slot] = a
         return b["out"]
 
     def host_sync(self):
