@@ -515,33 +515,35 @@ def run_b200(args):
     # (3) as (1) without the host-side expansion (the caller reads info["contact_mask"] or expands on demand)
     e2e_packed_s = timed_e2e(lambda t: env.step_host(h_pool[t % 2], packed_contacts=True), args.e2e_steps)
     # (4) as (1) with all 41 observation rows crossing PCIe (round 1's transport)
-    env.host_expand_contacts = False
+    env.host_expand_contacts = env.host_static_rows = False
     e2e_full_s = timed_e2e(lambda t: env.step_host(h_pool[t % 2]), args.e2e_steps)
-    env.host_expand_contacts = True
+    env.host_expand_contacts = env.host_static_rows = True
     # the ceiling: the same bytes per step in both directions at once, no kernels (tools/pcie_ceiling.py)
     ceiling = None
     try:
         sys.path.insert(0, os.path.join(ROOT, "tools"))
         import pcie_ceiling
-        cm = pcie_ceiling.measure(E, steps=max(10, args.e2e_steps // 2), device=dev, barrier=barrier, packed_contacts=True)
+        cm = pcie_ceiling.measure(E, steps=max(10, args.e2e_steps // 2), device=dev, barrier=barrier, rows=32, extra_bytes_per_env=8)
         csec = cm["seconds_per_step"]
         if world > 1:
             tt = torch.tensor([csec], device=dev, dtype=torch.float64)
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
             csec = float(tt.item())
         ceiling = {"value": E * n_gpus / csec, "seconds_per_step": csec, "h2d_gbs_per_gpu": cm["h2d_gbs"], "d2h_gbs_per_gpu": cm["d2h_gbs"],
-                   "how": "tools/pcie_ceiling.py: this step's H2D and D2H bytes (36 observation rows, reward, flags, contact mask) copied "
+                   "how": "tools/pcie_ceiling.py: this step's H2D and D2H bytes (32 observation rows, reward, flags, contact mask) copied "
                           "concurrently from / to pinned memory on two streams by every rank at once, no kernels; max over ranks"}
     except Exception as exc:       # the ceiling is context for e2e, never a reason to lose the line
         ceiling = {"value": None, "how": f"failed: {exc!r}"}
     e2e_value = E * n_gpus * args.e2e_steps / e2e_s
-    d2h_bytes = (env.ld * 36 * 4 + E * (4 + 3 + 1)) * n_gpus
+    d2h_bytes = (env.ld * 32 * 4 + E * (4 + 3 + 1)) * n_gpus
     e2e = {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": E * 15 * 4 * n_gpus,
            "d2h_bytes_per_step": d2h_bytes, "steps": args.e2e_steps,
-           "note": "synchronous step_host(), complete [n,45] observation in pinned host memory on return: 36 observation rows + reward + "
-                   "flags + the 1-byte contact mask cross PCIe (the constant quaternion rows are never re-copied; the five 0/1 contact "
-                   "rows are written by the calling thread from the masks while the download is still running); 16 chunks, H2D / kernel / D2H overlapped",
-           "api": "BatchedManipulationEnv.step_host -> dexsim_step_host", "gpu_launches": args.e2e_steps * max(1, min(16, E // 65536)),
+           "note": "synchronous step_host(), complete [n,45] observation in pinned host memory on return: 32 observation rows + reward + "
+                   "flags + the 1-byte contact mask cross PCIe every step (the constant quaternion rows are never re-copied; the five 0/1 "
+                   "contact rows are written by the calling thread from the masks while the download is still running; object x, y and "
+                   "their velocities only change at a reset and are mirrored into the pinned buffer by the step kernel); 8 chunks, "
+                   "H2D / kernel / D2H overlapped",
+           "api": "BatchedManipulationEnv.step_host -> dexsim_step_host", "gpu_launches": args.e2e_steps * max(1, min(8, E // 65536)),
            "numa_bound": bool(numa_bound),
            "copy_ceiling": ceiling,
            "frac_of_copy_ceiling": (e2e_value / ceiling["value"]) if ceiling and ceiling.get("value") else None,

@@ -24,7 +24,7 @@ RNG_STREAM_DYN, RNG_STREAM_OBS = 2, 3
 EPISODE_RECORD_DTYPE = _np.dtype([("env_gid", "u4"), ("episode", "u4"), ("steps", "i4"), ("success", "u1"),
                                   ("final_contacts", "u1"), ("label_metrics", "u1"), ("label_taxonomy", "u1"),
                                   ("episode_reward", "f8"), ("t_end", "u4"), ("var_tie", "u4")])
-HOST_SKIP_QUAT, HOST_ASYNC, HOST_PACKED_CONTACTS, HOST_EXPAND_CONTACTS = 1, 2, 4, 8
+HOST_SKIP_QUAT, HOST_ASYNC, HOST_PACKED_CONTACTS, HOST_EXPAND_CONTACTS, HOST_STATIC_ROWS = 1, 2, 4, 8, 16
 SCHED_WORDS = 64
 STEP_REVERSE_TILES = 1
 ROLLOUT_NO_DYN_NOISE = 1
@@ -67,7 +67,7 @@ class DexsimStepIO(C.Structure):
                 ("reward", C.c_void_p), ("reward_comps", C.c_void_p), ("terminated", C.c_void_p),
                 ("truncated", C.c_void_p), ("num_contacts", C.c_void_p), ("finished", C.c_void_p),
                 ("counters", C.c_void_p), ("ret_sums", C.c_void_p), ("reward64", C.c_void_p),
-                ("sigma_dyn", C.c_float), ("sigma_obs", C.c_float), ("sched", C.c_void_p)]
+                ("sigma_dyn", C.c_float), ("sigma_obs", C.c_float), ("sched", C.c_void_p), ("host_static_rows", C.c_void_p)]
 
 
 class DexsimEpisodeRecord(C.Structure):

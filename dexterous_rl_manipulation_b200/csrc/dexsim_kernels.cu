@@ -53,9 +53,18 @@ __device__ __forceinline__ void load_env(const DexsimState& st, int64_t i, EnvRe
 }
 
 // Full write-back (reset paths): every row including the constant quaternion.
-__device__ __forceinline__ void store_env_full(const DexsimState& st, int64_t i, const EnvRegs& e) {
+// `host`: optional mirror of observation rows 30, 31, 37, 38 in mapped host memory (DexsimStepIO.host_static_rows)
+__device__ __forceinline__ void mirror_static_rows(float* host, int64_t ld, int64_t i, const EnvRegs& e) {
+    host[(DEXSIM_ROW_OP + 0) * ld + i] = (float)e.op[0];
+    host[(DEXSIM_ROW_OP + 1) * ld + i] = (float)e.op[1];
+    host[(DEXSIM_ROW_OV + 0) * ld + i] = e.ov[0];
+    host[(DEXSIM_ROW_OV + 1) * ld + i] = e.ov[1];
+}
+
+__device__ __forceinline__ void store_env_full(const DexsimState& st, int64_t i, const EnvRegs& e, float* host = nullptr) {
     const int64_t ld = st.ld;
     float* __restrict__ obs = st.obs;
+    if (host) mirror_static_rows(host, ld, i, e);
 #pragma unroll
     for (int j = 0; j < NJ; ++j) obs[(DEXSIM_ROW_JP + j) * ld + i] = e.jp[j];
 #pragma unroll
@@ -81,7 +90,8 @@ __device__ __forceinline__ void store_env_full(const DexsimState& st, int64_t i,
 // Step write-back: joints always; object rows, contact rows and the mask only when they changed
 // (x, y never move after the first step; z rests at 0 for most of a long episode; contact flags
 // flip rarely).  The sector was read by this thread just before, so partial writes merge in L2.
-__device__ __forceinline__ void store_env_step(const DexsimState& st, int64_t i, const EnvRegs& e, const Hot& h) {
+__device__ __forceinline__ void store_env_step(const DexsimState& st, int64_t i, const EnvRegs& e, const Hot& h,
+                                               float* host = nullptr) {
     const int64_t ld = st.ld;
     float* __restrict__ obs = st.obs;
 #pragma unroll
@@ -93,8 +103,12 @@ __device__ __forceinline__ void store_env_step(const DexsimState& st, int64_t i,
         if (__double_as_longlong(e.op[k]) != __double_as_longlong(h.op_old[k])) {
             st.op64[k * ld + i] = e.op[k];
             obs[(DEXSIM_ROW_OP + k) * ld + i] = (float)e.op[k];
+            if (host && k < 2) host[(DEXSIM_ROW_OP + k) * ld + i] = (float)e.op[k];
         }
-        if (__float_as_uint(e.ov[k]) != __float_as_uint(h.ov_old[k])) obs[(DEXSIM_ROW_OV + k) * ld + i] = e.ov[k];
+        if (__float_as_uint(e.ov[k]) != __float_as_uint(h.ov_old[k])) {
+            obs[(DEXSIM_ROW_OV + k) * ld + i] = e.ov[k];
+            if (host && k < 2) host[(DEXSIM_ROW_OV + k) * ld + i] = e.ov[k];
+        }
     }
     const unsigned flip = e.cmask ^ h.cmask_old;
     if (flip) {
@@ -368,9 +382,9 @@ step_kernel(const DexsimState st, const DexsimParams p, const DexsimGroup* __res
                              cnt, rs, size, mass, friction, nullptr, /*classify=*/tracking);
             st.episode[i] = episode;
             st.size[i] = size; st.mass[i] = mass; st.friction[i] = friction;
-            store_env_full(st, i, e);
+            store_env_full(st, i, e, io.host_static_rows);
         } else {
-            store_env_step(st, i, e, h);
+            store_env_step(st, i, e, h, io.host_static_rows);
         }
         if (tracking) {
             st.ep_return[i] = ep_return;
@@ -945,7 +959,7 @@ static int launch_step(const DexsimState* st, const DexsimParams* p, const Dexsi
     const bool fused_obs = !io->obs_noise && io->sigma_obs != 0.0f;
     if ((io->obs_noise != nullptr || fused_obs) != (io->noisy_obs != nullptr)) return DEXSIM_E_NULL;
     if (pack_out && st->n != 1) return DEXSIM_E_SIZE;
-    const bool extras = io->dyn_noise || io->obs_noise || io->reward_comps || io->reward64 || io->finished ||
+    const bool extras = io->dyn_noise || io->obs_noise || io->reward_comps || io->reward64 || io->finished || io->host_static_rows ||
                         (p && p->auto_reset) || st->ep_return != nullptr || fused_dyn || fused_obs || pack_out != nullptr;
     const bool group_sigma = (fused_dyn && io->sigma_dyn < 0.0f) || (fused_obs && io->sigma_obs < 0.0f);
     rc = check_params(p, p && (p->auto_reset || group_sigma), groups, st->ep_return != nullptr && p && p->auto_reset);
@@ -1209,9 +1223,12 @@ struct HostPipe {
     cudaStream_t streams[HOST_STREAMS];
     cudaStream_t small;                // per-env vectors (reward, flags) of the WHOLE batch: a few large copies instead of
                                        // one small copy per vector per chunk
+    cudaStream_t upload;               // every chunk's action upload, back to back: the uploads run ahead of the downloads
+                                       // instead of queueing behind an earlier chunk's download in the same stream
     cudaEvent_t fork_ev;
-    cudaEvent_t join_ev[HOST_STREAMS + 1];
+    cudaEvent_t join_ev[HOST_STREAMS + 2];
     cudaEvent_t kdone[HOST_MAX_CHUNKS];
+    cudaEvent_t up_ev[HOST_MAX_CHUNKS];
 };
 HostPipe g_pipes[64];
 std::mutex g_pipes_mutex;      // first use from several host threads at once
@@ -1231,12 +1248,16 @@ int get_pipe(HostPipe** out) {
         }
         err = cudaStreamCreateWithFlags(&hp.small, cudaStreamNonBlocking);
         if (err != cudaSuccess) return -(int)err;
-        for (int k = 0; k < HOST_STREAMS + 1; ++k) {
+        err = cudaStreamCreateWithFlags(&hp.upload, cudaStreamNonBlocking);
+        if (err != cudaSuccess) return -(int)err;
+        for (int k = 0; k < HOST_STREAMS + 2; ++k) {
             err = cudaEventCreateWithFlags(&hp.join_ev[k], cudaEventDisableTiming);
             if (err != cudaSuccess) return -(int)err;
         }
         for (int k = 0; k < HOST_MAX_CHUNKS; ++k) {
             err = cudaEventCreateWithFlags(&hp.kdone[k], cudaEventDisableTiming);
+            if (err != cudaSuccess) return -(int)err;
+            err = cudaEventCreateWithFlags(&hp.up_ev[k], cudaEventDisableTiming);
             if (err != cudaSuccess) return -(int)err;
         }
         err = cudaEventCreateWithFlags(&hp.fork_ev, cudaEventDisableTiming);
@@ -1247,6 +1268,17 @@ int get_pipe(HostPipe** out) {
     return 0;
 }
 }  // namespace
+
+// DEXSIM_HOST_UPLOAD_STREAM=1: all action uploads of a host step on one dedicated stream, running ahead of the downloads
+// (experiment; default 0 = each chunk uploads on its own stream, behind the previous download of that stream).
+static bool upload_stream_choice() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("DEXSIM_HOST_UPLOAD_STREAM");
+        v = (e && atoi(e)) ? 1 : 0;
+    }
+    return v == 1;
+}
 
 int dexsim_expand_contact_rows(float* h_obs, const uint8_t* h_contact_mask, int64_t n, int64_t ld) {
     if (!h_obs || !h_contact_mask) return DEXSIM_E_NULL;
@@ -1290,12 +1322,26 @@ int dexsim_step_host(const DexsimState* st, const DexsimParams* p, const DexsimG
             err = cudaStreamWaitEvent(hp->streams[k], hp->fork_ev, 0);
             if (err != cudaSuccess) return -(int)err;
         }
+        err = cudaStreamWaitEvent(hp->upload, hp->fork_ev, 0);
+        if (err != cudaSuccess) return -(int)err;
     }
     // observation rows that travel: all 45, or without the constant quaternion rows 33-36 (SKIP_QUAT), and without the
     // five 0/1 contact rows 40-44 when the 1-byte contact mask is sent instead (PACKED_CONTACTS)
     const int rows_hi = (flags & DEXSIM_HOST_PACKED_CONTACTS) ? DEXSIM_ROW_CONTACT : DEXSIM_OBS;
     const bool expand_on_host = (flags & DEXSIM_HOST_EXPAND_CONTACTS) && (flags & DEXSIM_HOST_PACKED_CONTACTS) &&
                                 !(flags & DEXSIM_HOST_ASYNC) && h_obs != nullptr;
+    // Rows 30, 31, 37, 38 (object x, y and their velocities) only change when an episode is reset.  When h_obs is mapped
+    // page-locked memory the step kernel mirrors every such change straight into it (DexsimStepIO.host_static_rows), and a
+    // caller whose buffer is already current (DEXSIM_HOST_STATIC_ROWS) does not download those rows at all.
+    float* mirror = nullptr;
+    if (h_obs && !io->host_static_rows) {
+        cudaPointerAttributes attr;
+        if (cudaPointerGetAttributes(&attr, h_obs) == cudaSuccess && attr.type == cudaMemoryTypeHost && attr.devicePointer)
+            mirror = static_cast<float*>(attr.devicePointer);
+        else
+            (void)cudaGetLastError();                 // pageable memory: not an error, just no mirror
+    }
+    const bool skip_static = (flags & DEXSIM_HOST_STATIC_ROWS) && mirror != nullptr && (flags & DEXSIM_HOST_SKIP_QUAT);
     // Whatever happens while enqueueing, the caller's stream is joined with the internal ones before returning,
     // so that no copy is still in flight on a stream the caller cannot see.
     auto copy_vectors = [&](cudaStream_t s, int64_t lo, int64_t m) -> int {
@@ -1335,10 +1381,17 @@ int dexsim_step_host(const DexsimState* st, const DexsimParams* p, const DexsimG
         if (sio.reward64) sio.reward64 += lo;
         if (sio.finished) sio.finished += lo;
         if (sio.sched) sio.sched = (2 * (c + 1) + 1 < DEXSIM_SCHED_WORDS) ? io->sched + 2 * (c + 1) : nullptr;   // chunks run concurrently
+        if (mirror) sio.host_static_rows = mirror + lo;
         cudaError_t err;
-        if (aos) err = cudaMemcpyAsync(d_action, h_action + lo * NJ, (size_t)m * NJ * sizeof(float), cudaMemcpyHostToDevice, s);
-        else err = cudaMemcpy2DAsync(d_action, (size_t)ld * 4, h_action + lo, (size_t)ld * 4, (size_t)m * 4, NJ, cudaMemcpyHostToDevice, s);
+        cudaStream_t up = (nchunks > 1 && upload_stream_choice()) ? hp->upload : s;
+        if (aos) err = cudaMemcpyAsync(d_action, h_action + lo * NJ, (size_t)m * NJ * sizeof(float), cudaMemcpyHostToDevice, up);
+        else err = cudaMemcpy2DAsync(d_action, (size_t)ld * 4, h_action + lo, (size_t)ld * 4, (size_t)m * 4, NJ, cudaMemcpyHostToDevice, up);
         if (err != cudaSuccess) return -(int)err;
+        if (up != s) {                                   // the chunk's stream picks up where the upload stream got to
+            err = cudaEventRecord(hp->up_ev[c], up);
+            if (err == cudaSuccess) err = cudaStreamWaitEvent(s, hp->up_ev[c], 0);
+            if (err != cudaSuccess) return -(int)err;
+        }
         rc = launch_step(&sub, &sp, groups, group_of_env ? group_of_env + lo : nullptr, &sio, s);
         if (rc) return rc;
         if (nchunks > 1) {
@@ -1350,13 +1403,17 @@ int dexsim_step_host(const DexsimState* st, const DexsimParams* p, const DexsimG
             if (err != cudaSuccess) return -(int)err;
         }
         if (h_obs) {
-            if (flags & DEXSIM_HOST_SKIP_QUAT) {     // rows 33-36 are the constant (1,0,0,0): caller keeps them
-                err = cudaMemcpy2DAsync(h_obs + lo, (size_t)ld * 4, st->obs + lo, (size_t)ld * 4, (size_t)m * 4,
-                                        DEXSIM_ROW_QUAT, cudaMemcpyDeviceToHost, s);
-                if (err != cudaSuccess) return -(int)err;
-                err = cudaMemcpy2DAsync(h_obs + (size_t)DEXSIM_ROW_OV * ld + lo, (size_t)ld * 4,
-                                        st->obs + (size_t)DEXSIM_ROW_OV * ld + lo, (size_t)ld * 4, (size_t)m * 4,
-                                        rows_hi - DEXSIM_ROW_OV, cudaMemcpyDeviceToHost, s);
+            auto rows = [&](int r0, int r1) -> cudaError_t {       // observation rows [r0, r1) of this chunk
+                return cudaMemcpy2DAsync(h_obs + (size_t)r0 * ld + lo, (size_t)ld * 4, st->obs + (size_t)r0 * ld + lo, (size_t)ld * 4,
+                                         (size_t)m * 4, r1 - r0, cudaMemcpyDeviceToHost, s);
+            };
+            if (skip_static) {                       // joints, z, vz (+ contacts): x, y, vx, vy are mirrored by the kernel
+                err = rows(0, DEXSIM_ROW_OP);
+                if (err == cudaSuccess) err = rows(DEXSIM_ROW_OP + 2, DEXSIM_ROW_QUAT);
+                if (err == cudaSuccess) err = rows(DEXSIM_ROW_OV + 2, rows_hi);
+            } else if (flags & DEXSIM_HOST_SKIP_QUAT) {     // rows 33-36 are the constant (1,0,0,0): caller keeps them
+                err = rows(0, DEXSIM_ROW_QUAT);
+                if (err == cudaSuccess) err = rows(DEXSIM_ROW_OV, rows_hi);
             } else {
                 err = cudaMemcpy2DAsync(h_obs + lo, (size_t)ld * 4, st->obs + lo, (size_t)ld * 4, (size_t)m * 4, rows_hi,
                                         cudaMemcpyDeviceToHost, s);
@@ -1391,6 +1448,8 @@ int dexsim_step_host(const DexsimState* st, const DexsimParams* p, const DexsimG
         {
             cudaError_t err = cudaEventRecord(hp->join_ev[HOST_STREAMS], hp->small);
             if (err == cudaSuccess) err = cudaStreamWaitEvent(user, hp->join_ev[HOST_STREAMS], 0);
+            if (err == cudaSuccess) err = cudaEventRecord(hp->join_ev[HOST_STREAMS + 1], hp->upload);
+            if (err == cudaSuccess) err = cudaStreamWaitEvent(user, hp->join_ev[HOST_STREAMS + 1], 0);
             if (err != cudaSuccess && rc == 0) rc = -(int)err;
         }
         enqueue_lock.unlock();

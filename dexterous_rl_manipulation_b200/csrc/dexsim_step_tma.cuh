@@ -137,7 +137,8 @@ __device__ __forceinline__ uint32_t tile_cols(int64_t n, int64_t base) {
 __device__ __forceinline__ void warp_reset_draws(const unsigned rm, const bool do_reset, const int lane, const int wcol0,
                                                  const int64_t base, unsigned char* sp, const DexsimState& st,
                                                  const DexsimParams& p, const DexsimGroup* __restrict__ groups,
-                                                 const uint32_t episode, const int g, const bool any_ranged) {
+                                                 const uint32_t episode, const int g, const bool any_ranged,
+                                                 float* host_rows) {
     float* s_jpjv = reinterpret_cast<float*>(sp + OFF_JPJV);
     double* s_op = reinterpret_cast<double*>(sp + OFF_OP64);
     double* s_thr = reinterpret_cast<double*>(sp + OFF_THR);
@@ -194,6 +195,10 @@ __device__ __forceinline__ void warp_reset_draws(const unsigned rm, const bool d
                 st.op64[k * ld + i] = np3[k];
                 obs[(DEXSIM_ROW_OP + k) * ld + i] = (float)np3[k];
                 obs[(DEXSIM_ROW_OV + k) * ld + i] = 0.0f;
+                if (host_rows && k < 2) {
+                    host_rows[(DEXSIM_ROW_OP + k) * ld + i] = (float)np3[k];
+                    host_rows[(DEXSIM_ROW_OV + k) * ld + i] = 0.0f;
+                }
             }
             s_sc[c] = 0;
             if (!any_ranged) {                                        // fixed curricula: the group's constants
@@ -550,8 +555,14 @@ step_tma_kernel(const DexsimState st, const DexsimParams p, const DexsimGroup* _
                         if (__double_as_longlong(e.op[c]) != __double_as_longlong(op_old[c])) {
                             st.op64[c * ld + i] = e.op[c];
                             obs[(DEXSIM_ROW_OP + c) * ld + i] = (float)e.op[c];
+                            // x, y only move when an episode is reset: mirrored into the caller's host observation so that
+                            // the end-to-end path need not download those rows every step (DexsimStepIO.host_static_rows)
+                            if (c < 2 && io.host_static_rows) io.host_static_rows[(DEXSIM_ROW_OP + c) * ld + i] = (float)e.op[c];
                         }
-                        if (__float_as_uint(e.ov[c]) != __float_as_uint(ov_old[c])) obs[(DEXSIM_ROW_OV + c) * ld + i] = e.ov[c];
+                        if (__float_as_uint(e.ov[c]) != __float_as_uint(ov_old[c])) {
+                            obs[(DEXSIM_ROW_OV + c) * ld + i] = e.ov[c];
+                            if (c < 2 && io.host_static_rows) io.host_static_rows[(DEXSIM_ROW_OV + c) * ld + i] = e.ov[c];
+                        }
                     }
                     const unsigned flip = e.cmask ^ cmask_old;
                     if (flip) {
@@ -572,7 +583,7 @@ step_tma_kernel(const DexsimState st, const DexsimParams p, const DexsimGroup* _
                     bool ranged = false;
                     if (do_reset) ranged = (groups[g].size_ranged | groups[g].mass_ranged | groups[g].fric_ranged) != 0;
                     const bool any_ranged = __any_sync(0xffffffffu, ranged);
-                    warp_reset_draws(rm, do_reset, lane, wcol0, base, sp, st, p, groups, episode, g, any_ranged);
+                    warp_reset_draws(rm, do_reset, lane, wcol0, base, sp, st, p, groups, episode, g, any_ranged, io.host_static_rows);
                     if (EXTRA) {
                         __syncwarp();                   // the new state of MY env was written by other lanes
                         if (do_reset) {                 // rebuild the registers the noisy observation is made from

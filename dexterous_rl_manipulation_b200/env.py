@@ -225,6 +225,8 @@ class BatchedManipulationEnv:
         self._io_has_noise = False
         self._alternate_tiles = _L.STEP_REVERSE_TILES    # 0 switches the alternation off (experiments)
         self.host_expand_contacts = True                 # step_host(): contact columns travel packed, expanded on the host
+        self.host_static_rows = True                     # step_host(): reset-only rows mirrored by the kernel, not downloaded
+        self._h_primed_slot = None                       # result slot whose pinned observation is current (see step_host)
         self._state_ref, self._params_ref, self._io_ref = C.byref(self._state), C.byref(self._params), C.byref(self._io)
         self._goe_ptr = self._ptr(self._goe)
         self._step_out = None
@@ -415,6 +417,7 @@ class BatchedManipulationEnv:
 
     def reset(self, seed=None, options=None):
         """envs/manipulation_env.py:124-182.  ``options={"mask": BoolTensor[num_envs]}`` resets a subset."""
+        self._h_primed_slot = None
         with torch.cuda.device(self.device):
             self._sync_groups()
             mask = None
@@ -484,6 +487,7 @@ class BatchedManipulationEnv:
         float64, pos [n,3] float32 or None = keep each env's current position cast to float32
         (envs/manipulation_env.py:160-161).  This is the parity entry: identical initial states."""
         n, ld, dev = self.num_envs, self.ld, self.device
+        self._h_primed_slot = None
         with torch.cuda.device(dev):
             self._sync_groups()
 
@@ -563,6 +567,7 @@ class BatchedManipulationEnv:
             raise RuntimeError("call reset() before step()")
         if self._groups_dirty:
             self._sync_groups()
+        self._h_primed_slot = None
         plain = (dyn_noise is None and obs_noise is None and not self._noisy_env and not self.single
                  and isinstance(action, torch.Tensor) and action.is_cuda and action.dtype is torch.float32
                  and action.is_contiguous() and action.numel() == self._n15 and not (action.data_ptr() & 15))
@@ -700,6 +705,7 @@ class BatchedManipulationEnv:
         def replay():
             if self._groups_dirty:
                 self._sync_groups()
+            self._h_primed_slot = None
             graph.replay()
             return out
 
@@ -709,6 +715,7 @@ class BatchedManipulationEnv:
     def _step_soa(self, action_soa):
         """Step with actions already in the device layout [15, ld] (tests / internal callers)."""
         io = self._io
+        self._h_primed_slot = None
         io.action, io.action_layout = action_soa.data_ptr(), 0
         io.dyn_noise = io.obs_noise = io.noisy_obs = None
         io.sigma_dyn = io.sigma_obs = 0.0
@@ -844,7 +851,7 @@ class BatchedManipulationEnv:
         ``(obs [num_envs,45], reward, terminated, truncated, info)`` living in pinned buffers that
         the next call with the same ``slot`` overwrites.  One C-ABI call (dexsim_step_host): H2D copy of the actions,
         the step kernel, D2H copies of observation / reward / flags, stream synchronize.  Large batches are
-        split into ``chunks`` ranges (default: one per 65,536 envs, at most 16) so that the upload of one
+        split into ``chunks`` ranges (default: one per 65,536 envs, at most 8) so that the upload of one
         range overlaps the kernel and the download of the others.
 
         ``sync=False``: return as soon as everything is enqueued; call ``host_sync()`` (or synchronize the current
@@ -866,6 +873,11 @@ class BatchedManipulationEnv:
             # thread expands them into the pinned observation while the other rows are still being downloaded --
             # the returned observation is complete, 20 of 171 bytes per env never cross PCIe
             flags |= _L.HOST_PACKED_CONTACTS | _L.HOST_EXPAND_CONTACTS
+        if sync and self.host_static_rows and self._h_primed_slot == slot:
+            # object x, y and their velocities only change when an episode is reset; the step kernel mirrors every such
+            # change straight into this slot's pinned observation, which has been current since the previous call:
+            # those four rows are not downloaded (another 16 bytes per env)
+            flags |= _L.HOST_STATIC_ROWS
         with torch.cuda.device(self.device):
             self._sync_groups()
             io = self._io
@@ -876,7 +888,9 @@ class BatchedManipulationEnv:
                 C.byref(self._state), C.byref(self._params), self._ptr(self._groups_dev), self._ptr(self._goe),
                 C.byref(io), a.data_ptr(), b["obs"].data_ptr(), b["reward"].data_ptr(), b["term"].data_ptr(),
                 b["trunc"].data_ptr(), b["nc"].data_ptr(), b["cmask"].data_ptr(),
-                int(chunks) if chunks is not None else max(1, min(16, n // 65536)), flags, self._stream()), "dexsim_step_host")
+                int(chunks) if chunks is not None else max(1, min(8, n // 65536)), flags, self._stream()), "dexsim_step_host")
+        # this slot's observation is current now; any other entry point that touches the state resets the marker
+        self._h_primed_slot = slot if sync else None
         if not sync:
             # the upload may still be reading the action buffer: keep it alive until this slot is used again
             if getattr(self, "_host_keepalive", None) is None:
@@ -949,6 +963,7 @@ class BatchedManipulationEnv:
         (run_episode / evaluate_episode semantics); otherwise finished episodes auto-reset."""
         if not self._did_reset:
             raise RuntimeError("call reset() before rollout()")
+        self._h_primed_slot = None
         if self._ep_return is None:
             raise RuntimeError("rollout() needs track_episodes=True (per-env history summaries)")
         kind = {"external": _L.POLICY_EXTERNAL, "random": _L.POLICY_RANDOM, "heuristic": _L.POLICY_HEURISTIC,
@@ -1031,6 +1046,7 @@ class BatchedManipulationEnv:
         return sd
 
     def load_state_dict(self, sd):
+        self._h_primed_slot = None
         host = sd.get("_host")
         for k, v in sd.items():
             if k == "_host":

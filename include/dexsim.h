@@ -178,6 +178,12 @@ typedef struct DexsimStepIO {
      * leaves the words zero again; one buffer per step that can be in flight at a time (calls on the same stream may
      * share it).  dexsim_step uses words 0-1, dexsim_step_host words 2c, 2c+1 for its chunk c. */
     uint32_t*    sched;
+    /* Host mirror of the observation rows that only change when an episode is reset: object x, y (rows 30, 31) and
+     * their velocities (rows 37, 38).  When set -- a pointer to the caller's HOST [45, ld] observation buffer in mapped
+     * page-locked memory (any cudaHostAlloc / pinned allocation under unified addressing) -- every change of those four
+     * entries is ALSO written there by the step kernel (a handful of 4-byte stores per reset), so a caller that downloads
+     * the observation every step need not download these rows (dexsim_step_host: DEXSIM_HOST_STATIC_ROWS).  NULL = off. */
+    float*       host_static_rows;
 } DexsimStepIO;
 #define DEXSIM_SCHED_WORDS 64
 
@@ -338,6 +344,11 @@ int dexsim_classify_summary(const DexsimEpisodeSummary* s, const uint8_t* counts
                                         * the device and the 1-byte contact mask (bit f = finger f, DexsimState.cmask) is
                                         * copied to h_contact_mask instead (-19 bytes of 171 per env); the caller expands
                                         * the rows on the host if and when it needs them */
+#define DEXSIM_HOST_STATIC_ROWS 16     /* h_obs is mapped page-locked memory whose rows 30, 31, 37, 38 are already current (a
+                                        * previous dexsim_step_host call on the same buffer copied them and no other entry point has
+                                        * touched the state since): do not download them -- the step kernel mirrors every change of
+                                        * those entries straight into h_obs (DexsimStepIO.host_static_rows, set by this call).
+                                        * Without the flag the rows are downloaded like the others (and the buffer becomes current). */
 #define DEXSIM_HOST_EXPAND_CONTACTS 8  /* with PACKED_CONTACTS (and not ASYNC): the calling thread writes obs rows 40-44 of h_obs
                                         * from the masks while the other rows are still being downloaded, so h_obs is complete
                                         * on return although the five rows never crossed PCIe */

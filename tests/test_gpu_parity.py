@@ -710,6 +710,21 @@ def test_step_host_matches_device_step(dx, n, chunks, track):
     assert torch.equal(a_env._episode, b_env._episode)
     if track:
         assert torch.equal(a_env.counters, b_env.counters) and int(a_env.counters[:, 0].sum()) > 0
+    # The default transport does not download the rows that only change at a reset (object x, y and their velocities: the
+    # step kernel mirrors them into the pinned observation) once the buffer is current; every other entry point that
+    # touches the state must make the next call download them again: an explicit reset, a device-side step, a rollout.
+    a_env.reset(seed=77); b_env.reset(seed=77)
+    for t in range(30):
+        act = rng.uniform(-1.2, 1.2, (n, 15)).astype(np.float32)
+        if t in (7, 19):                              # device-side step in between (changes the state behind the host buffer)
+            a_env.step(torch.from_numpy(act).cuda()); b_env.step(torch.from_numpy(act).cuda())
+            act = rng.uniform(-1.2, 1.2, (n, 15)).astype(np.float32)
+        if t == 13:
+            a_env.reset(seed=5); b_env.reset(seed=5)
+        o1, r1, te1, tr1, i1 = a_env.step(torch.from_numpy(act).cuda())
+        o2, r2, te2, tr2, i2 = b_env.step_host(torch.from_numpy(act).pin_memory(), chunks=chunks)
+        assert torch.equal(o1.cpu(), o2) and torch.equal(r1.cpu(), r2), t
+        assert b_env._h_primed_slot == 0
     # asynchronous, double-buffered and with the contacts packed into their 1-byte mask: same results
     pins = [torch.empty(n, 15).pin_memory() for _ in range(2)]
     pending = None
@@ -1363,8 +1378,9 @@ def test_bench_b200_arm_prints_one_contract_line():
     assert r["sustained_steps"] >= 400 and 0.0 < r["frac_sustained"] < 2.0 and "traffic_steady_state" in r
     assert abs(d["value"] - 262144 * 20 / (d["ms_per_step"] * 20e-3)) / d["value"] < 1e-6
     e = d["e2e"]
-    # 36 observation rows + reward + 3 flag bytes + the contact mask cross PCIe; the 5 contact rows are expanded on the host
-    assert e["value"] > 0 and e["h2d_bytes_per_step"] == 262144 * 60 and e["d2h_bytes_per_step"] == 262144 * (36 * 4 + 8)
+    # 32 observation rows + reward + 3 flag bytes + the contact mask cross PCIe every step; the 5 contact rows are expanded on
+    # the host, object x, y and their velocities are mirrored by the step kernel when they change
+    assert e["value"] > 0 and e["h2d_bytes_per_step"] == 262144 * 60 and e["d2h_bytes_per_step"] == 262144 * (32 * 4 + 8)
     assert e["all_rows_d2h_bytes_per_step"] == 262144 * (41 * 4 + 7) and e["copy_ceiling"]["value"] > e["value"] * 0.8
     assert e["value"] < d["value"]                       # host buffers cross PCIe: never faster than the device-resident loop
 

@@ -14,18 +14,21 @@ import os
 import time
 
 
-def measure(num_envs, steps=20, warmup=3, device=None, packed_contacts=False, barrier=None):
-    """Seconds per step of the copies alone on this rank (caller takes the max over ranks)."""
+def measure(num_envs, steps=20, warmup=3, device=None, packed_contacts=False, barrier=None, rows=None, extra_bytes_per_env=None):
+    """Seconds per step of the copies alone on this rank (caller takes the max over ranks).
+    ``rows`` observation rows of 4 bytes + ``extra_bytes_per_env`` (reward, flags, masks) come down per env; the defaults are
+    41 + 7 (every row but the constant quaternion) or 36 + 8 with ``packed_contacts``."""
     import torch
     dev = device if device is not None else torch.device("cuda", torch.cuda.current_device())
     E = int(num_envs)
     ld = (E + 31) // 32 * 32
-    rows = 36 if packed_contacts else 41
+    rows = rows if rows is not None else (36 if packed_contacts else 41)
     h_act = torch.empty(E, 15).pin_memory()
     d_act = torch.empty(E, 15, device=dev)
     d_out = torch.empty(rows, ld, device=dev)
     h_out = torch.empty(rows, ld).pin_memory()
-    d_small = torch.empty(E * (4 + 3 + (1 if packed_contacts else 0)), dtype=torch.uint8, device=dev)
+    small = extra_bytes_per_env if extra_bytes_per_env is not None else (4 + 3 + (1 if packed_contacts else 0))
+    d_small = torch.empty(E * small, dtype=torch.uint8, device=dev)
     h_small = torch.empty_like(d_small, device="cpu").pin_memory()
     up, down = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
 
