@@ -687,7 +687,7 @@ def test_maximum_size_batch(dx):
         _lib.set_step_impl("auto")
 
 
-@pytest.mark.parametrize("n,chunks,track", [(5000, 3, True), (4096, 1, False), (70_000, 8, True)])
+@pytest.mark.parametrize("n,chunks,track", [(5000, 3, True), (4096, 1, False), (70_000, 8, True), (100, 1, True)])
 def test_step_host_matches_device_step(dx, n, chunks, track):
     """The end-to-end entry (host buffers, chunked copy/compute overlap) equals the device-tensor API."""
     CC = dx.CurriculumConfig
