@@ -1409,8 +1409,16 @@ int dexsim_step_host(const DexsimState* st, const DexsimParams* p, const DexsimG
             };
             if (skip_static) {                       // joints, z, vz (+ contacts): x, y, vx, vy are mirrored by the kernel
                 err = rows(0, DEXSIM_ROW_OP);
-                if (err == cudaSuccess) err = rows(DEXSIM_ROW_OP + 2, DEXSIM_ROW_QUAT);
-                if (err == cudaSuccess) err = rows(DEXSIM_ROW_OV + 2, rows_hi);
+                if (err == cudaSuccess && rows_hi == DEXSIM_ROW_CONTACT) {
+                    // object z (row 32) and its velocity (row 39) in ONE pitched copy: both sit 7 rows apart on either side
+                    // (every copy costs the DMA engine a fixed hand-over time, so fewer copies per chunk matter)
+                    constexpr int zr = DEXSIM_ROW_OP + 2, gap = (DEXSIM_ROW_OV + 2) - (DEXSIM_ROW_OP + 2);
+                    err = cudaMemcpy2DAsync(h_obs + (size_t)zr * ld + lo, (size_t)gap * ld * 4, st->obs + (size_t)zr * ld + lo,
+                                            (size_t)gap * ld * 4, (size_t)m * 4, 2, cudaMemcpyDeviceToHost, s);
+                } else {
+                    if (err == cudaSuccess) err = rows(DEXSIM_ROW_OP + 2, DEXSIM_ROW_QUAT);
+                    if (err == cudaSuccess) err = rows(DEXSIM_ROW_OV + 2, rows_hi);
+                }
             } else if (flags & DEXSIM_HOST_SKIP_QUAT) {     // rows 33-36 are the constant (1,0,0,0): caller keeps them
                 err = rows(0, DEXSIM_ROW_QUAT);
                 if (err == cudaSuccess) err = rows(DEXSIM_ROW_OV, rows_hi);
