@@ -543,7 +543,7 @@ def run_b200(args):
                    "contact rows are written by the calling thread from the masks while the download is still running; object x, y and "
                    "their velocities only change at a reset and are mirrored into the pinned buffer by the step kernel); 8 chunks, "
                    "H2D / kernel / D2H overlapped",
-           "api": "BatchedManipulationEnv.step_host -> dexsim_step_host", "gpu_launches": args.e2e_steps * max(1, min(8, E // 65536)),
+           "api": "BatchedManipulationEnv.step_host -> dexsim_step_host", "gpu_launches": args.e2e_steps * max(1, min(8, E // 8192)),
            "numa_bound": bool(numa_bound),
            "copy_ceiling": ceiling,
            "frac_of_copy_ceiling": (e2e_value / ceiling["value"]) if ceiling and ceiling.get("value") else None,

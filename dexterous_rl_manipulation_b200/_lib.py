@@ -25,8 +25,10 @@ EPISODE_RECORD_DTYPE = _np.dtype([("env_gid", "u4"), ("episode", "u4"), ("steps"
                                   ("final_contacts", "u1"), ("label_metrics", "u1"), ("label_taxonomy", "u1"),
                                   ("episode_reward", "f8"), ("t_end", "u4"), ("var_tie", "u4")])
 HOST_SKIP_QUAT, HOST_ASYNC, HOST_PACKED_CONTACTS, HOST_EXPAND_CONTACTS, HOST_STATIC_ROWS = 1, 2, 4, 8, 16
+HOST_ZERO_COPY = 32
 SCHED_WORDS = 64
 STEP_REVERSE_TILES = 1
+STEP_HOST_ALL_ROWS = 2
 ROLLOUT_NO_DYN_NOISE = 1
 
 # value strings of FailureType (evaluation/metrics.py:15-22) / FailureMode
@@ -67,7 +69,8 @@ class DexsimStepIO(C.Structure):
                 ("reward", C.c_void_p), ("reward_comps", C.c_void_p), ("terminated", C.c_void_p),
                 ("truncated", C.c_void_p), ("num_contacts", C.c_void_p), ("finished", C.c_void_p),
                 ("counters", C.c_void_p), ("ret_sums", C.c_void_p), ("reward64", C.c_void_p),
-                ("sigma_dyn", C.c_float), ("sigma_obs", C.c_float), ("sched", C.c_void_p), ("host_static_rows", C.c_void_p)]
+                ("sigma_dyn", C.c_float), ("sigma_obs", C.c_float), ("sched", C.c_void_p), ("host_static_rows", C.c_void_p),
+                ("host_cmask", C.c_void_p)]
 
 
 class DexsimEpisodeRecord(C.Structure):
@@ -100,6 +103,7 @@ EXPORTS = (
     "dexsim_reset_philox", "dexsim_step", "dexsim_rollout", "dexsim_fill_policy_actions",
     "dexsim_fill_normal", "dexsim_classify_summary", "dexsim_step_host", "dexsim_pack_env", "dexsim_pack_env_tagged", "dexsim_step_single",
     "dexsim_expand_contact_rows",
+    "dexsim_host_zero_copy_steps",
 )
 
 _lib = None
@@ -148,9 +152,11 @@ def lib():
     L.dexsim_step_host.argtypes = [C.POINTER(DexsimState), C.POINTER(DexsimParams), vp, vp, C.POINTER(DexsimStepIO),
                                    vp, vp, vp, vp, vp, vp, vp, i32, i32, vp]
     L.dexsim_expand_contact_rows.argtypes = [vp, vp, i64, i64]
+    L.dexsim_host_zero_copy_steps.argtypes = []
+    L.dexsim_host_zero_copy_steps.restype = C.c_int64
     for name in EXPORTS:
         fn = getattr(L, name)          # raises AttributeError if a declared symbol is not exported
-        if name not in ("dexsim_error_string",):
+        if name not in ("dexsim_error_string", "dexsim_host_zero_copy_steps"):
             fn.restype = C.c_int
     if L.dexsim_version() != ABI_VERSION:
         raise ImportError(f"libdexsim_b200.so ABI {L.dexsim_version()} != binding ABI {ABI_VERSION}")

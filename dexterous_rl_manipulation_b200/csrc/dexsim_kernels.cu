@@ -12,6 +12,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <atomic>
 #include <mutex>
 
 #include "dexsim_core.cuh"
@@ -913,12 +914,14 @@ static int launch_step_tma(const DexsimState* st, const DexsimParams* p, const D
                            const DexsimStepIO* io, cudaStream_t s, int track, bool extra, int sm_count) {
     // Tensor maps are pure functions of (base pointers, n, ld): a stepping loop re-encodes nothing.  One cached set
     // per host thread; the SoA action map is keyed by the action pointer too (AoS actions use 1-D bulk copies).
-    struct MapCache { const void* obs; const void* op64; const void* act; int64_t n, ld; bool valid; StepMaps maps; };
-    static thread_local MapCache cache = {nullptr, nullptr, nullptr, 0, 0, false, {}};
+    struct MapCache { const void* obs; const void* op64; const void* act; const void* host; int64_t n, ld; bool valid; StepMaps maps; };
+    static thread_local MapCache cache = {nullptr, nullptr, nullptr, nullptr, 0, 0, false, {}};
     const bool aos = io->action_layout == 1;
     const void* act_key = aos ? nullptr : (const void*)io->action;
-    if (!(cache.valid && cache.obs == st->obs && cache.op64 == st->op64 && cache.act == act_key && cache.n == st->n &&
-          cache.ld == st->ld)) {
+    // zero-copy host step: one more map, over the caller's mapped host observation (device alias of the host pointer)
+    const void* host_key = (io->flags & DEXSIM_STEP_HOST_ALL_ROWS) ? (const void*)io->host_static_rows : nullptr;
+    if (!(cache.valid && cache.obs == st->obs && cache.op64 == st->op64 && cache.act == act_key && cache.host == host_key &&
+          cache.n == st->n && cache.ld == st->ld)) {
         cache.valid = false;
         memset(&cache.maps, 0, sizeof(cache.maps));
         bool ok = make_map_2d(&cache.maps.obs_jpjv, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, st->obs, st->n, st->ld, DEXSIM_OBS, 30) &&
@@ -927,8 +930,11 @@ static int launch_step_tma(const DexsimState* st, const DexsimParams* p, const D
         if (ok && !aos)
             ok = make_map_2d(&cache.maps.act_soa, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(io->action), st->n,
                              st->ld, NJ, NJ);
+        if (ok && host_key)
+            ok = make_map_2d(&cache.maps.host_jpjv, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<void*>(host_key), st->n, st->ld,
+                             DEXSIM_OBS, 30);
         if (!ok) return 1;                           // caller falls back to the register-resident kernel
-        cache.obs = st->obs; cache.op64 = st->op64; cache.act = act_key; cache.n = st->n; cache.ld = st->ld;
+        cache.obs = st->obs; cache.op64 = st->op64; cache.act = act_key; cache.host = host_key; cache.n = st->n; cache.ld = st->ld;
         cache.valid = true;
     }
     const StepMaps& maps = cache.maps;
@@ -988,6 +994,7 @@ static int launch_step(const DexsimState* st, const DexsimParams* p, const Dexsi
         if (rc <= 0) return rc;                      // launched (0) or CUDA error (< 0); 1 = not available
     }
     if (impl == 2) return DEXSIM_E_PARAM;            // TMA pipeline was demanded but is not eligible
+    if (io->flags & DEXSIM_STEP_HOST_ALL_ROWS) return DEXSIM_E_PARAM;   // only the pipelined kernel mirrors every row
     const int grid = grid_for(st->n, STEP_THREADS, di.step_ctas, di.sm_count);
     const bool dense = p->reward_type == 1, aos = io->action_layout == 1;
     if (dense) { if (aos) launch_step_variant<true, true>(extras, grid, s, *st, *p, groups, goe, *io, pack_out, pack_tag);
@@ -1005,6 +1012,8 @@ void expand_contact_rows_range(float* h_obs, const uint8_t* mask, int64_t lo, in
 }  // namespace dexsim
 
 using namespace dexsim;
+
+static std::atomic<int64_t> g_zero_copy_steps{0};    // dexsim_step_host calls served by the single-launch transport
 
 extern "C" {
 
@@ -1280,12 +1289,25 @@ static bool upload_stream_choice() {
     return v == 1;
 }
 
+// zero-copy transport: 1 = the step kernel reads the actions from mapped host memory itself (no copy at all),
+// 0 = the copy engine uploads them chunk by chunk
+static bool zc_kernel_upload() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("DEXSIM_ZC_KERNEL_UPLOAD");
+        v = (e && atoi(e)) ? 1 : 0;
+    }
+    return v == 1;
+}
+
 int dexsim_expand_contact_rows(float* h_obs, const uint8_t* h_contact_mask, int64_t n, int64_t ld) {
     if (!h_obs || !h_contact_mask) return DEXSIM_E_NULL;
     if (n < 0 || ld < n) return DEXSIM_E_SIZE;
     expand_contact_rows_range(h_obs, h_contact_mask, 0, n, ld);
     return 0;
 }
+
+int64_t dexsim_host_zero_copy_steps(void) { return g_zero_copy_steps.load(std::memory_order_relaxed); }
 
 int dexsim_step_host(const DexsimState* st, const DexsimParams* p, const DexsimGroup* groups,
                      const uint16_t* group_of_env, const DexsimStepIO* io, const float* h_action, float* h_obs,
@@ -1301,10 +1323,47 @@ int dexsim_step_host(const DexsimState* st, const DexsimParams* p, const DexsimG
     const int64_t n = st->n, ld = st->ld;
     if (n == 0) return 0;
     const bool aos = io->action_layout == 1;
+    // Zero-copy transport (DEXSIM_HOST_ZERO_COPY): the pipelined kernel itself writes every result into the caller's mapped
+    // page-locked buffers -- the joint rows as a second bulk tensor store per tile, object z, its velocity and the contact
+    // mask as three more bulk rows, x / y and their velocities when a reset changes them (h_obs must be current, as for
+    // DEXSIM_HOST_STATIC_ROWS) -- so nothing is downloaded by the copy engine: no per-copy hand-over times, no pipeline
+    // fill, and the download of a tile starts the moment it is computed.  The contact rows follow from the mask
+    // (PACKED_CONTACTS semantics; EXPAND_CONTACTS as below).  The actions either come up chunk by chunk on the copy engine (default:
+    // uploads of chunk k+1 overlap the PCIe writes of chunk k's kernel) or are read from host memory by the kernel's own
+    // bulk loads (DEXSIM_ZC_KERNEL_UPLOAD=1: no copies at all).  Not eligible (a buffer that is not mapped, fewer envs
+    // than a tile, DEXSIM_STEP_IMPL=register): the copy transport below runs instead.
+    DexsimStepIO zio = *io;
+    bool zc = false;
+    if ((flags & DEXSIM_HOST_ZERO_COPY) && (flags & DEXSIM_HOST_PACKED_CONTACTS) && h_obs && n >= TILE) {
+        auto alias = [](const void* h) -> void* {
+            if (!h) return nullptr;
+            cudaPointerAttributes attr;
+            if (cudaPointerGetAttributes(&attr, h) == cudaSuccess && attr.type == cudaMemoryTypeHost && attr.devicePointer)
+                return attr.devicePointer;
+            (void)cudaGetLastError();
+            return nullptr;
+        };
+        zio.host_static_rows = static_cast<float*>(alias(h_obs));
+        zio.reward = static_cast<float*>(alias(h_reward));
+        zio.terminated = static_cast<uint8_t*>(alias(h_terminated));
+        zio.truncated = static_cast<uint8_t*>(alias(h_truncated));
+        if (h_num_contacts) zio.num_contacts = static_cast<uint8_t*>(alias(h_num_contacts));
+        zio.host_cmask = static_cast<uint8_t*>(alias(h_contact_mask));
+        zio.flags |= DEXSIM_STEP_HOST_ALL_ROWS;
+        zc = zio.host_static_rows && zio.reward && zio.terminated && zio.truncated && zio.num_contacts && zio.host_cmask;
+        if (zc && zc_kernel_upload()) {
+            const float* a = static_cast<const float*>(alias(h_action));
+            if (a) { zio.action = a; chunks = 1; }
+            else zc = false;
+        }
+    }
     // chunk boundaries are multiples of 1024 envs (tile- and alignment-friendly)
     if (chunks > HOST_MAX_CHUNKS) chunks = HOST_MAX_CHUNKS;
     int64_t per = ((n + (chunks > 0 ? chunks : 1) - 1) / (chunks > 0 ? chunks : 1) + 1023) / 1024 * 1024;
-    const int nchunks = (int)((n + per - 1) / per);
+    int nchunks = (int)((n + per - 1) / per);
+    // a last chunk below one tile would not run on the pipelined kernel: the zero-copy transport folds it into its neighbour
+    if (zc && nchunks > 1 && n - (int64_t)(nchunks - 1) * per < TILE) nchunks -= 1;
+    auto chunk_hi = [&](int c) -> int64_t { return c == nchunks - 1 ? n : (int64_t)(c + 1) * per; };
     HostPipe* hp = nullptr;
     int dev = 0;
     // A device's internal streams and events are shared by every caller on that device: enqueue one step at a time
@@ -1328,8 +1387,8 @@ int dexsim_step_host(const DexsimState* st, const DexsimParams* p, const DexsimG
     // observation rows that travel: all 45, or without the constant quaternion rows 33-36 (SKIP_QUAT), and without the
     // five 0/1 contact rows 40-44 when the 1-byte contact mask is sent instead (PACKED_CONTACTS)
     const int rows_hi = (flags & DEXSIM_HOST_PACKED_CONTACTS) ? DEXSIM_ROW_CONTACT : DEXSIM_OBS;
-    const bool expand_on_host = (flags & DEXSIM_HOST_EXPAND_CONTACTS) && (flags & DEXSIM_HOST_PACKED_CONTACTS) &&
-                                !(flags & DEXSIM_HOST_ASYNC) && h_obs != nullptr;
+    bool expand_on_host = (flags & DEXSIM_HOST_EXPAND_CONTACTS) && (flags & DEXSIM_HOST_PACKED_CONTACTS) &&
+                          !(flags & DEXSIM_HOST_ASYNC) && h_obs != nullptr;
     // Rows 30, 31, 37, 38 (object x, y and their velocities) only change when an episode is reset.  When h_obs is mapped
     // page-locked memory the step kernel mirrors every such change straight into it (DexsimStepIO.host_static_rows), and a
     // caller whose buffer is already current (DEXSIM_HOST_STATIC_ROWS) does not download those rows at all.
@@ -1363,7 +1422,7 @@ int dexsim_step_host(const DexsimState* st, const DexsimParams* p, const DexsimG
     };
     auto enqueue_chunks = [&]() -> int {
     for (int c = 0; c < nchunks; ++c) {
-        const int64_t lo = (int64_t)c * per, hi = (lo + per < n) ? lo + per : n, m = hi - lo;
+        const int64_t lo = (int64_t)c * per, hi = chunk_hi(c), m = hi - lo;
         cudaStream_t s = nchunks > 1 ? hp->streams[c % HOST_STREAMS] : user;
         DexsimState sub = *st;
         sub.n = m;
@@ -1373,18 +1432,21 @@ int dexsim_step_host(const DexsimState* st, const DexsimParams* p, const DexsimG
         if (sub.ep_stats) sub.ep_stats += lo;
         DexsimParams sp = *p;
         sp.env_gid0 = p->env_gid0 + lo;
-        DexsimStepIO sio = *io;
+        DexsimStepIO sio = zc ? zio : *io;
+        const bool kernel_upload = zc && zio.action != io->action;       // the kernel reads the actions from host memory
         float* d_action = const_cast<float*>(io->action) + (aos ? lo * NJ : lo);
-        sio.action = d_action;
+        sio.action = kernel_upload ? zio.action + (aos ? lo * NJ : lo) : d_action;
         sio.reward += lo; sio.terminated += lo; sio.truncated += lo; sio.num_contacts += lo;
         if (sio.reward_comps) sio.reward_comps += lo;
         if (sio.reward64) sio.reward64 += lo;
         if (sio.finished) sio.finished += lo;
         if (sio.sched) sio.sched = (2 * (c + 1) + 1 < DEXSIM_SCHED_WORDS) ? io->sched + 2 * (c + 1) : nullptr;   // chunks run concurrently
-        if (mirror) sio.host_static_rows = mirror + lo;
-        cudaError_t err;
+        if (zc) { sio.host_static_rows = zio.host_static_rows + lo; if (sio.host_cmask) sio.host_cmask += lo; }
+        else if (mirror) sio.host_static_rows = mirror + lo;
+        cudaError_t err = cudaSuccess;
         cudaStream_t up = (nchunks > 1 && upload_stream_choice()) ? hp->upload : s;
-        if (aos) err = cudaMemcpyAsync(d_action, h_action + lo * NJ, (size_t)m * NJ * sizeof(float), cudaMemcpyHostToDevice, up);
+        if (kernel_upload) up = s;
+        else if (aos) err = cudaMemcpyAsync(d_action, h_action + lo * NJ, (size_t)m * NJ * sizeof(float), cudaMemcpyHostToDevice, up);
         else err = cudaMemcpy2DAsync(d_action, (size_t)ld * 4, h_action + lo, (size_t)ld * 4, (size_t)m * 4, NJ, cudaMemcpyHostToDevice, up);
         if (err != cudaSuccess) return -(int)err;
         if (up != s) {                                   // the chunk's stream picks up where the upload stream got to
@@ -1394,6 +1456,13 @@ int dexsim_step_host(const DexsimState* st, const DexsimParams* p, const DexsimG
         }
         rc = launch_step(&sub, &sp, groups, group_of_env ? group_of_env + lo : nullptr, &sio, s);
         if (rc) return rc;
+        if (zc) {                                        // every result is already on its way to the host buffers
+            if (nchunks > 1) {
+                err = cudaEventRecord(hp->kdone[c], s);
+                if (err != cudaSuccess) return -(int)err;
+            }
+            continue;
+        }
         if (nchunks > 1) {
             if (expand_on_host) {                        // the chunk's contact masks first: the host expands them while its rows travel
                 err = cudaMemcpyAsync(h_contact_mask + lo, st->cmask + lo, (size_t)m, cudaMemcpyDeviceToHost, s);
@@ -1433,7 +1502,7 @@ int dexsim_step_host(const DexsimState* st, const DexsimParams* p, const DexsimG
             if (rc) return rc;
         }
     }
-    if (nchunks > 1) {
+    if (nchunks > 1 && !zc) {
         // reward / flags of the whole batch in one copy per vector (5 copies instead of 5 per chunk: every copy costs
         // the DMA engine a few microseconds whatever its size), on their own stream once every chunk's kernel has run --
         // the kernels finish long before the observation downloads do, so these ride along with them
@@ -1447,6 +1516,12 @@ int dexsim_step_host(const DexsimState* st, const DexsimParams* p, const DexsimG
     return 0;
     };
     rc = enqueue_chunks();
+    if (zc && rc == DEXSIM_E_PARAM) {
+        // the pipelined kernel is not available for this call (nothing has been launched): copy transport
+        zc = false;
+        rc = enqueue_chunks();
+    }
+    if (zc && rc == 0) g_zero_copy_steps.fetch_add(1, std::memory_order_relaxed);
     if (nchunks > 1) {
         for (int k = 0; k < HOST_STREAMS && k < nchunks; ++k) {
             cudaError_t err = cudaEventRecord(hp->join_ev[k], hp->streams[k]);
@@ -1468,7 +1543,7 @@ int dexsim_step_host(const DexsimState* st, const DexsimParams* p, const DexsimG
         // writes the five 0/1 contact rows chunk by chunk while the DMA engine is still downloading the other 36 rows --
         // 20 of 171 bytes per env never cross PCIe and the observation is complete on return.
         for (int c = 0; c < nchunks && rc == 0; ++c) {
-            const int64_t lo = (int64_t)c * per, hi = (lo + per < n) ? lo + per : n;
+            const int64_t lo = (int64_t)c * per, hi = chunk_hi(c);
             const cudaError_t err = nchunks > 1 ? cudaEventSynchronize(hp->kdone[c]) : cudaStreamSynchronize(user);
             if (err == cudaSuccess) expand_contact_rows_range(h_obs, h_contact_mask, lo, hi, ld);
             else rc = -(int)err;

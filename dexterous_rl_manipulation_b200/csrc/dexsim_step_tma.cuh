@@ -67,6 +67,7 @@ struct StepMaps {             // tensor maps live in kernel parameter space (__g
     CUtensorMap obs_ov;       // obs [45, ld] f32, box {128, 3}
     CUtensorMap op64;         // op64 [3, ld] f64, box {128, 3}
     CUtensorMap act_soa;      // action [15, ld] f32, box {128, 15} (only valid for layout 0)
+    CUtensorMap host_jpjv;    // the caller's mapped host observation [45, ld] f32, box {128, 30} (DEXSIM_STEP_HOST_ALL_ROWS)
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -288,6 +289,10 @@ step_tma_kernel(const DexsimState st, const DexsimParams p, const DexsimGroup* _
     // it every step, and an auto-reset needs it before it can draw anything -- as a dependent load from HBM inside the
     // compute phase it cost every warp with a finishing lane about a microsecond (ncu, 6.7 % resets per env-step:
     // long_scoreboard the top stall of the reset path); 4 B/env-step of extra traffic buy that latency back.
+    // zero-copy host step (dexsim_step_host, DEXSIM_HOST_ZERO_COPY): EVERY observation entry that changes is also written
+    // into the caller's mapped host observation -- the joint rows by a second bulk tensor store per tile, the rest from
+    // registers when they change
+    const bool host_all = (io.flags & DEXSIM_STEP_HOST_ALL_ROWS) != 0 && io.host_static_rows != nullptr;
     const bool load_episode = (EXTRA && ((!io.dyn_noise && io.sigma_dyn != 0.0f) || (!io.obs_noise && io.noisy_obs && io.sigma_obs != 0.0f))) ||
                               (TRACK && p.auto_reset);
 
@@ -317,6 +322,16 @@ step_tma_kernel(const DexsimState st, const DexsimParams p, const DexsimGroup* _
                 const uint32_t sb = smem_u32(stage_base + (size_t)s * STAGE_BYTES);
                 const uint32_t cols = tile_cols(n, base);
                 tma_store_2d(&maps.obs_jpjv, (int)base, DEXSIM_ROW_JP, sb + OFF_JPJV);
+                // zero-copy host step: the same 30 joint rows go straight into the caller's mapped host observation
+                // (object z, its velocity and the contact masks follow as three small rows: the compute warps left them in
+                // the stage slots of the velocity rows / the mask; x, y and their velocities only change at a reset and are
+                // written from registers then)
+                if (host_all) {
+                    tma_store_2d(&maps.host_jpjv, (int)base, DEXSIM_ROW_JP, sb + OFF_JPJV);
+                    bulk_store(io.host_static_rows + (int64_t)(DEXSIM_ROW_OP + 2) * ld + base, sb + OFF_OV, cols * 4);
+                    bulk_store(io.host_static_rows + (int64_t)(DEXSIM_ROW_OV + 2) * ld + base, sb + OFF_OV + 2 * TILE * 4, cols * 4);
+                    if (io.host_cmask) bulk_store(io.host_cmask + base, sb + OFF_CMASK, cols);
+                }
                 bulk_store(st.step_count + base, sb + OFF_SC, cols * 4);
                 bulk_store(io.reward + base, sb + OFF_REWARD, cols * 4);
                 bulk_store(io.terminated + base, sb + OFF_TERM, cols);
@@ -563,6 +578,14 @@ step_tma_kernel(const DexsimState st, const DexsimParams p, const DexsimGroup* _
                             obs[(DEXSIM_ROW_OV + c) * ld + i] = e.ov[c];
                             if (c < 2 && io.host_static_rows) io.host_static_rows[(DEXSIM_ROW_OV + c) * ld + i] = e.ov[c];
                         }
+                    }
+                    if (host_all) {
+                        // zero-copy host step: z, its velocity and the contact mask leave with the tile's bulk stores
+                        // (they change too often for 4-byte writes across PCIe); the velocity slots are free by now
+                        float* s_out = reinterpret_cast<float*>(sp + OFF_OV);
+                        s_out[col] = (float)e.op[2];
+                        s_out[2 * TILE + col] = e.ov[2];
+                        (sp + OFF_CMASK)[col] = (uint8_t)e.cmask;
                     }
                     const unsigned flip = e.cmask ^ cmask_old;
                     if (flip) {

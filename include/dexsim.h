@@ -143,6 +143,13 @@ typedef struct DexsimGroup {
  * the 126 MB L2 -- reads of those tiles hit, and their stores overwrite lines that are still dirty instead of costing a
  * write-back.  Results do not depend on it. */
 #define DEXSIM_STEP_REVERSE_TILES 1
+/* DexsimStepIO.flags, with host_static_rows set (pipelined kernel only; other configurations answer DEXSIM_E_PARAM):
+ * write the observation into the host buffer as part of the step, not just rows 30/31/37/38 -- each tile's 30 joint
+ * rows by a second bulk tensor store, object z (row 32) and its velocity (row 39) as two more row segments, and the
+ * 1-byte contact masks into host_cmask (the five 0/1 contact rows 40-44 are NOT written: they follow from the mask,
+ * dexsim_expand_contact_rows).  With the per-env outputs pointing at mapped host memory too, nothing is left to
+ * download (dexsim_step_host: DEXSIM_HOST_ZERO_COPY). */
+#define DEXSIM_STEP_HOST_ALL_ROWS 2
 
 /* Inputs / outputs of one batched step (all device pointers, SoA with the state's ld). */
 typedef struct DexsimStepIO {
@@ -184,6 +191,9 @@ typedef struct DexsimStepIO {
      * entries is ALSO written there by the step kernel (a handful of 4-byte stores per reset), so a caller that downloads
      * the observation every step need not download these rows (dexsim_step_host: DEXSIM_HOST_STATIC_ROWS).  NULL = off. */
     float*       host_static_rows;
+    /* With DEXSIM_STEP_HOST_ALL_ROWS in `flags` (pipelined kernel only): host copy of the 1-byte contact masks
+     * (DexsimState.cmask), written every step; or NULL. */
+    uint8_t*     host_cmask;
 } DexsimStepIO;
 #define DEXSIM_SCHED_WORDS 64
 
@@ -349,6 +359,14 @@ int dexsim_classify_summary(const DexsimEpisodeSummary* s, const uint8_t* counts
                                         * touched the state since): do not download them -- the step kernel mirrors every change of
                                         * those entries straight into h_obs (DexsimStepIO.host_static_rows, set by this call).
                                         * Without the flag the rows are downloaded like the others (and the buffer becomes current). */
+#define DEXSIM_HOST_ZERO_COPY 32       /* with PACKED_CONTACTS: every host output buffer of this call is mapped page-locked memory
+                                        * and h_obs is current in the STATIC_ROWS sense: the step kernel writes the results
+                                        * (joint rows, z, its velocity, contact masks, reward, flags) into the host buffers
+                                        * itself, tile by tile, as part of the launch (DEXSIM_STEP_HOST_ALL_ROWS) -- no
+                                        * device-to-host copies.  In this mode the per-env outputs exist ONLY in the host buffers
+                                        * (io->reward / terminated / truncated / num_contacts on the device are not written).
+                                        * Falls back to the copy transport when a buffer is not mapped, the batch is below one
+                                        * tile or the pipelined kernel is not eligible. */
 #define DEXSIM_HOST_EXPAND_CONTACTS 8  /* with PACKED_CONTACTS (and not ASYNC): the calling thread writes obs rows 40-44 of h_obs
                                         * from the masks while the other rows are still being downloaded, so h_obs is complete
                                         * on return although the five rows never crossed PCIe */
@@ -359,6 +377,9 @@ int dexsim_step_host(const DexsimState* st, const DexsimParams* p, const DexsimG
                      uint8_t* h_terminated, uint8_t* h_truncated, uint8_t* h_num_contacts /* host [ld] or NULL */,
                      uint8_t* h_contact_mask /* host [ld]; required with DEXSIM_HOST_PACKED_CONTACTS, else may be NULL */,
                      int32_t chunks, int32_t flags, void* stream);
+
+/* Diagnostic: how many dexsim_step_host calls of this process were served by the DEXSIM_HOST_ZERO_COPY launch. */
+int64_t dexsim_host_zero_copy_steps(void);
 
 /* HOST function: observation rows 40-44 (the five 0/1 contact floats, envs/manipulation_env.py:262) of envs [0, n) of a
  * host [45, ld] observation buffer from their 1-byte contact masks -- what DEXSIM_HOST_EXPAND_CONTACTS does chunk by chunk

@@ -746,6 +746,56 @@ def test_step_host_matches_device_step(dx, n, chunks, track):
     assert torch.equal(a_env._obs, b_env._obs)
 
 
+@pytest.mark.parametrize("n,track", [(5000, True), (70_001, True), (4096, False)])
+def test_step_host_zero_copy_launch(dx, n, track):
+    """DEXSIM_HOST_ZERO_COPY: once the pinned buffers are current and the actions are pinned too, a synchronous step_host
+    is ONE kernel launch that reads the actions from, and writes every result into, host memory -- same results as the
+    device-tensor API, entry by entry, through resets, and the device-side state stays identical."""
+    from dexterous_rl_manipulation_b200 import _lib
+    L = _lib.lib()
+    CC = dx.CurriculumConfig
+    kw = dict(max_episode_steps=15, reward_type="dense", seed=21, groups=[CC.easy(), CC.hard()])
+    if track:
+        kw.update(auto_reset=True, respawn=True, loop_max_steps=15, track_episodes=True)
+    a_env = dx.BatchedManipulationEnv(n, "cuda", **kw)
+    b_env = dx.BatchedManipulationEnv(n, "cuda", **kw)
+    a_env.reset(seed=21); b_env.reset(seed=21)
+    b_env.host_zero_copy = True                      # (default "auto": on up to 160K envs)
+    rng = np.random.default_rng(4)
+    pins = [torch.empty(n, 15).pin_memory() for _ in range(2)]
+    before = int(L.dexsim_host_zero_copy_steps())
+    for t in range(50):
+        act = rng.uniform(-1.2, 1.2, (n, 15)).astype(np.float32)
+        if t == 23:                                   # a device-side step behind the host buffer: next call re-primes
+            a_env.step(torch.from_numpy(act).cuda()); b_env.step(torch.from_numpy(act).cuda())
+            act = rng.uniform(-1.2, 1.2, (n, 15)).astype(np.float32)
+        if t == 31:
+            a_env.reset(seed=6); b_env.reset(seed=6)
+        pins[t % 2].copy_(torch.from_numpy(act))
+        o1, r1, te1, tr1, i1 = a_env.step(torch.from_numpy(act).cuda())
+        o2, r2, te2, tr2, i2 = b_env.step_host(pins[t % 2])
+        assert torch.equal(o1.cpu(), o2), (t, (o1.cpu() != o2).nonzero()[:5])
+        assert torch.equal(r1.cpu(), r2) and torch.equal(te1.cpu(), te2) and torch.equal(tr1.cpu(), tr2), t
+        assert torch.equal(i1["num_contacts"].cpu(), i2["num_contacts"]), t
+        assert torch.equal(i2["contact_mask"], a_env._cmask[:n].cpu()), t
+    # 50 calls, three of them priming downloads (first call, after the device-side step, after the reset)
+    assert int(L.dexsim_host_zero_copy_steps()) - before == 47
+    assert torch.equal(a_env._obs, b_env._obs) and torch.equal(a_env._op64, b_env._op64)
+    assert torch.equal(a_env._episode, b_env._episode) and torch.equal(a_env._cmask, b_env._cmask)
+    if track:
+        assert torch.equal(a_env.counters, b_env.counters) and int(a_env.counters[:, 0].sum()) > 0
+    # switched off: the copy transport, same results
+    b_env.host_zero_copy = False
+    before = int(L.dexsim_host_zero_copy_steps())
+    for t in range(5):
+        act = rng.uniform(-1.2, 1.2, (n, 15)).astype(np.float32)
+        pins[t % 2].copy_(torch.from_numpy(act))
+        o1, r1, te1, tr1, i1 = a_env.step(torch.from_numpy(act).cuda())
+        o2, r2, te2, tr2, i2 = b_env.step_host(pins[t % 2])
+        assert torch.equal(o1.cpu(), o2) and torch.equal(r1.cpu(), r2), t
+    assert int(L.dexsim_host_zero_copy_steps()) == before
+
+
 class _PatternPolicy:
     """Deterministic, observation-independent policy (step-indexed pattern) usable on both sides."""
 

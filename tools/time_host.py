@@ -13,7 +13,8 @@ env = dx.BatchedManipulationEnv(n, "cuda", max_episode_steps=200, reward_type="d
                                 loop_max_steps=200, track_episodes=False, curriculum_config=dx.CurriculumConfig.easy())
 env.reset(seed=1)
 pool = [torch.rand(n, 15).mul_(2).sub_(1).pin_memory() for _ in range(2)]
-for chunks in (1, 4, 6, 8, 12, 16, 24, 32):
+env.host_zero_copy = False                         # the copy transport first
+for chunks in (1, 4, 8, 12, 16):
     for t in range(3):
         env.step_host(pool[t % 2], chunks=chunks)
     t0 = time.perf_counter()
@@ -32,3 +33,20 @@ for chunks in (8, 16):
     env.host_sync()
     dt = (time.perf_counter() - t0) / 20
     print(f"async chunks {chunks:3d}: {dt * 1e3:6.3f} ms/step  {n / dt / 1e6:7.1f} M env-steps/s", flush=True)
+
+# zero-copy: one launch, actions read from / results written to pinned host memory by the kernel itself
+env.host_zero_copy = True
+from dexterous_rl_manipulation_b200 import _lib  # noqa: E402
+L = _lib.lib()
+for packed in (False, True):
+    for chunks in (1, 2, 4, 8, 16):
+        for t in range(3):
+            env.step_host(pool[t % 2], chunks=chunks, packed_contacts=packed)
+        z0 = int(L.dexsim_host_zero_copy_steps())
+        t0 = time.perf_counter()
+        for t in range(20):
+            env.step_host(pool[t % 2], chunks=chunks, packed_contacts=packed)
+        dt = (time.perf_counter() - t0) / 20
+        print(f"zero-copy chunks {chunks:3d} packed={int(packed)}: {dt * 1e3:6.3f} ms/step  {n / dt / 1e6:7.1f} M env-steps/s  "
+              f"(zero-copy launches {int(L.dexsim_host_zero_copy_steps()) - z0}/20, kernel upload {os.environ.get('DEXSIM_ZC_KERNEL_UPLOAD', '0')})",
+              flush=True)
