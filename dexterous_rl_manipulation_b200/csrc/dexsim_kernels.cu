@@ -1414,7 +1414,7 @@ int dexsim_step_host(const DexsimState* st, const DexsimParams* p, const DexsimG
             err = cudaMemcpyAsync(h_num_contacts + lo, io->num_contacts + lo, (size_t)m, cudaMemcpyDeviceToHost, s);
             if (err != cudaSuccess) return -(int)err;
         }
-        if ((flags & DEXSIM_HOST_PACKED_CONTACTS) && !(expand_on_host && nchunks > 1)) {
+        if (h_contact_mask && !(expand_on_host && nchunks > 1)) {        // (1 byte per env: sent whenever the caller has room for it)
             err = cudaMemcpyAsync(h_contact_mask + lo, st->cmask + lo, (size_t)m, cudaMemcpyDeviceToHost, s);
             if (err != cudaSuccess) return -(int)err;
         }

@@ -375,7 +375,7 @@ int dexsim_step_host(const DexsimState* st, const DexsimParams* p, const DexsimG
                      const float* h_action /* host [n, 15] (layout 1) or [15, ld] (layout 0) */,
                      float* h_obs /* host [45, ld] or NULL */, float* h_reward /* host [ld] */,
                      uint8_t* h_terminated, uint8_t* h_truncated, uint8_t* h_num_contacts /* host [ld] or NULL */,
-                     uint8_t* h_contact_mask /* host [ld]; required with DEXSIM_HOST_PACKED_CONTACTS, else may be NULL */,
+                     uint8_t* h_contact_mask /* host [ld]: filled whenever given; required with DEXSIM_HOST_PACKED_CONTACTS */,
                      int32_t chunks, int32_t flags, void* stream);
 
 /* Diagnostic: how many dexsim_step_host calls of this process were served by the DEXSIM_HOST_ZERO_COPY launch. */

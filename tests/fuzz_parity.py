@@ -1,7 +1,8 @@
 """Randomised differential test (experiments / soak; the fixed-seed versions of these checks live in
 tests/test_gpu_parity.py): CUDA fused rollout vs the oracle's rollout, dexsim_step (either step kernel, with and without
 pre-drawn noise) vs the oracle's step on hostile actions, and API-mode auto-reset stepping with the exposed Philox
-actions vs the oracle's rollout (the pipelined kernel's dynamic tile scheduler and reset path at multi-tile sizes).
+actions vs the oracle's rollout (the pipelined kernel's dynamic tile scheduler and reset path at multi-tile sizes), and the
+host-buffer entry (copy and zero-copy transports) vs the device-tensor API.
 Runs random configurations until the time budget is spent and stops at the first mismatch.
 
     python tests/fuzz_parity.py [seconds] [first_seed]
@@ -119,8 +120,66 @@ def fuzz_api_autoreset(case):
     return K * n, int(cnt[:, 0].sum())
 
 
+def fuzz_host_transport(case):
+    """env.step_host (copy transport and zero-copy transport, random chunk counts, contacts packed or expanded on the
+    host, resets and device-side steps in between) against a twin env stepped through the device-tensor API: every
+    returned host tensor every step, and the complete device state at the end."""
+    rng = np.random.default_rng(30_000_000 + case)
+    n = int(rng.choice([100, 128, 129, 1000, 4097, 33000, 70001, 150000]))
+    dense, track = bool(rng.integers(2)), bool(rng.integers(2))
+    max_steps = int(rng.choice([3, 9, 40]))
+    zc = [True, False, "auto"][int(rng.integers(3))]
+    K = int(rng.integers(5, 60 if n < 50000 else 16))
+    seed = int(rng.integers(0, 2 ** 63))
+    cfgs = [CC.easy(), CC(object_size=0.06, object_size_range=(0.03, 0.09), friction_range=(0.1, 0.9))][:int(rng.integers(1, 3))]
+    kw = dict(max_episode_steps=max_steps, reward_type="dense" if dense else "sparse", groups=cfgs, seed=seed)
+    if track:
+        kw.update(auto_reset=True, respawn=bool(rng.integers(2)), loop_max_steps=max_steps, track_episodes=bool(rng.integers(2)))
+    a_env = dx.BatchedManipulationEnv(n, "cuda", **kw)
+    b_env = dx.BatchedManipulationEnv(n, "cuda", **kw)
+    a_env.reset(seed=seed); b_env.reset(seed=seed)
+    b_env.host_zero_copy = zc
+    b_env.host_expand_contacts = bool(rng.integers(4))          # off: all rows downloaded (and no zero-copy)
+    desc = dict(case=case, mode="host", n=n, dense=dense, track=track, max_steps=max_steps, zc=zc, K=K,
+                expand=b_env.host_expand_contacts)
+    pins = [torch.empty(n, 15).pin_memory() for _ in range(2)]
+    for t in range(K):
+        act = torch.from_numpy(rng.uniform(-1.3, 1.3, (n, 15)).astype(np.float32))
+        event = int(rng.integers(12))
+        if event == 0:                                           # device-side step behind the host buffers
+            a_env.step(act.cuda()); b_env.step(act.cuda())
+        elif event == 1:
+            s2 = int(rng.integers(0, 2 ** 31))
+            a_env.reset(seed=s2); b_env.reset(seed=s2)
+        chunks = [None, 1, 2, 3, 8][int(rng.integers(5))]
+        packed = bool(rng.integers(3) == 0)
+        pins[t % 2].copy_(act)
+        o1, r1, te1, tr1, i1 = a_env.step(act.cuda())
+        o2, r2, te2, tr2, i2 = b_env.step_host(pins[t % 2] if rng.integers(2) else act.numpy(), chunks=chunks, packed_contacts=packed)
+        if packed:
+            o2 = b_env.expand_contacts_host()
+        ok = (torch.equal(o1.cpu(), o2) and torch.equal(r1.cpu(), r2) and torch.equal(te1.cpu(), te2) and torch.equal(tr1.cpu(), tr2)
+              and torch.equal(i1["num_contacts"].cpu(), i2["num_contacts"]) and torch.equal(i2["contact_mask"], a_env._cmask[:n].cpu()))
+        if not ok:
+            print("MISMATCH", desc, "step", t, flush=True)
+            sys.exit(1)
+    ok = (torch.equal(a_env._obs, b_env._obs) and torch.equal(a_env._op64, b_env._op64) and torch.equal(a_env._episode, b_env._episode)
+          and torch.equal(a_env._cmask, b_env._cmask) and torch.equal(a_env._step_count, b_env._step_count)
+          and (not track or torch.equal(a_env.counters, b_env.counters)))
+    if not ok:
+        print("MISMATCH (final state)", desc, flush=True)
+        sys.exit(1)
+    return K * n
+
+
 api_steps = 0
+host_steps = 0
 while time.time() < t_end:
+    if case % 4 == 3:
+        host_steps += fuzz_host_transport(case)
+        done += 1
+        case += 1
+        continue
     if case % 3 == 1:
         api_steps += fuzz_api_steps(case)
         done += 1
@@ -188,4 +247,4 @@ while time.time() < t_end:
     episodes += int(cnt[:, 0].sum())
     case += 1
     del env
-print(f"fuzz ok: {done} random configurations, {episodes} finished episodes and {api_steps} API env-steps compared, next seed {case}")
+print(f"fuzz ok: {done} random configurations, {episodes} finished episodes and {api_steps} API + {host_steps} host-transport env-steps compared, next seed {case}")
