@@ -99,7 +99,7 @@ class DexsimEpisodeSummary(C.Structure):
 EXPORTS = (
     "dexsim_version", "dexsim_error_string", "dexsim_sizeof_state", "dexsim_sizeof_params",
     "dexsim_sizeof_group", "dexsim_sizeof_step_io", "dexsim_sizeof_rollout_io", "dexsim_sizeof_episode_record",
-    "dexsim_device_info", "dexsim_set_step_impl", "dexsim_set_rollout_impl", "dexsim_reset_predrawn",
+    "dexsim_device_info", "dexsim_set_step_impl", "dexsim_set_step_tile", "dexsim_set_rollout_impl", "dexsim_reset_predrawn",
     "dexsim_reset_philox", "dexsim_step", "dexsim_rollout", "dexsim_fill_policy_actions",
     "dexsim_fill_normal", "dexsim_classify_summary", "dexsim_step_host", "dexsim_pack_env", "dexsim_pack_env_tagged", "dexsim_step_single",
     "dexsim_expand_contact_rows",
@@ -135,6 +135,7 @@ def lib():
         getattr(L, name).restype = C.c_int
     L.dexsim_device_info.argtypes = [C.POINTER(C.c_int)] * 3
     L.dexsim_set_step_impl.argtypes = [C.c_int]
+    L.dexsim_set_step_tile.argtypes = [C.c_int]
     L.dexsim_set_rollout_impl.argtypes = [C.c_int]
     L.dexsim_reset_predrawn.argtypes = [C.POINTER(DexsimState), C.POINTER(DexsimParams), vp, vp, vp, vp, vp, vp, vp]
     L.dexsim_reset_philox.argtypes = [C.POINTER(DexsimState), C.POINTER(DexsimParams), vp, vp, vp, i32, vp]
@@ -175,6 +176,11 @@ def set_step_impl(impl):
     """'auto' | 'register' | 'tma' -- which step kernel dexsim_step launches (tests / profiling)."""
     code = {"auto": 0, "register": 1, "tma": 2}[impl]
     check(lib().dexsim_set_step_impl(code), "dexsim_set_step_impl")
+
+
+def set_step_tile(tile):
+    """'auto' | 'narrow' | 'wide' -- tile width of the pipelined step kernel (tests / profiling)."""
+    check(lib().dexsim_set_step_tile({"auto": 0, "narrow": 1, "wide": 2}[tile]), "dexsim_set_step_tile")
 
 
 def set_rollout_impl(impl):

@@ -832,12 +832,13 @@ static bool pdl_in_graphs() {
     return v == 1;
 }
 
-template <bool DENSE, bool AOS, int TRACK, bool EXTRA, int STAGES>
+template <bool DENSE, bool AOS, int TRACK, bool EXTRA, int STAGES, int TILE_>
 static int launch_tma_variant(int sm_count, cudaStream_t s, const DexsimState& st, const DexsimParams& p,
                               const DexsimGroup* groups, const uint16_t* goe, const DexsimStepIO& io,
                               const StepMaps& maps, int num_tiles) {
-    auto kern = step_tma_kernel<DENSE, AOS, TRACK, EXTRA, STAGES>;
-    const size_t smem = (size_t)STAGES * STAGE_BYTES + 2 * STAGES * (sizeof(uint64_t) + sizeof(int)) +
+    auto kern = step_tma_kernel<DENSE, AOS, TRACK, EXTRA, STAGES, TILE_>;
+    constexpr int TMA_THREADS = TILE_ + 32;            // one compute thread per env of a tile + the producer warp
+    const size_t smem = (size_t)STAGES * StageLayout<TILE_>::stage_bytes(TRACK) + 2 * STAGES * (sizeof(uint64_t) + sizeof(int)) +
                         (TRACK ? TMA_GROUPS_MAX * (DEXSIM_NCOUNTERS * sizeof(unsigned long long) + 2 * sizeof(double)) : 0);
     // per template instantiation and per device: the shared-memory opt-in is a per-device function attribute
     static thread_local int occupancy[64] = {0};
@@ -909,40 +910,84 @@ static int64_t tma_min_envs(int track, bool extra) {
     return v < TILE ? TILE : v;
 }
 
+// Tile width of the pipelined kernel: 0 = auto, 1 = narrow (128 envs, three CTAs of four compute warps per SM) only,
+// 2 = wide (224 envs, two CTAs of seven compute warps per SM) wherever it exists.  Initialised from DEXSIM_STEP_TILE
+// (narrow | wide), changeable at run time with dexsim_set_step_tile().  Identical results either way.
+static int g_step_tile = -1;
+static int step_tile_choice() {
+    if (g_step_tile < 0) {
+        const char* e = getenv("DEXSIM_STEP_TILE");
+        g_step_tile = (e && !strcmp(e, "narrow")) ? 1 : (e && !strcmp(e, "wide")) ? 2 : 0;
+    }
+    return g_step_tile;
+}
+
+// A step of a batch whose state sits in L2 (below ~256 Ki envs) is bound by how many env-warps an SM can run side by side
+// and how many of them each compute warp has to run one after the other: ceil(tiles / resident CTAs) tiles per CTA.  The
+// wide tile has 14 instead of 12 compute warps per SM; it is taken when that makes the chain of tiles per CTA shorter.
+// Measured (tools/time_tile.py, profiles/r02_time_tile.txt, us per step narrow / wide, counts-only): 65,536 envs 9.4 / 9.8
+// (plain 7.4 / 6.5), 98,304 9.9 / 10.4, 131,072 11.7 / 10.7 (plain 9.2 / 8.9), 163,840 12.6 / 13.3, 196,608 14.1 / 13.8,
+// 229,376 15.2 / 15.7, 262,144 16.9 / 16.7, 1 Mi 57.9 / 57.8 --
+// HBM-bound batches gain nothing, so they stay on the narrow tile (more CTAs for the dynamic tile hand-out to balance).
+static bool use_wide_tile(int64_t n, int track, int sm_count) {
+    if (track == 1 || n < TILE_WIDE || TILE != 128) return false;       // full tracking: its stages only fit the narrow tile
+    const int choice = step_tile_choice();
+    if (choice) return choice == 2;
+    if (n >= (int64_t)1 << 18) return false;
+    // tiles per resident CTA, rounded up -- a handful of CTAs with one tile more (5 % of a round) do not count as a round:
+    // the dynamic hand-out spreads them over the SMs
+    auto depth = [](int64_t tiles, int64_t ctas) { return (int64_t)ceil((double)tiles / (double)ctas - 0.05); };
+    const int64_t depth_narrow = depth((n + TILE - 1) / TILE, 3 * (int64_t)sm_count);
+    const int64_t depth_wide = depth((n + TILE_WIDE - 1) / TILE_WIDE, 2 * (int64_t)sm_count);
+    return depth_wide < depth_narrow;
+}
+
 // track: 0 = plain step, 1 = full episode tracking (returns + history summaries -> labels), 2 = counts only
 static int launch_step_tma(const DexsimState* st, const DexsimParams* p, const DexsimGroup* groups, const uint16_t* goe,
                            const DexsimStepIO* io, cudaStream_t s, int track, bool extra, int sm_count) {
     // Tensor maps are pure functions of (base pointers, n, ld): a stepping loop re-encodes nothing.  One cached set
     // per host thread; the SoA action map is keyed by the action pointer too (AoS actions use 1-D bulk copies).
-    struct MapCache { const void* obs; const void* op64; const void* act; const void* host; int64_t n, ld; bool valid; StepMaps maps; };
-    static thread_local MapCache cache = {nullptr, nullptr, nullptr, nullptr, 0, 0, false, {}};
+    struct MapCache { const void* obs; const void* op64; const void* act; const void* host; int64_t n, ld; int tile; bool valid; StepMaps maps; };
+    static thread_local MapCache cache = {nullptr, nullptr, nullptr, nullptr, 0, 0, 0, false, {}};
     const bool aos = io->action_layout == 1;
+    const bool wide = use_wide_tile(st->n, track, sm_count);
+    const int tile = wide ? TILE_WIDE : TILE;
     const void* act_key = aos ? nullptr : (const void*)io->action;
     // zero-copy host step: one more map, over the caller's mapped host observation (device alias of the host pointer)
     const void* host_key = (io->flags & DEXSIM_STEP_HOST_ALL_ROWS) ? (const void*)io->host_static_rows : nullptr;
     if (!(cache.valid && cache.obs == st->obs && cache.op64 == st->op64 && cache.act == act_key && cache.host == host_key &&
-          cache.n == st->n && cache.ld == st->ld)) {
+          cache.n == st->n && cache.ld == st->ld && cache.tile == tile)) {
         cache.valid = false;
         memset(&cache.maps, 0, sizeof(cache.maps));
-        bool ok = make_map_2d(&cache.maps.obs_jpjv, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, st->obs, st->n, st->ld, DEXSIM_OBS, 30) &&
-                  make_map_2d(&cache.maps.obs_ov, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, st->obs, st->n, st->ld, DEXSIM_OBS, 3) &&
-                  make_map_2d(&cache.maps.op64, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 8, st->op64, st->n, st->ld, 3, 3);
+        bool ok = make_map_2d(&cache.maps.obs_jpjv, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, st->obs, st->n, st->ld, DEXSIM_OBS, 30, tile) &&
+                  make_map_2d(&cache.maps.obs_ov, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, st->obs, st->n, st->ld, DEXSIM_OBS, 3, tile) &&
+                  make_map_2d(&cache.maps.op64, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 8, st->op64, st->n, st->ld, 3, 3, tile);
         if (ok && !aos)
             ok = make_map_2d(&cache.maps.act_soa, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(io->action), st->n,
-                             st->ld, NJ, NJ);
+                             st->ld, NJ, NJ, tile);
         if (ok && host_key)
             ok = make_map_2d(&cache.maps.host_jpjv, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<void*>(host_key), st->n, st->ld,
-                             DEXSIM_OBS, 30);
+                             DEXSIM_OBS, 30, tile);
         if (!ok) return 1;                           // caller falls back to the register-resident kernel
-        cache.obs = st->obs; cache.op64 = st->op64; cache.act = act_key; cache.host = host_key; cache.n = st->n; cache.ld = st->ld;
+        cache.obs = st->obs; cache.op64 = st->op64; cache.act = act_key; cache.host = host_key; cache.n = st->n; cache.ld = st->ld; cache.tile = tile;
         cache.valid = true;
     }
     const StepMaps& maps = cache.maps;
-    const int num_tiles = (int)((st->n + TILE - 1) / TILE);
+    const int num_tiles = (int)((st->n + tile - 1) / tile);
     const bool dense = p->reward_type == 1;
 #define DEXSIM_TMA_CASE(D, A, T, X)                                                                                 \
     if (dense == D && aos == A && track == T && extra == X)                                                         \
-        return launch_tma_variant<D, A, T, X, DEXSIM_TMA_STAGES>(sm_count, s, *st, *p, groups, goe, *io, maps, num_tiles);
+        return launch_tma_variant<D, A, T, X, DEXSIM_TMA_STAGES, TILE>(sm_count, s, *st, *p, groups, goe, *io, maps, num_tiles);
+#define DEXSIM_TMA_WIDE_CASE(D, A, T, X)                                                                            \
+    if (wide && dense == D && aos == A && track == T && extra == X)                                                 \
+        return launch_tma_variant<D, A, T, X, 2, TILE_WIDE>(sm_count, s, *st, *p, groups, goe, *io, maps, num_tiles);
+    // wide tile: plain and counts-only steps
+    DEXSIM_TMA_WIDE_CASE(true, true, 0, false) DEXSIM_TMA_WIDE_CASE(true, true, 2, false)
+    DEXSIM_TMA_WIDE_CASE(true, false, 0, false) DEXSIM_TMA_WIDE_CASE(true, false, 2, false)
+    DEXSIM_TMA_WIDE_CASE(false, true, 0, false) DEXSIM_TMA_WIDE_CASE(false, true, 2, false)
+    DEXSIM_TMA_WIDE_CASE(false, false, 0, false) DEXSIM_TMA_WIDE_CASE(false, false, 2, false)
+    DEXSIM_TMA_WIDE_CASE(true, true, 0, true) DEXSIM_TMA_WIDE_CASE(true, true, 2, true)
+    DEXSIM_TMA_WIDE_CASE(false, true, 0, true) DEXSIM_TMA_WIDE_CASE(false, true, 2, true)
     DEXSIM_TMA_CASE(true, true, 0, false) DEXSIM_TMA_CASE(true, true, 1, false) DEXSIM_TMA_CASE(true, true, 2, false)
     DEXSIM_TMA_CASE(true, false, 0, false) DEXSIM_TMA_CASE(true, false, 1, false) DEXSIM_TMA_CASE(true, false, 2, false)
     DEXSIM_TMA_CASE(false, true, 0, false) DEXSIM_TMA_CASE(false, true, 1, false) DEXSIM_TMA_CASE(false, true, 2, false)
@@ -950,6 +995,7 @@ static int launch_step_tma(const DexsimState* st, const DexsimParams* p, const D
     // noise / reward components: the reference's [n,15] action layout only (SoA callers take the register kernel)
     DEXSIM_TMA_CASE(true, true, 0, true) DEXSIM_TMA_CASE(true, true, 1, true) DEXSIM_TMA_CASE(true, true, 2, true)
     DEXSIM_TMA_CASE(false, true, 0, true) DEXSIM_TMA_CASE(false, true, 1, true) DEXSIM_TMA_CASE(false, true, 2, true)
+#undef DEXSIM_TMA_WIDE_CASE
 #undef DEXSIM_TMA_CASE
     return 1;
 }
@@ -1037,6 +1083,12 @@ const char* dexsim_error_string(int code) {
 int dexsim_set_step_impl(int impl) {
     if (impl < 0 || impl > 2) return DEXSIM_E_PARAM;
     g_step_impl = impl;
+    return 0;
+}
+
+int dexsim_set_step_tile(int tile) {
+    if (tile < 0 || tile > 2) return DEXSIM_E_PARAM;
+    g_step_tile = tile;
     return 0;
 }
 

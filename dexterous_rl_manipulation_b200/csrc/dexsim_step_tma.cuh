@@ -27,40 +27,47 @@ namespace dexsim {
 #ifndef DEXSIM_TMA_STAGES
 #define DEXSIM_TMA_STAGES 2                        // stages per CTA: 2 (three CTAs per SM) or 3 (two CTAs per SM)
 #endif
-constexpr int TILE = DEXSIM_TMA_TILE;              // envs per tile: 128, or 96 (24.7 KB stages, four CTAs per SM)
+// Envs per tile.  The narrow tile (128 envs: four compute warps + the producer warp, three CTAs per SM; -DDEXSIM_TMA_TILE=96
+// builds 24.7 KB stages, four CTAs per SM) serves every instantiation.  The wide tile (224 envs: seven compute warps +
+// the producer warp, two CTAs per SM) puts 14 instead of 12 compute warps on an SM -- the register file (16 warps x 128
+// registers) and shared memory (2 CTAs x 2 stages x 54.9 KB) are both full then -- and is used for batches whose step is
+// bound by the compute warps' latency, not by HBM (launch_step_tma picks it; measured in profiles/r02_time_tile.txt).
+// Its stages only fit without the full-tracking arrays, so TRACK == 1 always takes the narrow tile.
+constexpr int TILE = DEXSIM_TMA_TILE;              // narrow tile; also the smallest batch the pipeline takes
+constexpr int TILE_WIDE = 224;
 static_assert(TILE % 32 == 0 && TILE <= 256, "a tile is a whole number of warps and one TMA box wide");
-constexpr int TMA_COMPUTE_THREADS = TILE;          // one thread per env of a tile
-constexpr int TMA_THREADS = TMA_COMPUTE_THREADS + 32;   // + the producer warp
 constexpr int TMA_GROUPS_MAX = 16;     // per-CTA counter staging (keeps 3 CTAs per SM with 2 stages)
 
 // byte offsets inside one stage (all multiples of 128: TMA box destinations need 128-byte alignment)
-constexpr int OFF_JPJV = 0;                         // [30][128] f32, in/out
-constexpr int OFF_OV = OFF_JPJV + 30 * TILE * 4;    // [3][128] f32, in
-constexpr int OFF_OP64 = OFF_OV + 3 * TILE * 4;     // [3][128] f64, in
-constexpr int OFF_THR = OFF_OP64 + 3 * TILE * 8;    // [128] f64, in
-constexpr int OFF_ACT = OFF_THR + TILE * 8;         // [128][15] (AoS) or [15][128] (SoA) f32, in
-constexpr int OFF_DAMP = OFF_ACT + NJ * TILE * 4;   // [128] f32, in
-constexpr int OFF_SC = OFF_DAMP + TILE * 4;         // [128] i32, in/out
-constexpr int OFF_REWARD = OFF_SC + TILE * 4;       // [128] f32, out
-constexpr int OFF_CMASK = OFF_REWARD + TILE * 4;    // [128] u8, in
-constexpr int OFF_TERM = OFF_CMASK + TILE;          // [128] u8, out
-constexpr int OFF_TRUNC = OFF_TERM + TILE;          // [128] u8, out
-constexpr int OFF_NC = OFF_TRUNC + TILE;            // [128] u8, out
-constexpr int OFF_EPRET = OFF_NC + TILE;            // [128] f64, in/out (tracking)
-constexpr int OFF_EPST0 = OFF_EPRET + TILE * 8;     // [128] u32, in/out (tracking)
-constexpr int OFF_EPST1 = OFF_EPST0 + TILE * 4;     // [128] u32, in/out (tracking)
-constexpr int OFF_FIN = OFF_EPST1 + TILE * 4;       // [128] u8, out (auto-reset)
-constexpr int OFF_EPISODE = OFF_FIN + TILE;         // [128] u32, in (in-kernel noise: Philox counter word)
-#ifdef DEXSIM_RESET_COOP
-constexpr int OFF_WSLOT = OFF_EPISODE + TILE * 4;   // [128] u64 scratch: one slot per resetting env of a warp (experiment build only)
-constexpr int STAGE_BYTES = (OFF_WSLOT + TILE * 8 + 127) / 128 * 128;
-#else
-constexpr int STAGE_BYTES = (OFF_EPISODE + TILE * 4 + 127) / 128 * 128;      // every stage starts 128-byte aligned
-#endif
-static_assert(OFF_OV % 128 == 0 && OFF_OP64 % 128 == 0 && OFF_ACT % 128 == 0, "tensor-map box destinations");
-static_assert(OFF_THR % 16 == 0 && OFF_DAMP % 16 == 0 && OFF_SC % 16 == 0 && OFF_REWARD % 16 == 0 && OFF_CMASK % 16 == 0 &&
-              OFF_TERM % 16 == 0 && OFF_TRUNC % 16 == 0 && OFF_NC % 16 == 0 && OFF_EPRET % 16 == 0 && OFF_EPST0 % 16 == 0 &&
-              OFF_EPST1 % 16 == 0 && OFF_FIN % 16 == 0 && OFF_EPISODE % 16 == 0, "1-D bulk copy destinations");
+template <int T>
+struct StageLayout {
+    static_assert(T % 32 == 0 && T <= 256, "a tile is a whole number of warps and one TMA box wide");
+    static constexpr int OFF_JPJV = 0;                         // [30][T] f32, in/out
+    static constexpr int OFF_OV = OFF_JPJV + 30 * T * 4;       // [3][T] f32, in
+    static constexpr int OFF_OP64 = OFF_OV + 3 * T * 4;        // [3][T] f64, in
+    static constexpr int OFF_THR = OFF_OP64 + 3 * T * 8;       // [T] f64, in
+    static constexpr int OFF_ACT = OFF_THR + T * 8;            // [T][15] (AoS) or [15][T] (SoA) f32, in
+    static constexpr int OFF_DAMP = OFF_ACT + NJ * T * 4;      // [T] f32, in
+    static constexpr int OFF_SC = OFF_DAMP + T * 4;            // [T] i32, in/out
+    static constexpr int OFF_REWARD = OFF_SC + T * 4;          // [T] f32, out
+    static constexpr int OFF_CMASK = OFF_REWARD + T * 4;       // [T] u8, in
+    static constexpr int OFF_TERM = OFF_CMASK + T;             // [T] u8, out
+    static constexpr int OFF_TRUNC = OFF_TERM + T;             // [T] u8, out
+    static constexpr int OFF_NC = OFF_TRUNC + T;               // [T] u8, out
+    static constexpr int OFF_FIN = OFF_NC + T;                 // [T] u8, out (auto-reset)
+    static constexpr int OFF_EPISODE = OFF_FIN + T;            // [T] u32, in (in-kernel noise / auto-reset: Philox counter word)
+    static constexpr int OFF_EPRET = OFF_EPISODE + T * 4;      // [T] f64, in/out  (full tracking only: the last three arrays
+    static constexpr int OFF_EPST0 = OFF_EPRET + T * 8;        // [T] u32, in/out   exist in the stages of the TRACK == 1
+    static constexpr int OFF_EPST1 = OFF_EPST0 + T * 4;        // [T] u32, in/out   instantiations only)
+    // every stage starts 128-byte aligned; without full tracking a stage ends after the episode words
+    __host__ __device__ static constexpr int stage_bytes(int track) {
+        return ((track == 1 ? OFF_EPST1 + T * 4 : OFF_EPRET) + 127) / 128 * 128;
+    }
+    static_assert(OFF_OV % 128 == 0 && OFF_OP64 % 128 == 0 && OFF_ACT % 128 == 0, "tensor-map box destinations");
+    static_assert(OFF_THR % 16 == 0 && OFF_DAMP % 16 == 0 && OFF_SC % 16 == 0 && OFF_REWARD % 16 == 0 && OFF_CMASK % 16 == 0 &&
+                  OFF_TERM % 16 == 0 && OFF_TRUNC % 16 == 0 && OFF_NC % 16 == 0 && OFF_EPRET % 16 == 0 && OFF_EPST0 % 16 == 0 &&
+                  OFF_EPST1 % 16 == 0 && OFF_FIN % 16 == 0 && OFF_EPISODE % 16 == 0, "1-D bulk copy destinations");
+};
 
 struct StepMaps {             // tensor maps live in kernel parameter space (__grid_constant__)
     CUtensorMap obs_jpjv;     // obs [45, ld] f32, box {128, 30}
@@ -113,150 +120,16 @@ __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.a
 // columns, and sub-states made by dexsim_step_host start at multiples of 1,024 envs of the parent, so
 // round_up(offset + n, 32) <= parent ld.  (Bounding by `ld - base` instead is wrong for sub-states, whose `ld`
 // is the PARENT's row pitch.)
+template <int T>
 __device__ __forceinline__ uint32_t tile_cols(int64_t n, int64_t base) {
     const int64_t left = n - base;
-    return left >= TILE ? (uint32_t)TILE : (uint32_t)((left + 31) & ~(int64_t)31);
+    return left >= T ? (uint32_t)T : (uint32_t)((left + 31) & ~(int64_t)31);
 }
 
-// ---- warp-cooperative episode reset (experiment, built only with -DDEXSIM_RESET_COOP) -------------------------
-// Episodes end at scattered times, so a warp typically has one or two lanes that must reset while the other thirty
-// wait (ncu, round 1: finish_and_reset ran with 1-2 active lanes, ~8 % of the executed instructions in a quiet phase).
-// This variant flattens the (resetting env, Philox block) pairs of a warp into work items spread over its 32 lanes:
-// one lane draws ONE block for ONE env and writes the results where they belong -- joints into the stage, position /
-// parameters to their rows -- so m resetting lanes cost ceil(5 m / 32) block evaluations of warp time instead of 5.
-// Bit-identical to reset_draws() + env_reset() (all GPU parity tests pass with it), but MEASURED SLOWER than the
-// owner-lane form on B200 at every reset rate (1 Mi envs, dynamic tiles, us per step, owner-lane vs cooperative):
-// 0.45 % resets per env-step 69.4 vs 70.6 (counts) and 77.4 vs 79.9 (full tracking); 6.8 % resets per env-step 99.2 vs
-// 104.1 and 119.7 vs 131.9 -- the shuffles, the rank search and the read-back of the new state through shared memory
-// cost more than the serialised Philox blocks they save.  The product therefore resets on the owning lane.
-//   rm: ballot of resetting lanes; episode / g: each lane's NEW episode index and group.  A resetting lane publishes
-//   (lane, group, episode) in a per-warp slot indexed by its rank among the resetting lanes; work items read their env from there.
-//   keep-position mode (p.respawn == 0): the owner has stored (double)(float)position into the stage before the call.
-//   Phase A: (env, Philox block) items -> joints into the stage, position / parameters to their rows.
-//   Phase B: (env, finger) items -> contact bits (finger_contact), contact rows, the mask assembled with one ballot.
-#ifdef DEXSIM_RESET_COOP
-__device__ __forceinline__ void warp_reset_draws(const unsigned rm, const bool do_reset, const int lane, const int wcol0,
-                                                 const int64_t base, unsigned char* sp, const DexsimState& st,
-                                                 const DexsimParams& p, const DexsimGroup* __restrict__ groups,
-                                                 const uint32_t episode, const int g, const bool any_ranged,
-                                                 float* host_rows) {
-    float* s_jpjv = reinterpret_cast<float*>(sp + OFF_JPJV);
-    double* s_op = reinterpret_cast<double*>(sp + OFF_OP64);
-    double* s_thr = reinterpret_cast<double*>(sp + OFF_THR);
-    int* s_sc = reinterpret_cast<int*>(sp + OFF_SC);
-    uint8_t* s_cmask = reinterpret_cast<uint8_t*>(sp + OFF_CMASK);
-    unsigned long long* wslot = reinterpret_cast<unsigned long long*>(sp + OFF_WSLOT) + wcol0;
-    float* __restrict__ obs = st.obs;
-    const int64_t ld = st.ld;
-    const int m = __popc(rm);
-    if (do_reset)
-        wslot[__popc(rm & ((1u << lane) - 1u))] = (unsigned long long)episode | ((unsigned long long)(unsigned)g << 32) |
-                                                  ((unsigned long long)(unsigned)lane << 48);
-    __syncwarp();
-    const int nb = any_ranged ? 7 : 5;
-    const int items = m * nb;
-    for (int t0 = 0; t0 < items; t0 += 32) {
-        const int t = t0 + lane;
-        if (t >= items) continue;
-        const int r = any_ranged ? t / 7 : t / 5;
-        const int b = t - r * nb;
-        const unsigned long long slot = wslot[r];
-        const uint32_t ep = (uint32_t)slot;
-        const int gi = (int)((slot >> 32) & 0xFFFFu);
-        const int c = wcol0 + (int)(slot >> 48);
-        const int64_t i = base + c;
-        const uint32_t gid = (uint32_t)(p.env_gid0 + i);
-        const DexsimGroup& grp = groups[gi];
-        if (b < 4) {                                                  // joints 4b .. 4b+3 (reset_draws blocks 0-3)
-            const U4 o = rng_block(p.seed, gid, ep, 0u, STREAM_RESET, (uint32_t)b);
-            const uint32_t w[4] = {o.x, o.y, o.z, o.w};
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                const int j = 4 * b + k;
-                if (j < NJ) {
-                    s_jpjv[j * TILE + c] = (float)__dadd_rn(-0.1, __dmul_rn(0.2, (double)u24(w[k])));
-                    s_jpjv[(NJ + j) * TILE + c] = 0.0f;
-                }
-            }
-        } else if (b == 4) {                                          // spawn position (block 4) + the rows a reset zeroes
-            double np3[3];
-            if (p.respawn) {
-                const U4 o = rng_block(p.seed, gid, ep, 0u, STREAM_RESET, 4u);
-                const uint32_t w[3] = {o.x, o.y, o.z};
-#pragma unroll
-                for (int k = 0; k < 3; ++k)
-                    np3[k] = (double)(float)lerp_rn(grp.spawn_lo[k], grp.spawn_hi[k], __dmul_rn((double)w[k], 0x1p-32));
-            } else {
-#pragma unroll
-                for (int k = 0; k < 3; ++k) np3[k] = s_op[k * TILE + c];
-            }
-#pragma unroll
-            for (int k = 0; k < 3; ++k) {
-                s_op[k * TILE + c] = np3[k];
-                st.op64[k * ld + i] = np3[k];
-                obs[(DEXSIM_ROW_OP + k) * ld + i] = (float)np3[k];
-                obs[(DEXSIM_ROW_OV + k) * ld + i] = 0.0f;
-                if (host_rows && k < 2) {
-                    host_rows[(DEXSIM_ROW_OP + k) * ld + i] = (float)np3[k];
-                    host_rows[(DEXSIM_ROW_OV + k) * ld + i] = 0.0f;
-                }
-            }
-            s_sc[c] = 0;
-            if (!any_ranged) {                                        // fixed curricula: the group's constants
-                st.size[i] = grp.size; st.mass[i] = grp.mass; st.friction[i] = grp.friction;
-                const double thr = __dmul_rn(grp.size, 1.5);
-                st.thr[i] = thr; s_thr[c] = thr;
-                st.damp[i] = (float)__dsub_rn(1.0, __dmul_rn(__dmul_rn(grp.friction, 0.1), 0.01));
-            }
-        } else if (b == 5) {                                          // size, mass (block 5)
-            double size = grp.size, mass = grp.mass;
-            if (grp.size_ranged | grp.mass_ranged) {
-                const U4 o = rng_block(p.seed, gid, ep, 0u, STREAM_RESET, 5u);
-                if (grp.size_ranged) size = lerp_rn(grp.size_lo, grp.size_hi, u53(o.x, o.y));
-                if (grp.mass_ranged) mass = lerp_rn(grp.mass_lo, grp.mass_hi, u53(o.z, o.w));
-            }
-            st.size[i] = size; st.mass[i] = mass;
-            const double thr = __dmul_rn(size, 1.5);
-            st.thr[i] = thr; s_thr[c] = thr;
-        } else {                                                      // friction (block 6)
-            double friction = grp.friction;
-            if (grp.fric_ranged) {
-                const U4 o = rng_block(p.seed, gid, ep, 0u, STREAM_RESET, 6u);
-                friction = lerp_rn(grp.fric_lo, grp.fric_hi, u53(o.x, o.y));
-            }
-            st.friction[i] = friction;
-            st.damp[i] = (float)__dsub_rn(1.0, __dmul_rn(__dmul_rn(friction, 0.1), 0.01));
-        }
-    }
-    __syncwarp();                                                     // joints / position / threshold of every resetting env are in the stage
-    // Phase B: six envs per round, lane = 5 * (env of the round) + finger
-    const int el = lane / 5, f = lane - 5 * el;
-    for (int r0 = 0; r0 < m; r0 += 6) {
-        const int r = r0 + el;
-        const bool act = lane < 30 && r < m;
-        bool cbit = false;
-        int c = 0;
-        int64_t i = 0;
-        if (act) {
-            c = wcol0 + (int)(wslot[r] >> 48);
-            i = base + c;
-            const double thr = s_thr[c];
-            const double thr2 = __dmul_rn(thr, thr);
-            double sq;
-            cbit = finger_contact(s_jpjv[(3 * f) * TILE + c], s_jpjv[(3 * f + 1) * TILE + c], s_jpjv[(3 * f + 2) * TILE + c],
-                                  s_op[c], s_op[TILE + c], s_op[2 * TILE + c], thr, __dmul_rn(thr2, 1.0 - 0x1p-50),
-                                  __dmul_rn(thr2, 1.0 + 0x1p-50), thr > 0.0, sq);
-            obs[(DEXSIM_ROW_CONTACT + f) * ld + i] = cbit ? 1.0f : 0.0f;
-        }
-        const unsigned bits = __ballot_sync(0xffffffffu, cbit);
-        if (act && f == 0) {
-            const uint8_t cm = (uint8_t)((bits >> (5 * el)) & 31u);
-            st.cmask[i] = cm;
-            s_cmask[c] = cm;                                          // for the owner (EXTRA instantiations rebuild the observation)
-        }
-    }
-}
-#endif
+// (A warp-cooperative episode reset -- the (resetting env, Philox block) pairs of a warp flattened into work items over its
+// 32 lanes -- was built and measured in round 2: bit-identical, but slower than the owner-lane reset at every reset rate
+// (profiles/r02_reset_coop_vs_owner.txt: 69.4 vs 70.6 us at 0.45 % resets per env-step, 99.2 vs 104.1 us at 6.8 %), so
+// the experiment build was dropped; the product resets on the owning lane.)
 
 // DENSE: reward type.  AOS: action layout [n,15].  TRACK: 0 = plain step; 1 = episode tracking (return + history
 // summary per env -> failure labels), auto-reset, counters; 2 = auto-reset and counters only (what a curriculum
@@ -268,11 +141,23 @@ __device__ __forceinline__ void warp_reset_draws(const unsigned rm, const bool d
 // tile is its block index, every further one comes from a global counter.  SMs do not progress at the same rate (ncu,
 // round 2: 125k .. 152k active cycles per SM under the static round-robin, the launch lasting as long as the slowest),
 // and tiles with episode resets take longer than others; with the counter every SM works until the batch is done.
-template <bool DENSE, bool AOS, int TRACK, bool EXTRA, int STAGES>
-__global__ void __launch_bounds__(TMA_THREADS, (STAGES == 2) ? (TILE <= 96 ? 4 : 3) : (STAGES == 1 ? 4 : 2))
+template <bool DENSE, bool AOS, int TRACK, bool EXTRA, int STAGES, int TILE_>
+__global__ void __launch_bounds__(TILE_ + 32, (STAGES == 2) ? (TILE_ <= 96 ? 4 : (TILE_ >= 192 ? 2 : 3)) : (STAGES == 1 ? 4 : 2))
 step_tma_kernel(const DexsimState st, const DexsimParams p, const DexsimGroup* __restrict__ groups,
                 const uint16_t* __restrict__ group_of_env, const DexsimStepIO io,
                 const __grid_constant__ StepMaps maps, const int num_tiles, const int pdl) {
+    // this instantiation's tile width (shadows the namespace-level narrow width) and stage layout
+    constexpr int TILE = TILE_;
+    static_assert(TRACK != 1 || TILE_ <= 128, "the full-tracking arrays only fit the narrow tile's stages");
+    using SL = StageLayout<TILE_>;
+    constexpr int OFF_JPJV = SL::OFF_JPJV, OFF_OV = SL::OFF_OV, OFF_OP64 = SL::OFF_OP64, OFF_THR = SL::OFF_THR, OFF_ACT = SL::OFF_ACT,
+                  OFF_DAMP = SL::OFF_DAMP, OFF_SC = SL::OFF_SC, OFF_REWARD = SL::OFF_REWARD, OFF_CMASK = SL::OFF_CMASK,
+                  OFF_TERM = SL::OFF_TERM, OFF_TRUNC = SL::OFF_TRUNC, OFF_NC = SL::OFF_NC, OFF_FIN = SL::OFF_FIN,
+                  OFF_EPISODE = SL::OFF_EPISODE, OFF_EPRET = SL::OFF_EPRET, OFF_EPST0 = SL::OFF_EPST0, OFF_EPST1 = SL::OFF_EPST1;
+    (void)OFF_EPRET; (void)OFF_EPST0; (void)OFF_EPST1; (void)OFF_ACT;
+    constexpr int STAGE_BYTES = SL::stage_bytes(TRACK);
+    constexpr int TMA_COMPUTE_THREADS = TILE;          // one thread per env of a tile
+    constexpr int TMA_THREADS = TMA_COMPUTE_THREADS + 32;   // + the producer warp
     extern __shared__ __align__(1024) unsigned char smem[];
     unsigned char* stage_base = smem;
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);      // full[S], out_ready[S]
@@ -320,7 +205,7 @@ step_tma_kernel(const DexsimState st, const DexsimParams p, const DexsimGroup* _
             auto issue_stores = [&](int s, int tile) {
                 const int64_t base = (int64_t)tile * TILE;
                 const uint32_t sb = smem_u32(stage_base + (size_t)s * STAGE_BYTES);
-                const uint32_t cols = tile_cols(n, base);
+                const uint32_t cols = tile_cols<TILE>(n, base);
                 tma_store_2d(&maps.obs_jpjv, (int)base, DEXSIM_ROW_JP, sb + OFF_JPJV);
                 // zero-copy host step: the same 30 joint rows go straight into the caller's mapped host observation
                 // (object z, its velocity and the contact masks follow as three small rows: the compute warps left them in
@@ -372,7 +257,7 @@ step_tma_kernel(const DexsimState st, const DexsimParams p, const DexsimGroup* _
                 s_tile[s] = tile_id;
                 held |= 1u << s;
                 const int64_t base = (int64_t)tile_id * TILE;
-                const uint32_t cols = tile_cols(n, base);
+                const uint32_t cols = tile_cols<TILE>(n, base);
                 const bool full_tile = (n - base) >= TILE;
                 uint32_t tx = (30 + 3) * TILE * 4 + 3 * TILE * 8 + cols * (8 + 4 + 4 + 1);
                 if (AOS) tx += full_tile ? NJ * TILE * 4 : 0;
@@ -417,9 +302,6 @@ step_tma_kernel(const DexsimState st, const DexsimParams p, const DexsimGroup* _
     } else {
         // ===== compute warps: lane == column of the tile =====
         const int col = tid;
-        const int lane = tid & 31;
-        const int wcol0 = col - lane;
-        (void)wcol0; (void)lane;        // used by the -DDEXSIM_RESET_COOP experiment build only
         for (int k = 0;; ++k) {
             const int s = k % STAGES;
             unsigned char* sp = stage_base + (size_t)s * STAGE_BYTES;
@@ -432,7 +314,7 @@ step_tma_kernel(const DexsimState st, const DexsimParams p, const DexsimGroup* _
             double* s_op = reinterpret_cast<double*>(sp + OFF_OP64);
             float* __restrict__ obs = st.obs;
             const bool valid = i < n;
-            bool do_reset = false, lane_reset = false;
+            bool lane_reset = false;
             bool fused_dyn = false, fused_obs = false;
             uint32_t episode = 0u;
             int g = 0;
@@ -518,7 +400,7 @@ step_tma_kernel(const DexsimState st, const DexsimParams p, const DexsimGroup* _
                     }
                     const bool done = r.terminated || r.truncated || (p.loop_max_steps > 0 && e.sc >= p.loop_max_steps);
                     if (p.auto_reset && done) {
-                        // episode end on the owning lane (counters, labels); the reset draws are shared by the warp below
+                        // episode end on the owning lane (counters, labels)
                         g = group_of_env ? (int)group_of_env[i] : (int)((uint32_t)gid % (uint32_t)p.num_groups);
                         episode = reinterpret_cast<const uint32_t*>(sp + OFF_EPISODE)[col];     // load_episode is on with auto-reset
                         unsigned long long* cnt = nullptr;
@@ -527,7 +409,6 @@ step_tma_kernel(const DexsimState st, const DexsimParams p, const DexsimGroup* _
                             cnt = (staged_cnt ? sh_cnt : reinterpret_cast<unsigned long long*>(io.counters)) + (int64_t)g * DEXSIM_NCOUNTERS;
                             if (io.ret_sums) rs = (staged_cnt ? sh_rs : io.ret_sums) + 2 * g;
                         }
-#ifndef DEXSIM_RESET_COOP
                         // the owning lane draws all of its env's Philox blocks (reset_draws + env_reset, dexsim_core.cuh)
                         {
                             double size, mass, friction;
@@ -538,28 +419,15 @@ step_tma_kernel(const DexsimState st, const DexsimParams p, const DexsimGroup* _
                             st.thr[i] = e.thr; st.damp[i] = e.damp;
                             lane_reset = true;
                         }
-#else
-                        do_reset = true;
-                        finish_episode(e, p, (uint32_t)gid, episode, ep_return, es, r.terminated, r.n_c, cnt, rs, nullptr,
-                                       /*classify=*/TRACK == 1);
-                        episode += 1u;
-                        st.episode[i] = episode;
-                        ep_return = 0.0;
-                        es.w0 = 0u; es.w1 = 0u;
-                        if (!p.respawn) {           // reused env object: position re-cast to float32 (envs/manipulation_env.py:160-161)
-#pragma unroll
-                            for (int c = 0; c < 3; ++c) s_op[c * TILE + col] = (double)(float)e.op[c];
-                        }
-#endif
                     }
                     if (TRACK == 1) {
                         reinterpret_cast<double*>(sp + OFF_EPRET)[col] = ep_return;
                         reinterpret_cast<uint32_t*>(sp + OFF_EPST0)[col] = es.w0;
                         reinterpret_cast<uint32_t*>(sp + OFF_EPST1)[col] = es.w1;
                     }
-                    (sp + OFF_FIN)[col] = (do_reset || lane_reset) ? 1 : 0;
+                    (sp + OFF_FIN)[col] = lane_reset ? 1 : 0;
                 }
-                if (!do_reset) {
+                {
                     // always-changing state goes back through the stage (one bulk store per tile)
 #pragma unroll
                     for (int j = 0; j < NJ; ++j) { s_jpjv[j * TILE + col] = e.jp[j]; s_jpjv[(NJ + j) * TILE + col] = e.jv[j]; }
@@ -596,31 +464,6 @@ step_tma_kernel(const DexsimState st, const DexsimParams p, const DexsimGroup* _
                     }
                 }
             }
-#ifdef DEXSIM_RESET_COOP
-            if (TRACK) {
-                // warp-uniform from here: every lane of the warp takes part in its resetting lanes' draws
-                __syncwarp();
-                const unsigned rm = __ballot_sync(0xffffffffu, do_reset);
-                if (rm) {
-                    // does a resetting env's group randomise size / mass / friction?  (then Philox blocks 5 and 6 are drawn too)
-                    bool ranged = false;
-                    if (do_reset) ranged = (groups[g].size_ranged | groups[g].mass_ranged | groups[g].fric_ranged) != 0;
-                    const bool any_ranged = __any_sync(0xffffffffu, ranged);
-                    warp_reset_draws(rm, do_reset, lane, wcol0, base, sp, st, p, groups, episode, g, any_ranged, io.host_static_rows);
-                    if (EXTRA) {
-                        __syncwarp();                   // the new state of MY env was written by other lanes
-                        if (do_reset) {                 // rebuild the registers the noisy observation is made from
-#pragma unroll
-                            for (int j = 0; j < NJ; ++j) { e.jp[j] = s_jpjv[j * TILE + col]; e.jv[j] = 0.0f; }
-#pragma unroll
-                            for (int c = 0; c < 3; ++c) { e.op[c] = s_op[c * TILE + col]; e.ov[c] = 0.0f; }
-                            e.sc = 0;
-                            e.cmask = (sp + OFF_CMASK)[col];
-                        }
-                    }
-                }
-            }
-#endif
             if (EXTRA && valid && io.noisy_obs) {
                 // evaluation/robustness_tests.py:204-205: all 45 entries of the observation AFTER the step (and after a
                 // possible auto-reset), rows written straight from registers
@@ -682,14 +525,14 @@ static EncodeTiledFn get_encode_fn() {
     return fn;
 }
 
-// 2-D row-major [rows, n] view with row pitch ld elements; box = {TILE columns, box_rows rows}.
+// 2-D row-major [rows, n] view with row pitch ld elements; box = {tile columns, box_rows rows}.
 static bool make_map_2d(CUtensorMap* m, CUtensorMapDataType dt, size_t elem, void* base, int64_t n, int64_t ld,
-                        int rows, int box_rows) {
+                        int rows, int box_rows, int tile) {
     EncodeTiledFn enc = get_encode_fn();
     if (!enc) return false;
     const cuuint64_t dims[2] = {(cuuint64_t)n, (cuuint64_t)rows};
     const cuuint64_t strides[1] = {(cuuint64_t)ld * elem};
-    const cuuint32_t box[2] = {(cuuint32_t)TILE, (cuuint32_t)box_rows};
+    const cuuint32_t box[2] = {(cuuint32_t)tile, (cuuint32_t)box_rows};
     const cuuint32_t estr[2] = {1, 1};
     return enc(m, dt, 2, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
                CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;

@@ -213,6 +213,10 @@ int         dexsim_device_info(int* sm_count, int* step_ctas_per_sm, int* rollou
  * returns DEXSIM_E_PARAM when a call is not eligible).  Both produce identical results; the switch
  * exists for tests and profiling.  Process-wide. */
 int         dexsim_set_step_impl(int impl);
+/* Tile width of the TMA pipeline: 0 = auto (by batch size), 1 = narrow tiles only (128 envs, 3 CTAs x 4 compute warps per
+ * SM), 2 = wide tiles (224 envs, 2 CTAs x 7 compute warps per SM) wherever that instantiation exists (every step without
+ * full per-env episode tracking).  Identical results; for tests and profiling.  Process-wide. */
+int         dexsim_set_step_tile(int tile);
 /* Which fused-rollout kernel dexsim_rollout uses: 0 = auto (the 5-lanes-per-env kernel for small batches with an
  * in-kernel policy and no dynamics noise, else one thread per env), 1 = one thread per env, 2 = 5 lanes per env
  * whenever eligible.  Identical results; for tests and profiling.  Process-wide. */

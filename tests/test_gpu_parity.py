@@ -110,19 +110,19 @@ def test_noise_wrapper_golden(dx, golden_dir):
         np.testing.assert_allclose(rew.cpu().numpy(), g["reward"][:, t], rtol=REWARD_RTOL, atol=REWARD_ATOL)
 
 
-def test_noise_wrapper_golden_on_the_tma_pipeline(dx, golden_dir):
+@pytest.mark.parametrize("kernel,reps", [("tma", 32), ("tma_wide", 48)])
+def test_noise_wrapper_golden_on_the_tma_pipeline(dx, golden_dir, kernel, reps):
     """The same golden (CombinedNoiseWrapper with its own normal draws replayed, evaluation/robustness_tests.py:177-207)
-    served by the TMA/mbarrier step kernel: the six golden envs are tiled to 192 so that the batch is pipeline-sized,
-    and the register-resident kernel is switched off for the test."""
+    served by the TMA/mbarrier step kernel: the six golden envs are tiled to 192 (288 for the 224-env tile: one full
+    and one ragged tile) so that the batch is pipeline-sized, and the register-resident kernel is switched off for the test."""
     from dexterous_rl_manipulation_b200 import _lib
     g = _load(golden_dir, "noise.npz")
-    reps = 32
     n0, T = g["actions"].shape[:2]
     n = n0 * reps
     tile = lambda a: np.concatenate([a] * reps, axis=0)
     env = _make_env(dx, n, True, int(g["max_steps"]))
     obs0, _ = env.reset_from_draws(tile(g["jp0"]), tile(g["size"]), tile(g["mass"]), tile(g["friction"]), tile(g["pos"]))
-    _lib.set_step_impl("tma")
+    _set_step_kernel(kernel)
     try:
         for t in range(T):
             obs, rew, te, tr, info = env.step(torch.from_numpy(tile(g["actions"][:, t])).cuda(),
@@ -133,7 +133,7 @@ def test_noise_wrapper_golden_on_the_tma_pipeline(dx, golden_dir):
             assert np.array_equal(info["num_contacts"].cpu().numpy(), tile(g["num_contacts"][:, t]))
             np.testing.assert_allclose(rew.cpu().numpy(), tile(g["reward"][:, t]), rtol=REWARD_RTOL, atol=REWARD_ATOL)
     finally:
-        _lib.set_step_impl("auto")
+        _set_step_kernel("auto")
 
 
 def _random_draws(rng, n, ragged=True):
@@ -148,6 +148,14 @@ def _random_draws(rng, n, ragged=True):
     return jp0, size, mass, fric, pos
 
 
+def _set_step_kernel(impl):
+    """'auto' | 'register' | 'tma' (narrow 128-env tiles) | 'tma_wide' (224-env tiles where that instantiation exists; full
+    tracking always runs on the narrow tile)."""
+    from dexterous_rl_manipulation_b200 import _lib
+    _lib.set_step_impl("tma" if impl == "tma_wide" else impl)
+    _lib.set_step_tile("wide" if impl == "tma_wide" else "narrow" if impl == "tma" else "auto")
+
+
 @pytest.fixture
 def step_impl():
     """Pin dexsim_step to one of its two kernels for a test (the auto choice goes by batch size: small batches take
@@ -155,15 +163,20 @@ def step_impl():
     from dexterous_rl_manipulation_b200 import _lib
 
     def choose(impl):
-        _lib.set_step_impl(impl)
+        # "tma_wide": the pipeline with its 224-env tiles (2 CTAs x 7 compute warps per SM) wherever that instantiation exists
+        _lib.set_step_impl("tma" if impl == "tma_wide" else impl)
+        _lib.set_step_tile("wide" if impl == "tma_wide" else "narrow" if impl == "tma" else "auto")
     yield choose
     _lib.set_step_impl("auto")
+    _lib.set_step_tile("auto")
 
 
 @pytest.mark.parametrize("n,dense,comps,impl", [(1, True, True, "auto"), (33, False, True, "auto"), (1000, True, True, "register"),
                                                 (1000, True, True, "tma"), (4096, True, True, "tma"), (1000, True, False, "tma"),
                                                 (4096, False, False, "tma"), (4096, False, False, "register"),
-                                                (20000, True, False, "tma"), (20000, True, False, "auto")])
+                                                (20000, True, False, "tma"), (20000, True, False, "auto"),
+                                                (1000, True, True, "tma_wide"), (224 * 19 + 3, False, False, "tma_wide"),
+                                                (20000, True, False, "tma_wide")])
 def test_step_matches_oracle(dx, n, dense, comps, impl, step_impl):
     """Ragged batch sizes (1, 33, 1000 are not multiples of the warp / CTA size) vs the oracle, through both step
     kernels (with and without the reward-component outputs)."""
@@ -243,7 +256,7 @@ def test_fused_rollout_matches_oracle(dx, policy, dense, respawn, n):
     np.testing.assert_allclose(env._ep_return[:n].cpu().numpy(), ob.env["ep_return"], rtol=1e-12, atol=1e-12)
 
 
-@pytest.mark.parametrize("impl", ["register", "tma"])
+@pytest.mark.parametrize("impl", ["register", "tma", "tma_wide"])
 def test_step_autoreset_equals_fused_rollout(dx, impl, step_impl):
     """Stepping with the exposed Philox actions + in-kernel auto-reset == the fused rollout kernel."""
     step_impl(impl)
@@ -268,7 +281,7 @@ def test_step_autoreset_equals_fused_rollout(dx, impl, step_impl):
     torch.testing.assert_close(a.ret_sums, b.ret_sums, rtol=1e-9, atol=0)
 
 
-@pytest.mark.parametrize("impl", ["register", "tma"])
+@pytest.mark.parametrize("impl", ["register", "tma", "tma_wide"])
 def test_noisy_step_equals_noisy_fused_rollout(dx, impl, step_impl):
     """Dynamics-noise cells (per-group sigma): API stepping with in-kernel noise == the fused rollout kernel's noise --
     two independent code paths drawing from the same Philox stream keyed by (env, episode, step)."""
@@ -459,7 +472,7 @@ def test_tma_pipeline_equals_register_kernel(dx, n, track, dense):
         kw.update(auto_reset=True, respawn=True, loop_max_steps=25, track_episodes=track != "counts")
     envs = {}
     try:
-        for impl in ("register", "tma"):
+        for impl in ("register", "tma", "tma_wide"):
             env = dx.BatchedManipulationEnv(n, "cuda", **kw)
             env.reset(seed=3)
             envs[impl] = env
@@ -469,20 +482,20 @@ def test_tma_pipeline_equals_register_kernel(dx, n, track, dense):
             a = torch.rand(n, 15, device="cuda", generator=gen) * 2.6 - 1.3
             outs = {}
             for impl, env in envs.items():
-                _lib.set_step_impl(impl)
+                _set_step_kernel(impl)
                 if t % 2:
                     soa[:, :n] = a.t()
                     o = env._step_soa(soa)
                 else:
                     o = env.step(a)
                 outs[impl] = [x.clone() for x in o[:4]] + [o[4]["num_contacts"].clone()]
-            for x, y in zip(outs["register"], outs["tma"]):
-                assert torch.equal(x, y), t
-        a, b = envs["register"], envs["tma"]
+            for x, y, z in zip(outs["register"], outs["tma"], outs["tma_wide"]):
+                assert torch.equal(x, y) and torch.equal(x, z), t
+        a, b, w = envs["register"], envs["tma"], envs["tma_wide"]
         for name in ("_obs", "_op64", "_thr", "_damp", "_step_count", "_cmask", "_size", "_mass", "_friction", "_episode"):
-            assert torch.equal(getattr(a, name), getattr(b, name)), name
+            assert torch.equal(getattr(a, name), getattr(b, name)) and torch.equal(getattr(a, name), getattr(w, name)), name
         if track:
-            assert torch.equal(a.counters, b.counters) and int(a.counters[:, 0].sum()) > 0
+            assert torch.equal(a.counters, b.counters) and torch.equal(a.counters, w.counters) and int(a.counters[:, 0].sum()) > 0
         if track == "counts":
             # same trajectories as full tracking: episodes / successes / lengths agree, labels and returns stay empty
             full = dx.BatchedManipulationEnv(n, "cuda", **dict(kw, track_episodes=True))
@@ -501,7 +514,7 @@ def test_tma_pipeline_equals_register_kernel(dx, n, track, dense):
             assert torch.equal(a._ep_stats, b._ep_stats) and torch.equal(a._ep_return, b._ep_return)
             torch.testing.assert_close(a.ret_sums, b.ret_sums, rtol=1e-9, atol=0)
     finally:
-        _lib.set_step_impl("auto")
+        _set_step_kernel("auto")
 
 
 @pytest.mark.parametrize("n,track,ranged,respawn,predrawn", [(4096 + 77, False, False, True, False), (1000, True, False, True, False),
@@ -522,7 +535,7 @@ def test_tma_pipeline_noise_and_components_equal_register_kernel(dx, n, track, r
         kw.update(auto_reset=True, respawn=respawn, loop_max_steps=20, track_episodes=track != "counts")
     envs = {}
     try:
-        for impl in ("register", "tma"):
+        for impl in ("register", "tma", "tma_wide"):
             env = dx.BatchedManipulationEnv(n, "cuda", **kw)
             env.reset(seed=11)
             envs[impl] = env
@@ -535,25 +548,25 @@ def test_tma_pipeline_noise_and_components_equal_register_kernel(dx, n, track, r
                              obs_noise=torch.randn(n, 45, device="cuda", generator=gen) * 0.05)
             outs = {}
             for impl, env in envs.items():
-                _lib.set_step_impl(impl)
+                _set_step_kernel(impl)
                 o = env.step(a, **extra)
                 rc = o[4]["reward_components"]
                 outs[impl] = [x.clone() for x in o[:4]] + [o[4]["num_contacts"].clone()] + [rc[k].clone() for k in ("distance", "contact", "closure", "stability")]
-            for x, y in zip(outs["register"], outs["tma"]):
-                assert torch.equal(x, y), t
-        a, b = envs["register"], envs["tma"]
+            for x, y, z in zip(outs["register"], outs["tma"], outs["tma_wide"]):
+                assert torch.equal(x, y) and torch.equal(x, z), t
+        a, b, w = envs["register"], envs["tma"], envs["tma_wide"]
         for name in ("_obs", "_op64", "_thr", "_damp", "_step_count", "_cmask", "_size", "_mass", "_friction", "_episode", "_noisy_obs"):
-            assert torch.equal(getattr(a, name), getattr(b, name)), name
+            assert torch.equal(getattr(a, name), getattr(b, name)) and torch.equal(getattr(a, name), getattr(w, name)), name
         if track:
-            assert torch.equal(a.counters, b.counters) and int(a.counters[:, 0].sum()) > n
+            assert torch.equal(a.counters, b.counters) and torch.equal(a.counters, w.counters) and int(a.counters[:, 0].sum()) > n
         if track is True:
             assert torch.equal(a._ep_stats, b._ep_stats) and torch.equal(a._ep_return, b._ep_return)
     finally:
-        _lib.set_step_impl("auto")
+        _set_step_kernel("auto")
 
 
 @pytest.mark.parametrize("n,track", [(1000, False), (4096 + 5, True)])
-@pytest.mark.parametrize("impl", ["register", "tma"])
+@pytest.mark.parametrize("impl", ["register", "tma", "tma_wide"])
 def test_in_kernel_noise_equals_separate_noise_kernels(dx, n, track, impl, step_impl):
     """DexsimStepIO.sigma_dyn / sigma_obs (Philox normals drawn inside the step kernel) give exactly what the
     separate dexsim_fill_normal launches + add give: same streams, same counters, also across auto-resets."""
@@ -582,7 +595,7 @@ def test_in_kernel_noise_equals_separate_noise_kernels(dx, n, track, impl, step_
         assert torch.equal(a.counters, b.counters) and int(a.counters[:, 0].sum()) > n
 
 
-@pytest.mark.parametrize("impl", ["register", "tma"])
+@pytest.mark.parametrize("impl", ["register", "tma", "tma_wide"])
 def test_group_noise_cells_in_step(dx, impl, step_impl):
     """Noise cells as groups of one batch (group_sigma_*), stepped through the API with external actions: every
     env behaves like the same env of a batch whose env-level noise is its group's value."""
@@ -685,6 +698,35 @@ def test_maximum_size_batch(dx):
             del env
     finally:
         _lib.set_step_impl("auto")
+
+
+@pytest.mark.parametrize("n,chunks", [(40_000 + 77, None), (70_000, 4)])
+def test_step_host_on_the_wide_tile(dx, n, chunks):
+    """Host transports (zero-copy: the kernel's own bulk stores into the pinned buffers; copy: chunked sub-batches) with the
+    224-env tile forced, against the device API stepping a twin env on the 128-env tile."""
+    from dexterous_rl_manipulation_b200 import _lib
+    CC = dx.CurriculumConfig
+    kw = dict(max_episode_steps=20, reward_type="dense", seed=8, groups=[CC.easy(), CC.hard()],
+              auto_reset=True, respawn=True, loop_max_steps=20, track_episodes=False)
+    a_env = dx.BatchedManipulationEnv(n, "cuda", **kw)
+    b_env = dx.BatchedManipulationEnv(n, "cuda", **kw)
+    a_env.reset(seed=8); b_env.reset(seed=8)
+    rng = np.random.default_rng(1)
+    try:
+        for t in range(45):
+            act = rng.uniform(-1.2, 1.2, (n, 15)).astype(np.float32)
+            _set_step_kernel("tma")
+            o1, r1, te1, tr1, i1 = a_env.step(torch.from_numpy(act).cuda())
+            _set_step_kernel("auto")
+            _lib.set_step_tile("wide")
+            o2, r2, te2, tr2, i2 = b_env.step_host(torch.from_numpy(act).pin_memory(), chunks=chunks)
+            assert torch.equal(o1.cpu(), o2) and torch.equal(r1.cpu(), r2), t
+            assert torch.equal(te1.cpu(), te2) and torch.equal(tr1.cpu(), tr2)
+            assert torch.equal(i1["num_contacts"].cpu(), i2["num_contacts"])
+        assert torch.equal(a_env._obs, b_env._obs) and torch.equal(a_env._op64, b_env._op64)
+        assert torch.equal(a_env.counters, b_env.counters) and int(a_env.counters[:, 0].sum()) > n
+    finally:
+        _set_step_kernel("auto")
 
 
 @pytest.mark.parametrize("n,chunks,track", [(5000, 3, True), (4096, 1, False), (70_000, 8, True), (100, 1, True)])
@@ -1222,17 +1264,19 @@ def test_no_out_of_bounds_writes_counts_and_noise_paths(dx, n):
     check = _with_guard_bands(env)
     env.reset(seed=2)
     try:
-        for impl in ("tma", "register"):
-            _lib.set_step_impl(impl)
+        for impl in ("tma", "tma_wide", "register"):
+            _set_step_kernel(impl)
             for t in range(25):
                 env.step(torch.rand(n, 15, device="cuda", generator=gen) * 2 - 1)
             check()
-        _lib.set_step_impl("auto")
-        for chunks in (1, 5):
-            env.step_host(torch.rand(n, 15).mul_(2).sub_(1).pin_memory(), chunks=chunks)
-            check()
+        for tile_w in ("auto", "wide"):
+            _set_step_kernel("auto")
+            _lib.set_step_tile(tile_w)
+            for chunks in (1, 5):
+                env.step_host(torch.rand(n, 15).mul_(2).sub_(1).pin_memory(), chunks=chunks)
+                check()
     finally:
-        _lib.set_step_impl("auto")
+        _set_step_kernel("auto")
     assert int(env.counters[:, 0].sum()) > n
     noisy = dx.BatchedManipulationEnv(n, "cuda", max_episode_steps=10, reward_type="sparse", auto_reset=True, respawn=True,
                                       loop_max_steps=10, track_episodes=True, curriculum_config=CC.medium(), seed=3,
