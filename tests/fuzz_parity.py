@@ -32,6 +32,7 @@ def fuzz_api_steps(case):
     comps = bool(rng.integers(2))
     noisy = bool(rng.integers(3) == 0)                  # pre-drawn dynamics + observation noise (EXTRA instantiations)
     impl = ["auto", "register", "tma"][int(rng.integers(3))] if n >= 128 else "auto"
+    tile = ["auto", "narrow", "wide"][int(rng.integers(3))]      # tile width of the pipelined kernel (224-env tiles from 224 envs up)
     max_steps = int(rng.choice([1, 5, 60, 200]))
     T = int(rng.integers(1, 120 if n < 50000 else 10))
     w = tuple(float(x) for x in rng.uniform(0.0, 3.0, 4)) if dense and rng.integers(2) else None
@@ -47,9 +48,10 @@ def fuzz_api_steps(case):
                                     reward_components=comps, **kw)
     ob = oracle.OracleBatch(n, dense=dense, max_episode_steps=max_steps, **({"weights": w} if w is not None else {}))
     g0, _ = env.reset_from_draws(jp0, size, mass, fric, pos)
-    desc = dict(case=case, mode="api", n=n, dense=dense, comps=comps, max_steps=max_steps, T=T, weights=w, noisy=noisy, impl=impl)
+    desc = dict(case=case, mode="api", n=n, dense=dense, comps=comps, max_steps=max_steps, T=T, weights=w, noisy=noisy, impl=impl, tile=tile)
     assert np.array_equal(g0.cpu().numpy(), ob.reset_predrawn(jp0, size, mass, fric, pos)), ("reset", desc)
     _lib.set_step_impl(impl)
+    _lib.set_step_tile(tile)
     for t in range(T):
         kind = int(rng.integers(5))
         a = (rng.uniform(-1.5, 1.5, (n, 15)) if kind < 2 else rng.normal(0, [0.3, 3.0, 1e3][kind - 2], (n, 15))).astype(np.float32)
@@ -69,6 +71,7 @@ def fuzz_api_steps(case):
             print("MISMATCH", desc, "step", t, flush=True)
             sys.exit(1)
     _lib.set_step_impl("auto")
+    _lib.set_step_tile("auto")
     return T * n
 
 
@@ -82,6 +85,7 @@ def fuzz_api_autoreset(case):
     policy_kind = int(rng.integers(1, 3))
     full = bool(rng.integers(2))
     impl = ["auto", "register", "tma"][int(rng.integers(3))]
+    tile = ["auto", "narrow", "wide"][int(rng.integers(3))]
     max_steps = int(rng.choice([2, 7, 40]))
     loop_max = int(rng.choice([2 * max_steps, max_steps, max(1, max_steps // 2)]))
     K = int(rng.integers(3, 70 if n < 50000 else 14))
@@ -97,15 +101,17 @@ def fuzz_api_autoreset(case):
     G = len(cfgs)
     ob.reset_predrawn(env._obs[:15, :n].t().cpu().numpy(), env._size[:n].cpu().numpy(), env._mass[:n].cpu().numpy(),
                       env._friction[:n].cpu().numpy(), env._obs[30:33, :n].t().cpu().numpy())
-    desc = dict(case=case, mode="api_autoreset", n=n, dense=dense, respawn=respawn, policy=policy_kind, full=full, impl=impl,
+    desc = dict(case=case, mode="api_autoreset", n=n, dense=dense, respawn=respawn, policy=policy_kind, full=full, impl=impl, tile=tile,
                 max_steps=max_steps, loop_max=loop_max, K=K, gid0=gid0, groups=G)
     _lib.set_step_impl(impl)
+    _lib.set_step_tile(tile)
     act = torch.zeros(15, env.ld, device="cuda")
     for _ in range(K):
         _lib.check(env._lib.dexsim_fill_policy_actions(C.byref(env._state), C.byref(env._params), policy_kind, act.data_ptr(),
                                                        env._stream()), "fill")
         env.step(act[:, :n].t().contiguous())
     _lib.set_step_impl("auto")
+    _lib.set_step_tile("auto")
     cnt_o, _ = ob.rollout(groups, K, seed, policy_kind=policy_kind, respawn=respawn, env_gid0=gid0, loop_max_steps=loop_max, threads=8)
     cnt = env.counters.cpu().numpy()
     cols = list(range(16)) + [17] if full else [0, 1, 2, 3, 17]
@@ -140,8 +146,10 @@ def fuzz_host_transport(case):
     a_env.reset(seed=seed); b_env.reset(seed=seed)
     b_env.host_zero_copy = zc
     b_env.host_expand_contacts = bool(rng.integers(4))          # off: all rows downloaded (and no zero-copy)
+    tile = ["auto", "narrow", "wide"][int(rng.integers(3))]
+    _lib.set_step_tile(tile)
     desc = dict(case=case, mode="host", n=n, dense=dense, track=track, max_steps=max_steps, zc=zc, K=K,
-                expand=b_env.host_expand_contacts)
+                expand=b_env.host_expand_contacts, tile=tile)
     pins = [torch.empty(n, 15).pin_memory() for _ in range(2)]
     for t in range(K):
         act = torch.from_numpy(rng.uniform(-1.3, 1.3, (n, 15)).astype(np.float32))
@@ -169,6 +177,7 @@ def fuzz_host_transport(case):
     if not ok:
         print("MISMATCH (final state)", desc, flush=True)
         sys.exit(1)
+    _lib.set_step_tile("auto")
     return K * n
 
 
