@@ -1341,6 +1341,29 @@ static bool upload_stream_choice() {
     return v == 1;
 }
 
+// DEXSIM_HOST_TRACE=1: device-side timeline of every tenth chunked dexsim_step_host call on stderr (experiments): when each
+// chunk's upload, kernel and row download finished, relative to the call's fork point (profiles/r02_host_step_timeline.txt).
+static bool host_trace() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("DEXSIM_HOST_TRACE");
+        v = (e && atoi(e)) ? 1 : 0;
+    }
+    return v == 1;
+}
+struct HostTrace {
+    cudaEvent_t t0, up[32], k[32], down[32], small;
+    bool made = false;
+    void make() {
+        if (made) return;
+        cudaEventCreate(&t0); cudaEventCreate(&small);
+        for (int i = 0; i < 32; ++i) { cudaEventCreate(&up[i]); cudaEventCreate(&k[i]); cudaEventCreate(&down[i]); }
+        made = true;
+    }
+};
+static HostTrace g_trace;
+static int g_trace_calls = 0;
+
 // zero-copy transport: 1 = the step kernel reads the actions from mapped host memory itself (no copy at all),
 // 0 = the copy engine uploads them chunk by chunk
 static bool zc_kernel_upload() {
@@ -1418,6 +1441,8 @@ int dexsim_step_host(const DexsimState* st, const DexsimParams* p, const DexsimG
     auto chunk_hi = [&](int c) -> int64_t { return c == nchunks - 1 ? n : (int64_t)(c + 1) * per; };
     HostPipe* hp = nullptr;
     int dev = 0;
+    const bool tracing = host_trace() && nchunks > 1 && !zc && h_obs && (++g_trace_calls % 10 == 0);
+    if (tracing) g_trace.make();
     // A device's internal streams and events are shared by every caller on that device: enqueue one step at a time
     // per device (callers driving different GPUs from different host threads do not wait for each other).
     std::unique_lock<std::mutex> enqueue_lock;
@@ -1429,6 +1454,7 @@ int dexsim_step_host(const DexsimState* st, const DexsimParams* p, const DexsimG
         enqueue_lock = std::unique_lock<std::mutex>(g_enqueue_mutex[dev & 63]);
         err = cudaEventRecord(hp->fork_ev, user);
         if (err != cudaSuccess) return -(int)err;
+        if (tracing) cudaEventRecord(g_trace.t0, user);
         for (int k = 0; k < HOST_STREAMS && k < nchunks; ++k) {
             err = cudaStreamWaitEvent(hp->streams[k], hp->fork_ev, 0);
             if (err != cudaSuccess) return -(int)err;
@@ -1506,8 +1532,10 @@ int dexsim_step_host(const DexsimState* st, const DexsimParams* p, const DexsimG
             if (err == cudaSuccess) err = cudaStreamWaitEvent(s, hp->up_ev[c], 0);
             if (err != cudaSuccess) return -(int)err;
         }
+        if (tracing) cudaEventRecord(g_trace.up[c], s);
         rc = launch_step(&sub, &sp, groups, group_of_env ? group_of_env + lo : nullptr, &sio, s);
         if (rc) return rc;
+        if (tracing) cudaEventRecord(g_trace.k[c], s);
         if (zc) {                                        // every result is already on its way to the host buffers
             if (nchunks > 1) {
                 err = cudaEventRecord(hp->kdone[c], s);
@@ -1548,6 +1576,7 @@ int dexsim_step_host(const DexsimState* st, const DexsimParams* p, const DexsimG
                                         cudaMemcpyDeviceToHost, s);
             }
             if (err != cudaSuccess) return -(int)err;
+            if (tracing) cudaEventRecord(g_trace.down[c], s);
         }
         if (nchunks == 1) {
             rc = copy_vectors(s, 0, n);
@@ -1564,6 +1593,7 @@ int dexsim_step_host(const DexsimState* st, const DexsimParams* p, const DexsimG
         }
         rc = copy_vectors(hp->small, 0, n);
         if (rc) return rc;
+        if (tracing) cudaEventRecord(g_trace.small, hp->small);
     }
     return 0;
     };
@@ -1602,6 +1632,19 @@ int dexsim_step_host(const DexsimState* st, const DexsimParams* p, const DexsimG
         }
     }
     const int sync_rc = cuda_rc(cudaStreamSynchronize(user));
+    if (tracing && rc == 0 && sync_rc == 0) {
+        fprintf(stderr, "dexsim_step_host trace (us after fork; n %lld, %d chunks):\n", (long long)n, nchunks);
+        for (int c = 0; c < nchunks; ++c) {
+            float a = 0, b = 0, d = 0;
+            cudaEventElapsedTime(&a, g_trace.t0, g_trace.up[c]); cudaEventElapsedTime(&b, g_trace.t0, g_trace.k[c]);
+            cudaEventElapsedTime(&d, g_trace.t0, g_trace.down[c]);
+            fprintf(stderr, "  chunk %2d [%8lld, %8lld): upload done %8.1f  kernel done %8.1f  rows down %8.1f\n", c,
+                    (long long)((int64_t)c * per), (long long)chunk_hi(c), a * 1e3, b * 1e3, d * 1e3);
+        }
+        float v = 0;
+        cudaEventElapsedTime(&v, g_trace.t0, g_trace.small);
+        fprintf(stderr, "  per-env vectors down %8.1f\n", v * 1e3);
+    }
     return rc ? rc : sync_rc;
 }
 
