@@ -1351,18 +1351,21 @@ static bool host_trace() {
     }
     return v == 1;
 }
-struct HostTrace {
-    cudaEvent_t t0, up[32], k[32], down[32], small;
-    bool made = false;
-    void make() {
-        if (made) return;
-        cudaEventCreate(&t0); cudaEventCreate(&small);
-        for (int i = 0; i < 32; ++i) { cudaEventCreate(&up[i]); cudaEventCreate(&k[i]); cudaEventCreate(&down[i]); }
-        made = true;
+struct HostTrace {               // one set of timing events, owned by the first device (and thread) that traces
+    cudaEvent_t t0, up[HOST_MAX_CHUNKS], k[HOST_MAX_CHUNKS], down[HOST_MAX_CHUNKS], small;
+    int dev = -1;
+    bool make(int device) {
+        if (dev >= 0) return dev == device;
+        bool ok = cudaEventCreate(&t0) == cudaSuccess && cudaEventCreate(&small) == cudaSuccess;
+        for (int i = 0; ok && i < HOST_MAX_CHUNKS; ++i)
+            ok = cudaEventCreate(&up[i]) == cudaSuccess && cudaEventCreate(&k[i]) == cudaSuccess && cudaEventCreate(&down[i]) == cudaSuccess;
+        if (!ok) { (void)cudaGetLastError(); return false; }
+        dev = device;
+        return true;
     }
 };
 static HostTrace g_trace;
-static int g_trace_calls = 0;
+static std::atomic<int> g_trace_calls{0};
 
 // zero-copy transport: 1 = the step kernel reads the actions from mapped host memory itself (no copy at all),
 // 0 = the copy engine uploads them chunk by chunk
@@ -1441,8 +1444,12 @@ int dexsim_step_host(const DexsimState* st, const DexsimParams* p, const DexsimG
     auto chunk_hi = [&](int c) -> int64_t { return c == nchunks - 1 ? n : (int64_t)(c + 1) * per; };
     HostPipe* hp = nullptr;
     int dev = 0;
-    const bool tracing = host_trace() && nchunks > 1 && !zc && h_obs && (++g_trace_calls % 10 == 0);
-    if (tracing) g_trace.make();
+    bool tracing = host_trace() && nchunks > 1 && !zc && h_obs && !(flags & DEXSIM_HOST_ASYNC) &&
+                   (g_trace_calls.fetch_add(1, std::memory_order_relaxed) % 10 == 9);
+    if (tracing) {
+        int tdev = -1;
+        tracing = cudaGetDevice(&tdev) == cudaSuccess && g_trace.make(tdev);
+    }
     // A device's internal streams and events are shared by every caller on that device: enqueue one step at a time
     // per device (callers driving different GPUs from different host threads do not wait for each other).
     std::unique_lock<std::mutex> enqueue_lock;
