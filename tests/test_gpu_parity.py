@@ -524,7 +524,7 @@ def test_tma_pipeline_noise_and_components_equal_register_kernel(dx, n, track, r
     """Noise (Philox in-kernel or pre-drawn), reward components and the float64 reward on the TMA pipeline
     (EXTRA instantiations) against the register-resident kernel: every output and every state array bit for bit,
     across auto-resets in both spawn modes and with ranged size / mass / friction groups (Philox blocks 5-6 of the
-    warp-cooperative reset)."""
+    reset draws)."""
     from dexterous_rl_manipulation_b200 import _lib
     CC = dx.CurriculumConfig
     g1 = CC(object_size_range=(0.03, 0.09), object_mass_range=(0.05, 0.3), friction_range=(0.2, 0.9)) if ranged else CC.hard()
