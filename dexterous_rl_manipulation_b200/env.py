@@ -684,13 +684,19 @@ class BatchedManipulationEnv:
     def capture_step(self, action_buffer, steps=1):
         """CUDA-graph the hot path for small batches, where one step is bound by the ~8 us host launch path
         rather than by the GPU: returns ``replay()`` which re-runs ``steps`` env-steps reading the actions
-        from ``action_buffer`` (CUDA float32 [num_envs, 15], or [steps, num_envs, 15]; refill it in place
-        between replays) and returns the same persistent output tensors as ``step()``.
+        from ``action_buffer`` (CUDA float32 [num_envs, 15], or [steps, num_envs, 15], or a sequence of ``steps``
+        [num_envs, 15] tensors, which may repeat; refill them in place between replays) and returns the same persistent
+        output tensors as ``step()``.
         Kernel parameters (seed, reward weights, group count ...) are frozen at capture time; curriculum
         updates still apply because the group table is read from device memory at replay."""
         if self.single or self._noisy_env:
             raise RuntimeError("capture_step() is for batched, noise-free stepping")
-        a = action_buffer.reshape(steps, self.num_envs, 15)
+        if isinstance(action_buffer, (list, tuple)):
+            if len(action_buffer) != steps:
+                raise ValueError("capture_step(): one action tensor per captured step")
+            a = [t.reshape(self.num_envs, 15) for t in action_buffer]
+        else:
+            a = action_buffer.reshape(steps, self.num_envs, 15)
         if self._groups_dirty:
             self._sync_groups()
         side = torch.cuda.Stream(device=self.device)

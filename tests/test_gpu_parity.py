@@ -1059,6 +1059,19 @@ def test_capture_step_graph_replay_equals_eager(dx):
         ob = replay()
         assert torch.equal(oa[0], ob[0]) and torch.equal(oa[1], ob[1]) and torch.equal(oa[2], ob[2])
     assert torch.equal(a._obs, b._obs) and torch.equal(a.counters, b.counters) and int(a.counters[:, 0].sum()) > n
+    # a sequence of action tensors (two buffers, each used twice per replay) instead of one stacked buffer
+    pool = [torch.rand(n, 15, device="cuda") * 2 - 1 for _ in range(2)]
+    replay2 = b.capture_step(pool + pool, steps=4)
+    for it in range(3):
+        for t in pool:
+            t.copy_(torch.rand(n, 15, device="cuda") * 2 - 1)
+        for k in range(4):
+            oa = a.step(pool[k % 2])
+        ob = replay2()
+        assert torch.equal(oa[0], ob[0]) and torch.equal(oa[1], ob[1])
+    assert torch.equal(a._obs, b._obs) and torch.equal(a.counters, b.counters)
+    with pytest.raises(ValueError):
+        b.capture_step(pool, steps=4)
 
 
 def test_heldout_noise_sweep_full_size_properties(dx):
