@@ -46,7 +46,7 @@ doc = {
                "it, walk direction alternating from step to step (profiles/r02_counts_steady_state.csv); "
                "profiles/r02_counts_steady_state_noalt.csv holds the same with one direction"},
     "kernel": "step_tma_kernel<dense, AoS, counts-only, 2 stages> (the bench's main loop)",
-    "report": "profiles/r02_step_tma_kernel_ncu.txt (launch 9 of tools/profile_step.py 1048576 api_counts)",
+    "report": "profiles/r02_step_tma_tile_width_ncu.txt, last block (launch 9 of tools/profile_step.py 1048576 api_counts)",
     "step_kernel_sha256": bi["step_kernel_sha256"],
     "step_kernel_files": ["csrc/dexsim_step_tma.cuh", "csrc/dexsim_core.cuh"],
 }
